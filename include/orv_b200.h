@@ -1,0 +1,277 @@
+/* orv_b200.h — C ABI of liborv_b200.so, the B200 (sm_100a) implementation of ORV's denoising hot path.
+ *
+ * The reference has no FFI on this path: the boundary is the Python class
+ * `CogVideoXTransformer3DModelTraj.forward` (reference orv/models/cogvideox_control.py:715-948) called once per
+ * scheduler step from `CogVideoXImageToVideoPipelineTraj.__call__` (:1402-1473).  This header is what a binding
+ * for that call would bind: plain pointers and sizes, no torch types.  The Python host
+ * (`orv_b200/`) mirrors the reference's module API on top of it through ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - tensors are contiguous row-major; `bf16` = __nv_bfloat16 bits; weights keep torch's nn.Linear layout
+ *     [out_features, in_features];
+ *   - the library never allocates or frees caller tensors: activations live in a caller-provided workspace;
+ *   - kernels are enqueued on the `stream` argument (a cudaStream_t passed as void*), never synchronise, and are
+ *     CUDA-graph capturable;
+ *   - every function returns ORVB_OK (0) or a negative error code; orvb_last_error() returns the thread-local
+ *     message.  No C++ exception crosses this boundary.
+ */
+#ifndef ORV_B200_H_
+#define ORV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORVB_VERSION 100
+
+enum {
+  ORVB_OK = 0,
+  ORVB_EINVAL = -1, /* bad argument (null pointer, unsupported option)            */
+  ORVB_ESHAPE = -2, /* shape / alignment the kernels do not support               */
+  ORVB_ECUDA = -3,  /* a CUDA runtime / driver call failed                        */
+  ORVB_EARCH = -4,  /* the current device is not compute capability 10.x (B200)   */
+  ORVB_ENOMEM = -5  /* caller workspace too small                                 */
+};
+
+int orvb_version(void);
+const char* orvb_last_error(void);
+/* ORVB_OK when the current CUDA device can run the sm_100a kernels. */
+int orvb_check_device(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Granular operators (unit-testable pieces of the path)
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* Epilogue selector of orvb_gemm_bf16. */
+enum {
+  ORVB_EPI_BIAS = 0,      /* out = acc + bias                                                     */
+  ORVB_EPI_GELU = 1,      /* out = gelu_tanh(acc + bias)           (FeedForward net.0, ref a9)    */
+  ORVB_EPI_GATE_RESID = 2,/* out = resid + gate[g(row)] * (acc + bias)   (gated residual, ref a6) */
+  ORVB_EPI_QKV = 3        /* out = acc + bias, then per-head LayerNorm(64) (+RoPE) on the Q and K
+                             thirds of the row (attention processor, ref a8)                      */
+};
+
+/* Row -> modulation-group map of a joint [text | video] sequence (reference LayerNormZero semantics,
+ * cogvideox_control.py:117-145): with s = row % seq_len and b = row / seq_len,
+ *   group(row) = b * groups_per_batch + (s < text_len ? 0 : 1 + (s - text_len) / tokens_per_group).
+ * Group 0 of every batch is the text group.  seq_len == 0 disables the map (group = 0). */
+typedef struct orvb_rowmap {
+  int32_t seq_len;
+  int32_t text_len;
+  int32_t tokens_per_group;
+  int32_t groups_per_batch;
+} orvb_rowmap;
+
+typedef struct orvb_gemm_args {
+  /* out[M,N] = epilogue(A[M,K] @ W[N,K]^T); A row pitch lda, W row pitch ldw (elements). */
+  const void* a;     /* bf16 [M, lda]  */
+  const void* w;     /* bf16 [N, ldw]  */
+  void* out;         /* bf16 [*, ldo]  */
+  const void* bias;  /* bf16 [N] or NULL */
+  int32_t m, n, k;
+  int32_t lda, ldw, ldo;
+  int32_t epilogue;  /* ORVB_EPI_* */
+
+  /* Output-row remap: out_row = (row / src_rows) * dst_rows + dst_offset + row % src_rows.
+   * src_rows == 0 -> identity. Used to scatter per-batch blocks into the joint sequence. */
+  int32_t src_rows, dst_rows, dst_offset;
+
+  /* GATE_RESID: resid may alias out.  resid row = resid_mod > 0 ? (row % resid_mod) + resid_view_stride *
+   * ((row / resid_mod) % resid_views) : out_row (a positional table broadcast over the batch when resid_mod>0).
+   * gate (fp32, row pitch gate_ld) may be NULL (= 1.0).  For a row of group g the gate vector starts at
+   * gate + g * gate_ld + (g % groups_per_batch == 0 ? gate_text_off : gate_video_off). */
+  const void* resid; /* bf16 [*, ldr] */
+  int32_t ldr;
+  int32_t resid_mod, resid_views, resid_view_stride;
+  const float* gate;
+  int32_t gate_ld, gate_text_off, gate_video_off;
+  orvb_rowmap rowmap;
+
+  /* QKV: n == 3 * qk_dim; columns [0, 2*qk_dim) get LayerNorm over each 64-wide head with the q / k affine
+   * parameters (bf16 [64]); rope_cos/sin (fp32 [video_tokens, 64], may be NULL) rotate rows whose position in
+   * the sequence is >= rowmap.text_len (diffusers apply_rotary_emb, interleaved pairs). */
+  int32_t qk_dim;
+  const void* q_norm_w; const void* q_norm_b;
+  const void* k_norm_w; const void* k_norm_b;
+  float qk_eps;
+  const float* rope_cos; const float* rope_sin;
+} orvb_gemm_args;
+
+/* tcgen05 / TMA GEMM.  Requirements: k % 8 == 0, n % 8 == 0, lda/ldw/ldo % 8 == 0, 16-byte aligned bases. */
+int orvb_gemm_bf16(const orvb_gemm_args* args, void* stream);
+
+/* Non-causal multi-head attention over a packed QKV buffer (reference a8: F.scaled_dot_product_attention).
+ * qkv: bf16 [batch * seq_len, 3 * heads * 64] with Q | K | V column blocks; out: bf16 [batch * seq_len, heads*64].
+ * softmax scale = scale (1/sqrt(64) in the reference).  head_dim is fixed at 64 (every shipped config). */
+int orvb_attention_bf16(const void* qkv, void* out, int32_t batch, int32_t seq_len, int32_t heads, float scale,
+                        void* stream);
+
+/* LayerNorm(eps, affine) followed by AdaLN modulation y = LN(x) * (1 + scale_g) + shift_g where g is the row's
+ * group and (shift, scale) come from the fp32 table `mod` (row pitch mod_ld):
+ *   group 0 (text):  shift = mod[g] + text_off,  scale = shift + dim
+ *   video groups:    shift = mod[g] + video_off, scale = shift + dim      (`scale_first` swaps the two)
+ * mod == NULL -> plain LayerNorm.  Output rows may be remapped like the GEMM (src_rows/dst_rows/dst_offset apply
+ * to the OUTPUT row; with in_skip_text != 0 input row r reads x row (r / (seq-text)) * seq + text + r % (seq-text)).
+ * Reference: CogVideoXLayerNormZero / AdaLayerNorm, cogvideox_control.py:41-197. */
+typedef struct orvb_ln_args {
+  const void* x; void* y;       /* bf16 [rows, dim] */
+  const void* ln_w; const void* ln_b; /* bf16 [dim] or NULL */
+  int32_t rows, dim;
+  float eps;
+  const float* mod; int32_t mod_ld, text_off, video_off, scale_first;
+  orvb_rowmap rowmap;
+  int32_t in_video_only;        /* gather only video rows of the joint sequence (norm_final / norm_out) */
+} orvb_ln_args;
+int orvb_ln_modulate(const orvb_ln_args* args, void* stream);
+
+/* y[r, n] = act(sum_k x[r,k] * W[n,k] + b[n]) for a handful of rows (AdaLN tables, time/ofs/action MLPs).
+ * x, y fp32; W, b bf16.  act: 0 none, 1 silu, 2 gelu_tanh.  rows <= 64. */
+int orvb_skinny_linear(const float* x, const void* w, const void* b, float* y, int32_t rows, int32_t n, int32_t k,
+                       int32_t act, void* stream);
+
+/* Patch gather (im2col of CogVideoXPatchEmbed):
+ *   patch_t == 0: out[b, (f,i,j), c*p*p + kh*p + kw]           = x[b, f, c, i*p+kh, j*p+kw]
+ *   patch_t  > 0: out[b, (f',i,j), c*pt*p*p + t*p*p + kh*p + kw] = x[b, f'*pt+t, c, i*p+kh, j*p+kw]
+ * x: bf16 [B, F, C, H, W]; out: bf16 [B * F/pt * H/p * W/p, C*pt*p*p]. */
+int orvb_patchify(const void* x, void* out, int32_t b, int32_t f, int32_t c, int32_t h, int32_t w, int32_t p,
+                  int32_t patch_t, void* stream);
+/* Inverse map for the model output (cogvideox_control.py:926-936).
+ * y: bf16 [B * F/pt * H/p * W/p, C*pt*p*p] -> out: bf16 [B, F, C, H, W]. */
+int orvb_unpatchify(const void* y, void* out, int32_t b, int32_t f, int32_t c, int32_t h, int32_t w, int32_t p,
+                    int32_t patch_t, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Whole-model forward (reference a2: CogVideoXTransformer3DModelTraj.forward)
+ * ------------------------------------------------------------------------------------------------------------ */
+
+typedef struct orvb_config {
+  int32_t dim;              /* num_attention_heads * attention_head_dim                     */
+  int32_t heads;
+  int32_t head_dim;         /* must be 64                                                   */
+  int32_t layers;
+  int32_t ff_dim;           /* 4 * dim                                                      */
+  int32_t time_embed_dim;   /* 512                                                          */
+  int32_t text_embed_dim;   /* 4096                                                         */
+  int32_t in_channels;      /* 32 (latent 16 + image-condition 16)                          */
+  int32_t out_channels;     /* 16                                                           */
+  int32_t patch_size;       /* 2                                                            */
+  int32_t patch_size_t;     /* 0 = None (2B family), 2 for CogVideoX1.5                     */
+  int32_t use_rope;         /* use_rotary_positional_embeddings                             */
+  int32_t has_ofs;          /* ofs_embed_dim is not None                                    */
+  int32_t ofs_embed_dim;
+  int32_t flip_sin_to_cos;
+  float   freq_shift;
+  float   norm_eps;
+  int32_t visual_guidance;  /* initial_combine_linear present                               */
+  int32_t num_control_keys;
+  int32_t multiview;        /* mv_blocks present                                            */
+  int32_t max_n_view;
+  int32_t action_state_dim; /* 7                                                            */
+  int32_t action_compress;  /* 4                                                            */
+  int32_t action_hidden;    /* 4 * time_embed_dim                                           */
+} orvb_config;
+
+/* Borrowed device pointers (bf16), one struct per CogVideoXBlock / MVBlock.  to_q/to_k/to_v are passed FUSED:
+ * qkv_w = cat([to_q.weight, to_k.weight, to_v.weight], 0). */
+typedef struct orvb_block_weights {
+  const void* norm1_lin_w; const void* norm1_lin_b;   /* [6D, T], [6D] */
+  const void* norm1_ln_w;  const void* norm1_ln_b;    /* [D] */
+  const void* qkv_w;       const void* qkv_b;         /* [3D, D], [3D] */
+  const void* q_norm_w;    const void* q_norm_b;      /* [64] */
+  const void* k_norm_w;    const void* k_norm_b;      /* [64] */
+  const void* out_w;       const void* out_b;         /* [D, D], [D] */
+  const void* norm2_lin_w; const void* norm2_lin_b;   /* [6D, T], [6D]  (NULL in MVBlock) */
+  const void* norm2_ln_w;  const void* norm2_ln_b;
+  const void* ff1_w;       const void* ff1_b;         /* [FF, D], [FF] (NULL in MVBlock) */
+  const void* ff2_w;       const void* ff2_b;         /* [D, FF], [D]  (NULL in MVBlock) */
+  const void* proj_out_w;  const void* proj_out_b;    /* MVBlock only: [D, D], [D] */
+} orvb_block_weights;
+
+typedef struct orvb_weights {
+  const void* patch_w;  const void* patch_b;      /* [D, C*pt*p*p] (conv weight flattened), [D] or NULL */
+  const void* text_w;   const void* text_b;       /* [D, text_dim], [D] */
+  const void* pos_embed;                          /* bf16 [views or 1, video_tokens, D] joint sin-cos rows, or NULL */
+  const void* time1_w;  const void* time1_b;      /* [T, D], [T] */
+  const void* time2_w;  const void* time2_b;      /* [T, T], [T] */
+  const void* ofs1_w;   const void* ofs1_b;       /* [T, ofs], [T] or NULL */
+  const void* ofs2_w;   const void* ofs2_b;
+  const void* act1_w;   const void* act1_b;       /* [4T, 28*pt], [4T] */
+  const void* act2_w;   const void* act2_b;       /* [T, 4T], [T] */
+  const void* act_mask_embed;                     /* [T] */
+  const void* combine_w; const void* combine_b;   /* [D, keys*D], [D] or NULL */
+  const void* norm_final_w; const void* norm_final_b; /* [D] */
+  const void* norm_out_lin_w; const void* norm_out_lin_b; /* [2D, T], [2D] */
+  const void* norm_out_ln_w;  const void* norm_out_ln_b;  /* [D] */
+  const void* proj_out_w; const void* proj_out_b; /* [p*p*pt*out_ch, D] */
+  const orvb_block_weights* blocks_host;          /* HOST array [layers] */
+  const orvb_block_weights* mv_blocks_host;       /* HOST array [layers] or NULL */
+} orvb_weights;
+
+typedef struct orvb_model orvb_model;
+
+int orvb_model_create(const orvb_config* cfg, orvb_model** out);
+void orvb_model_destroy(orvb_model* m);
+/* Records the (borrowed) weight pointers; the caller keeps the tensors alive. */
+int orvb_model_bind_weights(orvb_model* m, const orvb_weights* w);
+
+typedef struct orvb_shape {
+  int32_t batch;        /* transformer batch (clips x CFG copies x views folded by the caller: B * V) */
+  int32_t views;        /* V (1 = single view)                                                     */
+  int32_t frames;       /* latent frames per view                                                  */
+  int32_t height;       /* latent height (pixels / 8)                                              */
+  int32_t width;
+  int32_t text_len;     /* 226                                                                     */
+  int32_t action_frames;/* rows of the action embedding per sample (= frames / max(patch_t,1)); 0 = none */
+} orvb_shape;
+
+size_t orvb_workspace_bytes(const orvb_model* m, const orvb_shape* s);
+
+typedef struct orvb_forward_args {
+  orvb_shape shape;
+  const void* hidden_states;   /* bf16 [batch, frames, in_channels, height, width]  (views already folded) */
+  const void* text;            /* bf16 [batch, text_len, text_embed_dim]                                   */
+  const float* timesteps;      /* fp32 [batch]                                                             */
+  float ofs;                   /* ofs scalar (2.0 in the reference pipeline) when cfg.has_ofs              */
+  const void* actions;         /* bf16 [batch, action_frames, state*compress*max(pt,1)] pre-padded/reshaped
+                                  (host does the integer padding of cogvideox_control.py:805-811), or NULL  */
+  const uint8_t* action_mask;  /* u8 [batch] 1 = replace by mask_embed (drawn by the caller), or NULL       */
+  const void* depths;          /* bf16 [batch, frames, in_channels, height, width] or NULL                 */
+  const void* labels;          /* same, or NULL                                                            */
+  const float* rope_cos;       /* fp32 [video_tokens, 64] or NULL                                          */
+  const float* rope_sin;
+  void* out;                   /* bf16 [batch, frames, out_channels, height, width]                        */
+  void* workspace; size_t workspace_bytes;
+  /* optional taps for parity tests (bf16 [batch*seq, dim] joint hidden state after block `tap_layer`) */
+  void* tap_hidden; int32_t tap_layer;
+} orvb_forward_args;
+
+int orvb_forward(orvb_model* m, const orvb_forward_args* a, void* stream);
+
+/* Number of kernel launches orvb_forward enqueued in its most recent call on this model (for bench.py's
+ * `gpu_launches`). */
+int orvb_last_launch_count(const orvb_model* m);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Sampler step (reference a14: CFG combine + CogVideoXDDIMScheduler/CogVideoXDPMScheduler.step + bf16 cast)
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct orvb_sampler_step_args {
+  const void* model_out;   /* bf16 [cfg_copies * n]  (uncond first, then cond, as torch.cat([latents]*2)) */
+  void* latents;           /* bf16 [n] in/out                                                            */
+  float* old_x0;           /* fp32 [n] in/out (DPM only; written every step)                             */
+  const float* noise;      /* fp32 [n] (DPM only) or NULL                                                */
+  int64_t n;
+  int32_t cfg_copies;      /* 1 or 2 */
+  float guidance_scale;
+  /* x0 = c_x * x + c_v * v ; x_prev = k_x * x + k_x0 * x0 + k_old * old_x0 + k_noise * noise */
+  float c_x, c_v, k_x, k_x0, k_old, k_noise;
+} orvb_sampler_step_args;
+int orvb_sampler_step(const orvb_sampler_step_args* a, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORV_B200_H_ */

@@ -1,0 +1,480 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a:  out = epilogue(A[M,K] · W[N,K]^T)
+//
+//   warp 0      TMA producer   (cp.async.bulk.tensor → 128B-swizzled smem ring)
+//   warp 1      MMA issuer     (one thread, tcgen05.mma cta_group::1, 128 x BN x 16 atoms, fp32 accum in TMEM)
+//   warp 2      TMEM allocator
+//   warps 4-7   epilogue       (tcgen05.ld → registers → fused epilogue → 16-byte global stores)
+//
+// Two TMEM accumulator buffers let the epilogue of tile i overlap the mainloop of tile i+1.
+// The epilogues fuse what the reference executes as separate ATen kernels around each nn.Linear
+// (reference orv/models/cogvideox_control.py): bias; GELU-tanh (FeedForward, :431-440); gated residual
+// `hidden + gate * linear(x)` (:419-421, :442-443); per-head QK LayerNorm + RoPE (:243-254); positional-table add
+// (CogVideoXPatchEmbed).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace orvb {
+
+struct GemmDev {
+  int M, N, K;
+  bf16* out;
+  int ldo;
+  const bf16* bias;
+  int src_rows, dst_rows, dst_offset;
+  const bf16* resid;
+  int ldr, resid_mod, resid_views, resid_view_stride;
+  const float* gate;
+  int gate_ld, gate_text_off, gate_video_off;
+  orvb_rowmap rm;
+  int qk_dim;
+  const bf16 *qw, *qb, *kw, *kb;
+  float qk_eps;
+  const float *rope_cos, *rope_sin;
+  int num_m_tiles, num_n_tiles;
+};
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle span
+constexpr int GEMM_THREADS = 256;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 192 ? 5 : (BN >= 128 ? 6 : 8));
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ int row_group(const orvb_rowmap& rm, int row, int* s_out) {
+  if (rm.seq_len <= 0) {
+    *s_out = row;
+    return 0;
+  }
+  int b = row / rm.seq_len;
+  int s = row - b * rm.seq_len;
+  *s_out = s;
+  int g = (s < rm.text_len) ? 0 : 1 + (s - rm.text_len) / rm.tokens_per_group;
+  return b * rm.groups_per_batch + g;
+}
+
+// Epilogue over one 64-column unit held by one thread (one output row).
+template <int EPI>
+__device__ __forceinline__ void epilogue_unit(const GemmDev& p, float (&v)[64], int row, int n0, int ncols) {
+  // ---- bias --------------------------------------------------------------------------------------
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j * 8 < ncols) {
+        uint4 bb = *reinterpret_cast<const uint4*>(p.bias + n0 + j * 8);
+        v[j * 8 + 0] += bf16_lo(bb.x); v[j * 8 + 1] += bf16_hi(bb.x);
+        v[j * 8 + 2] += bf16_lo(bb.y); v[j * 8 + 3] += bf16_hi(bb.y);
+        v[j * 8 + 4] += bf16_lo(bb.z); v[j * 8 + 5] += bf16_hi(bb.z);
+        v[j * 8 + 6] += bf16_lo(bb.w); v[j * 8 + 7] += bf16_hi(bb.w);
+      }
+    }
+  }
+  int out_row = row;
+  if (p.src_rows > 0) {
+    int q = row / p.src_rows;
+    out_row = q * p.dst_rows + p.dst_offset + (row - q * p.src_rows);
+  }
+
+  if (EPI == ORVB_EPI_GELU) {
+#pragma unroll
+    for (int j = 0; j < 64; ++j) v[j] = gelu_tanh(v[j]);
+  }
+
+  if (EPI == ORVB_EPI_QKV) {
+    int s;
+    (void)row_group(p.rm, row, &s);
+    if (n0 < 2 * p.qk_dim) {  // Q or K head: LayerNorm over the 64 values of this head
+      float mean = 0.f;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) mean += v[j];
+      mean *= (1.0f / 64.0f);
+      float var = 0.f;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        float d = v[j] - mean;
+        var += d * d;
+      }
+      var *= (1.0f / 64.0f);
+      float rstd = rsqrtf(var + p.qk_eps);
+      const bf16* w = (n0 < p.qk_dim) ? p.qw : p.kw;
+      const bf16* b = (n0 < p.qk_dim) ? p.qb : p.kb;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint4 ww = *reinterpret_cast<const uint4*>(w + j * 8);
+        uint4 bb = *reinterpret_cast<const uint4*>(b + j * 8);
+        const uint32_t wv[4] = {ww.x, ww.y, ww.z, ww.w};
+        const uint32_t bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          v[j * 8 + 2 * t] = (v[j * 8 + 2 * t] - mean) * rstd * bf16_lo(wv[t]) + bf16_lo(bv[t]);
+          v[j * 8 + 2 * t + 1] = (v[j * 8 + 2 * t + 1] - mean) * rstd * bf16_hi(wv[t]) + bf16_hi(bv[t]);
+        }
+      }
+      if (p.rope_cos != nullptr && s >= p.rm.text_len) {
+        // The reference rounds the LayerNorm output to bf16 before apply_rotary_emb upcasts it again.
+        const float* cs = p.rope_cos + static_cast<size_t>(s - p.rm.text_len) * 64;
+        const float* sn = p.rope_sin + static_cast<size_t>(s - p.rm.text_len) * 64;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float4 c4 = *reinterpret_cast<const float4*>(cs + j * 4);
+          float4 s4 = *reinterpret_cast<const float4*>(sn + j * 4);
+          float x0 = v[j * 4 + 0], x1 = v[j * 4 + 1], x2 = v[j * 4 + 2], x3 = v[j * 4 + 3];
+          v[j * 4 + 0] = x0 * c4.x - x1 * s4.x;
+          v[j * 4 + 1] = x1 * c4.y + x0 * s4.y;
+          v[j * 4 + 2] = x2 * c4.z - x3 * s4.z;
+          v[j * 4 + 3] = x3 * c4.w + x2 * s4.w;
+        }
+      }
+    }
+  }
+
+  if (EPI == ORVB_EPI_GATE_RESID) {
+    if (p.gate != nullptr) {
+      int s;
+      int g = row_group(p.rm, row, &s);
+      int is_text = (p.rm.seq_len > 0) ? (s < p.rm.text_len) : 0;
+      const float* gp = p.gate + static_cast<size_t>(g) * p.gate_ld + (is_text ? p.gate_text_off : p.gate_video_off) + n0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (j * 4 < ncols) {
+          float4 g4 = *reinterpret_cast<const float4*>(gp + j * 4);
+          v[j * 4 + 0] *= g4.x; v[j * 4 + 1] *= g4.y; v[j * 4 + 2] *= g4.z; v[j * 4 + 3] *= g4.w;
+        }
+      }
+    }
+    if (p.resid != nullptr) {
+      size_t rrow;
+      if (p.resid_mod > 0) {
+        int q = row / p.resid_mod;
+        rrow = static_cast<size_t>(row - q * p.resid_mod) +
+               static_cast<size_t>(p.resid_views > 1 ? (q % p.resid_views) : 0) * p.resid_view_stride;
+      } else {
+        rrow = static_cast<size_t>(out_row);
+      }
+      const bf16* rp = p.resid + rrow * p.ldr + n0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j * 8 < ncols) {
+          uint4 rr = *reinterpret_cast<const uint4*>(rp + j * 8);
+          v[j * 8 + 0] += bf16_lo(rr.x); v[j * 8 + 1] += bf16_hi(rr.x);
+          v[j * 8 + 2] += bf16_lo(rr.y); v[j * 8 + 3] += bf16_hi(rr.y);
+          v[j * 8 + 4] += bf16_lo(rr.z); v[j * 8 + 5] += bf16_hi(rr.z);
+          v[j * 8 + 6] += bf16_lo(rr.w); v[j * 8 + 7] += bf16_hi(rr.w);
+        }
+      }
+    }
+  }
+
+  // ---- store ---------------------------------------------------------------------------------------
+  bf16* op = p.out + static_cast<size_t>(out_row) * p.ldo + n0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (j * 8 < ncols) {
+      uint4 o;
+      o.x = pack_bf16(v[j * 8 + 0], v[j * 8 + 1]);
+      o.y = pack_bf16(v[j * 8 + 2], v[j * 8 + 3]);
+      o.z = pack_bf16(v[j * 8 + 4], v[j * 8 + 5]);
+      o.w = pack_bf16(v[j * 8 + 6], v[j * 8 + 7]);
+      *reinterpret_cast<uint4*>(op + j * 8) = o;
+    }
+  }
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                 const GemmDev p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_k = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % p.num_m_tiles;
+        const int n_blk = tile / p.num_m_tiles;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
+          tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t a_desc = umma_desc_sw128(sa);
+          const uint64_t b_desc = umma_desc_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle span: +2 in the (addr >> 4) field
+            umma_f16_ss(d_tmem, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc,
+                        static_cast<uint32_t>((kb | k) != 0));
+          }
+          tc_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit(&tfull_bar[acc]);  // accumulator complete
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ====================================
+    const int ew = warp - 4;  // == warp % 4: TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % p.num_m_tiles;
+      const int n_blk = tile / p.num_m_tiles;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BM + ew * 32 + lane;
+      const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(ew * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 64) {
+        const int n0 = n_blk * BN + c;
+        if (n0 >= p.N) break;  // warp-uniform
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c), r0);
+        tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c + 32), r1);
+        tmem_ld_wait();
+        if (row < p.M) {
+          float v[64];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] = __uint_as_float(r0[j]);
+            v[32 + j] = __uint_as_float(r1[j]);
+          }
+          const int ncols = (p.N - n0 < 64) ? (p.N - n0) : 64;
+          epilogue_unit<EPI>(p, v, row, n0, ncols);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  // ---- teardown ----------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+template <int BN, int EPI>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  auto kern = gemm_bf16_kernel<BN, EPI>;
+  if (!attr_set) {
+    ORVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  int tiles = p.num_m_tiles * p.num_n_tiles;
+  int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  ORVB_CHECK_CUDA(cudaGetLastError());
+  return ORVB_OK;
+}
+
+template <int BN>
+static int launch_gemm_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p,
+                           cudaStream_t stream) {
+  switch (epi) {
+    case ORVB_EPI_BIAS: return launch_gemm<BN, ORVB_EPI_BIAS>(ta, tb, p, stream);
+    case ORVB_EPI_GELU: return launch_gemm<BN, ORVB_EPI_GELU>(ta, tb, p, stream);
+    case ORVB_EPI_GATE_RESID: return launch_gemm<BN, ORVB_EPI_GATE_RESID>(ta, tb, p, stream);
+    case ORVB_EPI_QKV: return launch_gemm<BN, ORVB_EPI_QKV>(ta, tb, p, stream);
+  }
+  set_error("orvb_gemm_bf16: unknown epilogue %d", epi);
+  return ORVB_EINVAL;
+}
+
+// Picks the N tile that minimises (waves x tile cost) on this GPU for a persistent 1-CTA/SM launch.
+int gemm_pick_bn(int m, int n) {
+  const int sms = sm_count();
+  const int mt = (m + BM - 1) / BM;
+  int best_bn = 128;
+  double best = 1e30;
+  const int cands[3] = {256, 128, 64};
+  for (int i = 0; i < 3; ++i) {
+    int bn = cands[i];
+    if (bn > 64 && n < bn) continue;
+    int nt = (n + bn - 1) / bn;
+    long tiles = static_cast<long>(mt) * nt;
+    long waves = (tiles + sms - 1) / sms;
+    // per-tile cost model: MMA time ~ bn, plus a fixed per-tile overhead; small tiles are smem-bandwidth bound
+    double tile_cost = bn * (bn >= 256 ? 1.0 : (bn >= 128 ? 1.12 : 1.5)) + 8.0;
+    double cost = waves * tile_cost;
+    if (cost < best) {
+      best = cost;
+      best_bn = bn;
+    }
+  }
+  return best_bn;
+}
+
+int gemm_launch_prepared(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int bn, int epi,
+                         cudaStream_t stream) {
+  switch (bn) {
+    case 256: return launch_gemm_epi<256>(epi, ta, tb, p, stream);
+    case 128: return launch_gemm_epi<128>(epi, ta, tb, p, stream);
+    case 64: return launch_gemm_epi<64>(epi, ta, tb, p, stream);
+  }
+  set_error("gemm: unsupported BN %d", bn);
+  return ORVB_EINVAL;
+}
+
+int gemm_prepare(const orvb_gemm_args* a, int bn_override, CUtensorMap* ta, CUtensorMap* tb, GemmDev* p, int* bn_out) {
+  ORVB_REQUIRE(a != nullptr && a->a && a->w && a->out, ORVB_EINVAL, "orvb_gemm_bf16: null pointer");
+  ORVB_REQUIRE(a->m > 0 && a->n > 0 && a->k > 0, ORVB_ESHAPE, "orvb_gemm_bf16: empty problem m=%d n=%d k=%d", a->m,
+               a->n, a->k);
+  ORVB_REQUIRE(a->k % 8 == 0 && a->n % 8 == 0 && a->lda % 8 == 0 && a->ldw % 8 == 0 && a->ldo % 8 == 0, ORVB_ESHAPE,
+               "orvb_gemm_bf16: k, n and row pitches must be multiples of 8 (k=%d n=%d lda=%d ldw=%d ldo=%d)", a->k,
+               a->n, a->lda, a->ldw, a->ldo);
+  ORVB_REQUIRE((reinterpret_cast<uintptr_t>(a->a) | reinterpret_cast<uintptr_t>(a->w) |
+                reinterpret_cast<uintptr_t>(a->out)) % 16 == 0,
+               ORVB_ESHAPE, "orvb_gemm_bf16: base pointers must be 16-byte aligned");
+  if (a->epilogue == ORVB_EPI_QKV) {
+    ORVB_REQUIRE(a->qk_dim > 0 && a->qk_dim % 64 == 0 && a->n == 3 * a->qk_dim, ORVB_ESHAPE,
+                 "orvb_gemm_bf16: QKV epilogue needs n == 3*qk_dim, qk_dim %% 64 == 0");
+    ORVB_REQUIRE(a->q_norm_w && a->q_norm_b && a->k_norm_w && a->k_norm_b, ORVB_EINVAL,
+                 "orvb_gemm_bf16: QKV epilogue needs the q/k norm parameters");
+  }
+  if (a->epilogue == ORVB_EPI_GATE_RESID) {
+    ORVB_REQUIRE(a->resid == nullptr || a->ldr % 8 == 0, ORVB_ESHAPE, "orvb_gemm_bf16: ldr must be a multiple of 8");
+    ORVB_REQUIRE(a->gate == nullptr || (a->gate_ld % 4 == 0 && a->gate_text_off % 4 == 0 && a->gate_video_off % 4 == 0),
+                 ORVB_ESHAPE, "orvb_gemm_bf16: gate pitch/offsets must be multiples of 4");
+  }
+  int bn = bn_override > 0 ? bn_override : gemm_pick_bn(a->m, a->n);
+  int rc = make_tmap_2d_bf16(ta, a->a, a->m, a->k, a->lda, BM, BK);
+  if (rc != ORVB_OK) return rc;
+  rc = make_tmap_2d_bf16(tb, a->w, a->n, a->k, a->ldw, bn, BK);
+  if (rc != ORVB_OK) return rc;
+  GemmDev d;
+  d.M = a->m; d.N = a->n; d.K = a->k;
+  d.out = static_cast<bf16*>(a->out); d.ldo = a->ldo;
+  d.bias = static_cast<const bf16*>(a->bias);
+  d.src_rows = a->src_rows; d.dst_rows = a->dst_rows; d.dst_offset = a->dst_offset;
+  d.resid = static_cast<const bf16*>(a->resid); d.ldr = a->ldr;
+  d.resid_mod = a->resid_mod; d.resid_views = a->resid_views; d.resid_view_stride = a->resid_view_stride;
+  d.gate = a->gate; d.gate_ld = a->gate_ld; d.gate_text_off = a->gate_text_off; d.gate_video_off = a->gate_video_off;
+  d.rm = a->rowmap;
+  d.qk_dim = a->qk_dim;
+  d.qw = static_cast<const bf16*>(a->q_norm_w); d.qb = static_cast<const bf16*>(a->q_norm_b);
+  d.kw = static_cast<const bf16*>(a->k_norm_w); d.kb = static_cast<const bf16*>(a->k_norm_b);
+  d.qk_eps = a->qk_eps;
+  d.rope_cos = a->rope_cos; d.rope_sin = a->rope_sin;
+  d.num_m_tiles = (a->m + BM - 1) / BM;
+  d.num_n_tiles = (a->n + bn - 1) / bn;
+  *p = d;
+  *bn_out = bn;
+  return ORVB_OK;
+}
+
+}  // namespace orvb
+
+extern "C" int orvb_gemm_bf16(const orvb_gemm_args* args, void* stream) {
+  using namespace orvb;
+  int rc = check_arch();
+  if (rc != ORVB_OK) return rc;
+  CUtensorMap ta, tb;
+  GemmDev p;
+  int bn;
+  rc = gemm_prepare(args, 0, &ta, &tb, &p, &bn);
+  if (rc != ORVB_OK) return rc;
+  return gemm_launch_prepared(ta, tb, p, bn, args->epilogue, static_cast<cudaStream_t>(stream));
+}
+
+// Test hook: same as orvb_gemm_bf16 with a forced N tile (64 / 128 / 256).
+extern "C" int orvb_gemm_bf16_bn(const orvb_gemm_args* args, int bn, void* stream) {
+  using namespace orvb;
+  int rc = check_arch();
+  if (rc != ORVB_OK) return rc;
+  CUtensorMap ta, tb;
+  GemmDev p;
+  int bn_used;
+  rc = gemm_prepare(args, bn, &ta, &tb, &p, &bn_used);
+  if (rc != ORVB_OK) return rc;
+  return gemm_launch_prepared(ta, tb, p, bn_used, args->epilogue, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,143 @@
+"""Torch-tensor front ends of the granular C-ABI operators (used by the parity tests and by bench.py).
+
+Each function validates dtypes/devices, passes raw device pointers through ctypes and returns torch tensors.
+None of them falls back to PyTorch arithmetic.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+
+def _req(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (liborv_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+
+
+def rowmap(seq_len=0, text_len=0, tokens_per_group=1, groups_per_batch=1) -> L.RowMap:
+    return L.RowMap(seq_len, text_len, max(tokens_per_group, 1), groups_per_batch)
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, epilogue: int = L.EPI_BIAS,
+         out: Optional[torch.Tensor] = None, ldo: Optional[int] = None, out_col_offset: int = 0,
+         row_remap=(0, 0, 0), resid: Optional[torch.Tensor] = None, resid_mod: int = 0, resid_views: int = 1,
+         resid_view_stride: int = 0, gate: Optional[torch.Tensor] = None, gate_text_off: int = 0,
+         gate_video_off: int = 0, rm: Optional[L.RowMap] = None, qk_dim: int = 0, q_norm=None, k_norm=None,
+         qk_eps: float = 1e-6, rope=None, bn: int = 0) -> torch.Tensor:
+    """out = epilogue(a @ w.T)  — a [M,K] bf16, w [N,K] bf16 (nn.Linear layout)."""
+    _req(a, torch.bfloat16, "a")
+    _req(w, torch.bfloat16, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K
+    if out is None:
+        rows = M if row_remap[0] == 0 else (M // row_remap[0]) * row_remap[1]
+        out = torch.empty((rows, N), dtype=torch.bfloat16, device=a.device)
+    _req(out, torch.bfloat16, "out")
+    args = L.GemmArgs()
+    args.a, args.w = a.data_ptr(), w.data_ptr()
+    args.out = out.data_ptr() + out_col_offset * 2
+    args.bias = L.ptr(bias)
+    args.m, args.n, args.k = M, N, K
+    args.lda, args.ldw = a.stride(0), w.stride(0)
+    args.ldo = ldo if ldo is not None else out.stride(0)
+    args.epilogue = epilogue
+    args.src_rows, args.dst_rows, args.dst_offset = row_remap
+    if resid is not None:
+        _req(resid, torch.bfloat16, "resid")
+        args.resid, args.ldr = resid.data_ptr(), resid.stride(-2)
+    args.resid_mod, args.resid_views, args.resid_view_stride = resid_mod, resid_views, resid_view_stride
+    if gate is not None:
+        _req(gate, torch.float32, "gate")
+        args.gate, args.gate_ld = gate.data_ptr(), gate.stride(-2)
+    args.gate_text_off, args.gate_video_off = gate_text_off, gate_video_off
+    args.rowmap = rm if rm is not None else rowmap()
+    args.qk_dim = qk_dim
+    if q_norm is not None:
+        args.q_norm_w, args.q_norm_b = q_norm[0].data_ptr(), q_norm[1].data_ptr()
+        args.k_norm_w, args.k_norm_b = k_norm[0].data_ptr(), k_norm[1].data_ptr()
+    args.qk_eps = qk_eps
+    if rope is not None:
+        _req(rope[0], torch.float32, "rope_cos")
+        _req(rope[1], torch.float32, "rope_sin")
+        args.rope_cos, args.rope_sin = rope[0].data_ptr(), rope[1].data_ptr()
+    lib = L.load()
+    if bn:
+        L.check(lib.orvb_gemm_bf16_bn(C.byref(args), bn, L.current_stream()), "orvb_gemm_bf16")
+    else:
+        L.check(lib.orvb_gemm_bf16(C.byref(args), L.current_stream()), "orvb_gemm_bf16")
+    return out
+
+
+def attention(qkv: torch.Tensor, batch: int, seq_len: int, heads: int, scale: float,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(qkv, torch.bfloat16, "qkv")
+    assert qkv.shape == (batch * seq_len, 3 * heads * 64)
+    if out is None:
+        out = torch.empty((batch * seq_len, heads * 64), dtype=torch.bfloat16, device=qkv.device)
+    L.check(L.load().orvb_attention_bf16(qkv.data_ptr(), out.data_ptr(), batch, seq_len, heads, scale,
+                                         L.current_stream()), "orvb_attention_bf16")
+    return out
+
+
+def ln_modulate(x: torch.Tensor, ln_w, ln_b, eps: float, mod: Optional[torch.Tensor] = None, text_off: int = 0,
+                video_off: int = 0, scale_first: bool = False, rm: Optional[L.RowMap] = None,
+                in_video_only: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(x, torch.bfloat16, "x")
+    rows_in, dim = x.shape
+    rmap = rm if rm is not None else rowmap()
+    rows = rows_in
+    if in_video_only:
+        nb = rows_in // rmap.seq_len
+        rows = nb * (rmap.seq_len - rmap.text_len)
+    if out is None:
+        out = torch.empty((rows, dim), dtype=torch.bfloat16, device=x.device)
+    a = L.LnArgs()
+    a.x, a.y = x.data_ptr(), out.data_ptr()
+    a.ln_w, a.ln_b = L.ptr(ln_w), L.ptr(ln_b)
+    a.rows, a.dim, a.eps = rows, dim, eps
+    if mod is not None:
+        _req(mod, torch.float32, "mod")
+        a.mod, a.mod_ld = mod.data_ptr(), mod.stride(-2)
+    a.text_off, a.video_off, a.scale_first = text_off, video_off, int(scale_first)
+    a.rowmap = rmap
+    a.in_video_only = int(in_video_only)
+    L.check(L.load().orvb_ln_modulate(C.byref(a), L.current_stream()), "orvb_ln_modulate")
+    return out
+
+
+def skinny_linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], act: int = 0) -> torch.Tensor:
+    _req(x, torch.float32, "x")
+    _req(w, torch.bfloat16, "w")
+    rows, k = x.shape
+    n = w.shape[0]
+    y = torch.empty((rows, n), dtype=torch.float32, device=x.device)
+    L.check(L.load().orvb_skinny_linear(x.data_ptr(), w.data_ptr(), L.ptr(b), y.data_ptr(), rows, n, k, act,
+                                        L.current_stream()), "orvb_skinny_linear")
+    return y
+
+
+def patchify(x: torch.Tensor, p: int, patch_t: int = 0) -> torch.Tensor:
+    _req(x, torch.bfloat16, "x")
+    B, F, Cc, H, W = x.shape
+    pt = max(patch_t, 1)
+    out = torch.empty((B * (F // pt) * (H // p) * (W // p), Cc * pt * p * p), dtype=torch.bfloat16, device=x.device)
+    L.check(L.load().orvb_patchify(x.data_ptr(), out.data_ptr(), B, F, Cc, H, W, p, patch_t, L.current_stream()),
+            "orvb_patchify")
+    return out
+
+
+def unpatchify(y: torch.Tensor, B: int, F: int, Cc: int, H: int, W: int, p: int, patch_t: int = 0) -> torch.Tensor:
+    _req(y, torch.bfloat16, "y")
+    out = torch.empty((B, F, Cc, H, W), dtype=torch.bfloat16, device=y.device)
+    L.check(L.load().orvb_unpatchify(y.data_ptr(), out.data_ptr(), B, F, Cc, H, W, p, patch_t, L.current_stream()),
+            "orvb_unpatchify")
+    return out
