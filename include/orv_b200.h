@@ -58,7 +58,9 @@ enum {
 /* Row -> modulation-group map of a joint [text | video] sequence (reference LayerNormZero semantics,
  * cogvideox_control.py:117-145): with s = row % seq_len and b = row / seq_len,
  *   group(row) = b * groups_per_batch + (s < text_len ? 0 : 1 + (s - text_len) / tokens_per_group).
- * Group 0 of every batch is the text group.  seq_len == 0 disables the map (group = 0). */
+ * Group 0 of every batch is the text group (modulated by the time embedding alone).  tokens_per_group <= 0 sends
+ * the video rows to group 0 as well (no per-frame action modulation: MVBlock.norm1, :323-325).
+ * seq_len == 0 disables the map (group = 0, every row counts as video). */
 typedef struct orvb_rowmap {
   int32_t seq_len;
   int32_t text_len;
@@ -125,6 +127,9 @@ typedef struct orvb_ln_args {
   const float* mod; int32_t mod_ld, text_off, video_off, scale_first;
   orvb_rowmap rowmap;
   int32_t in_video_only;        /* gather only video rows of the joint sequence (norm_final / norm_out) */
+  const void* pre_w; const void* pre_b; /* optional first LayerNorm (norm_final, cogvideox_control.py:909-916)
+                                           applied before the modulated one; bf16 [dim] or NULL */
+  float pre_eps;
 } orvb_ln_args;
 int orvb_ln_modulate(const orvb_ln_args* args, void* stream);
 

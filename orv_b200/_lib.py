@@ -50,6 +50,7 @@ class LnArgs(C.Structure):
         ("mod", c_void_p), ("mod_ld", c_int), ("text_off", c_int), ("video_off", c_int), ("scale_first", c_int),
         ("rowmap", RowMap),
         ("in_video_only", c_int),
+        ("pre_w", c_void_p), ("pre_b", c_void_p), ("pre_eps", c_float),
     ]
 
 

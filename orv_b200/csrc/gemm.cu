@@ -55,7 +55,7 @@ __device__ __forceinline__ int row_group(const orvb_rowmap& rm, int row, int* s_
   int b = row / rm.seq_len;
   int s = row - b * rm.seq_len;
   *s_out = s;
-  int g = (s < rm.text_len) ? 0 : 1 + (s - rm.text_len) / rm.tokens_per_group;
+  int g = (s < rm.text_len || rm.tokens_per_group <= 0) ? 0 : 1 + (s - rm.text_len) / rm.tokens_per_group;
   return b * rm.groups_per_batch + g;
 }
 

@@ -1,0 +1,434 @@
+// Memory-bound kernels of the path: LayerNorm + AdaLN modulation, the skinny (few-row) linears that build the
+// modulation tables, patch gather / scatter, and the fused sampler step.  All of them are plain SIMT kernels
+// with 128-bit global accesses; none is worth a tensor core.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "pointwise.cuh"
+
+namespace orvb {
+
+__device__ __forceinline__ int row_group_pw(const orvb_rowmap& rm, int row, int* is_text) {
+  if (rm.seq_len <= 0) {
+    *is_text = 0;
+    return 0;
+  }
+  int b = row / rm.seq_len;
+  int s = row - b * rm.seq_len;
+  *is_text = (s < rm.text_len);
+  int g = (s < rm.text_len || rm.tokens_per_group <= 0) ? 0 : 1 + (s - rm.text_len) / rm.tokens_per_group;
+  return b * rm.groups_per_batch + g;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// LayerNorm (+ optional preceding LayerNorm) + AdaLN modulate.  One warp per row, row kept in registers.
+// Reference: CogVideoXLayerNormZero.forward (cogvideox_control.py:117-145), AdaLayerNorm.forward (:153-197),
+// norm_final (:909-916).
+// ---------------------------------------------------------------------------------------------------
+struct LnDev {
+  const bf16* x;
+  bf16* y;
+  const bf16 *w, *b, *pre_w, *pre_b;
+  int rows, dim;
+  float eps, pre_eps;
+  const float* mod;
+  int mod_ld, text_off, video_off, scale_first;
+  orvb_rowmap rm;
+  int in_video_only;
+};
+
+template <int MAXC>
+__device__ __forceinline__ void ln_stats(const float (&v)[MAXC][8], int nchunks, int lane, int dim, float eps,
+                                         float* mean_out, float* rstd_out) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i)
+    if (lane + 32 * i < nchunks) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    }
+  const float mean = warp_sum(s) / static_cast<float>(dim);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i)
+    if (lane + 32 * i < nchunks) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float d = v[i][j] - mean;
+        q += d * d;
+      }
+    }
+  const float var = warp_sum(q) / static_cast<float>(dim);
+  *mean_out = mean;
+  *rstd_out = rsqrtf(var + eps);
+}
+
+template <int MAXC>
+__global__ void __launch_bounds__(256) ln_modulate_kernel(const LnDev p) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= p.rows) return;
+  const int nchunks = p.dim >> 3;
+  int in_row = row;
+  if (p.in_video_only) {
+    const int sv = p.rm.seq_len - p.rm.text_len;
+    const int b = row / sv;
+    in_row = b * p.rm.seq_len + p.rm.text_len + (row - b * sv);
+  }
+  const bf16* xr = p.x + static_cast<size_t>(in_row) * p.dim;
+  float v[MAXC][8];
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nchunks) {
+      uint4 u = *reinterpret_cast<const uint4*>(xr + c * 8);
+      unpack8(u, v[i]);
+    }
+  }
+  float mean, rstd;
+  if (p.pre_w != nullptr) {
+    ln_stats<MAXC>(v, nchunks, lane, p.dim, p.pre_eps, &mean, &rstd);
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nchunks) {
+        float w[8], b[8];
+        unpack8(*reinterpret_cast<const uint4*>(p.pre_w + c * 8), w);
+        unpack8(*reinterpret_cast<const uint4*>(p.pre_b + c * 8), b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          // the reference materialises norm_final's output in bf16 before norm_out reads it
+          v[i][j] = __bfloat162float(__float2bfloat16((v[i][j] - mean) * rstd * w[j] + b[j]));
+        }
+      }
+    }
+  }
+  ln_stats<MAXC>(v, nchunks, lane, p.dim, p.eps, &mean, &rstd);
+
+  const float* shift = nullptr;
+  const float* scale = nullptr;
+  if (p.mod != nullptr) {
+    int is_text;
+    const int g = row_group_pw(p.rm, in_row, &is_text);
+    const float* base = p.mod + static_cast<size_t>(g) * p.mod_ld + (is_text ? p.text_off : p.video_off);
+    shift = p.scale_first ? base + p.dim : base;
+    scale = p.scale_first ? base : base + p.dim;
+  }
+  bf16* yr = p.y + static_cast<size_t>(row) * p.dim;
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nchunks) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd;
+      if (p.w != nullptr) {
+        float w[8], b[8];
+        unpack8(*reinterpret_cast<const uint4*>(p.w + c * 8), w);
+        unpack8(*reinterpret_cast<const uint4*>(p.b + c * 8), b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = o[j] * w[j] + b[j];
+      }
+      if (shift != nullptr) {
+        const float4 s0 = *reinterpret_cast<const float4*>(scale + c * 8);
+        const float4 s1 = *reinterpret_cast<const float4*>(scale + c * 8 + 4);
+        const float4 h0 = *reinterpret_cast<const float4*>(shift + c * 8);
+        const float4 h1 = *reinterpret_cast<const float4*>(shift + c * 8 + 4);
+        o[0] = o[0] * (1.f + s0.x) + h0.x; o[1] = o[1] * (1.f + s0.y) + h0.y;
+        o[2] = o[2] * (1.f + s0.z) + h0.z; o[3] = o[3] * (1.f + s0.w) + h0.w;
+        o[4] = o[4] * (1.f + s1.x) + h1.x; o[5] = o[5] * (1.f + s1.y) + h1.y;
+        o[6] = o[6] * (1.f + s1.z) + h1.z; o[7] = o[7] * (1.f + s1.w) + h1.w;
+      }
+      uint4 u;
+      u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]);
+      u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
+      *reinterpret_cast<uint4*>(yr + c * 8) = u;
+    }
+  }
+}
+
+int ln_modulate_launch(const orvb_ln_args* a, cudaStream_t stream) {
+  ORVB_REQUIRE(a && a->x && a->y, ORVB_EINVAL, "orvb_ln_modulate: null pointer");
+  ORVB_REQUIRE(a->rows > 0 && a->dim > 0 && a->dim % 8 == 0 && a->dim <= 4096, ORVB_ESHAPE,
+               "orvb_ln_modulate: dim must be a multiple of 8 and <= 4096 (got %d)", a->dim);
+  ORVB_REQUIRE((a->ln_w == nullptr) == (a->ln_b == nullptr), ORVB_EINVAL, "orvb_ln_modulate: ln_w/ln_b must pair");
+  ORVB_REQUIRE(a->mod == nullptr || (a->mod_ld % 4 == 0 && a->text_off % 4 == 0 && a->video_off % 4 == 0), ORVB_ESHAPE,
+               "orvb_ln_modulate: modulation pitch/offsets must be multiples of 4");
+  ORVB_REQUIRE(!a->in_video_only || (a->rowmap.seq_len > a->rowmap.text_len), ORVB_EINVAL,
+               "orvb_ln_modulate: in_video_only needs a row map");
+  LnDev d;
+  d.x = static_cast<const bf16*>(a->x); d.y = static_cast<bf16*>(a->y);
+  d.w = static_cast<const bf16*>(a->ln_w); d.b = static_cast<const bf16*>(a->ln_b);
+  d.pre_w = static_cast<const bf16*>(a->pre_w); d.pre_b = static_cast<const bf16*>(a->pre_b);
+  d.rows = a->rows; d.dim = a->dim; d.eps = a->eps; d.pre_eps = a->pre_eps;
+  d.mod = a->mod; d.mod_ld = a->mod_ld; d.text_off = a->text_off; d.video_off = a->video_off;
+  d.scale_first = a->scale_first; d.rm = a->rowmap; d.in_video_only = a->in_video_only;
+  const int rows_per_block = 8;
+  dim3 grid((a->rows + rows_per_block - 1) / rows_per_block);
+  const int nchunks = a->dim / 8;
+  if (nchunks <= 32 * 8) ln_modulate_kernel<8><<<grid, 256, 0, stream>>>(d);
+  else if (nchunks <= 32 * 12) ln_modulate_kernel<12><<<grid, 256, 0, stream>>>(d);
+  else ln_modulate_kernel<16><<<grid, 256, 0, stream>>>(d);
+  ORVB_CHECK_CUDA(cudaGetLastError());
+  return ORVB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Skinny linear: y[r, n] = act(x[r, :] . W[n, :] + b[n]) for <= 8 rows per pass.  HBM-bound on W (the AdaLN
+// linears hold 354 M parameters in the 2B model: ~0.7 GB read per forward), so each warp streams 4 weight rows
+// with 16-byte loads and reuses the fp32 activations (L1-resident) across them.
+// ---------------------------------------------------------------------------------------------------
+constexpr int SK_ROWS = 8;
+constexpr int SK_COLS = 4;
+
+template <bool BATCHED>
+__global__ void __launch_bounds__(256) skinny_linear_kernel(const float* __restrict__ x, SkinnyJob single,
+                                                            const SkinnyJob* __restrict__ jobs, int rows, int n,
+                                                            int k, int act) {
+  const SkinnyJob job = BATCHED ? jobs[blockIdx.z] : single;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int n0 = (blockIdx.x * (blockDim.x >> 5) + warp) * SK_COLS;
+  if (n0 >= n) return;
+  const int r0 = blockIdx.y * SK_ROWS;
+  const int nr = min(SK_ROWS, rows - r0);
+  float acc[SK_ROWS][SK_COLS];
+#pragma unroll
+  for (int r = 0; r < SK_ROWS; ++r)
+#pragma unroll
+    for (int c = 0; c < SK_COLS; ++c) acc[r][c] = 0.f;
+
+  for (int k0 = lane * 8; k0 < k; k0 += 256) {
+    float w[SK_COLS][8];
+#pragma unroll
+    for (int c = 0; c < SK_COLS; ++c) {
+      if (n0 + c < n) {
+        unpack8(*reinterpret_cast<const uint4*>(job.w + static_cast<size_t>(n0 + c) * k + k0), w[c]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[c][j] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < SK_ROWS; ++r) {
+      if (r < nr) {
+        const float4 a0 = *reinterpret_cast<const float4*>(x + static_cast<size_t>(r0 + r) * k + k0);
+        const float4 a1 = *reinterpret_cast<const float4*>(x + static_cast<size_t>(r0 + r) * k + k0 + 4);
+        const float xv[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+        for (int c = 0; c < SK_COLS; ++c)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[r][c] = fmaf(xv[j], w[c][j], acc[r][c]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < SK_ROWS; ++r)
+#pragma unroll
+    for (int c = 0; c < SK_COLS; ++c) acc[r][c] = warp_sum(acc[r][c]);
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < SK_ROWS; ++r) {
+      if (r < nr) {
+#pragma unroll
+        for (int c = 0; c < SK_COLS; ++c) {
+          if (n0 + c < n) {
+            float v = acc[r][c] + (job.b != nullptr ? __bfloat162float(job.b[n0 + c]) : 0.f);
+            if (act == 1) v = silu(v);
+            else if (act == 2) v = gelu_tanh(v);
+            job.y[static_cast<size_t>(r0 + r) * n + n0 + c] = v;
+          }
+        }
+      }
+    }
+  }
+}
+
+int skinny_linear_launch(const float* x, const SkinnyJob& job, const SkinnyJob* jobs_dev, int num_jobs, int rows,
+                         int n, int k, int act, cudaStream_t stream) {
+  ORVB_REQUIRE(x != nullptr && rows > 0 && n > 0 && k > 0, ORVB_EINVAL, "orvb_skinny_linear: bad arguments");
+  ORVB_REQUIRE(k % 8 == 0, ORVB_ESHAPE, "orvb_skinny_linear: k must be a multiple of 8 (got %d)", k);
+  const int cols_per_block = 8 * SK_COLS;
+  dim3 grid((n + cols_per_block - 1) / cols_per_block, (rows + SK_ROWS - 1) / SK_ROWS, jobs_dev ? num_jobs : 1);
+  if (jobs_dev != nullptr) skinny_linear_kernel<true><<<grid, 256, 0, stream>>>(x, job, jobs_dev, rows, n, k, act);
+  else skinny_linear_kernel<false><<<grid, 256, 0, stream>>>(x, job, nullptr, rows, n, k, act);
+  ORVB_CHECK_CUDA(cudaGetLastError());
+  return ORVB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Patch gather / scatter (p = 2).  Index maps are the closed forms of SURVEY App. A.1 / A.6 and must be
+// bit-exact with the reference's reshape/permute chains.
+// ---------------------------------------------------------------------------------------------------
+__global__ void patchify_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int B, int F, int C, int H, int W,
+                                int pt) {
+  // one thread per (token, channel, t): gathers the 2x2 spatial patch
+  const int Hp = H >> 1, Wp = W >> 1, Fp = F / pt;
+  const long total = static_cast<long>(B) * Fp * Hp * Wp * C * pt;
+  const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  int j = idx % Wp;
+  long r = idx / Wp;
+  int i = r % Hp; r /= Hp;
+  int t = r % pt; r /= pt;
+  int c = r % C; r /= C;
+  int fp = r % Fp;
+  int b = r / Fp;
+  const int f = fp * pt + t;
+  const bf16* src = x + ((((static_cast<size_t>(b) * F + f) * C + c) * H + 2 * i) * W + 2 * j);
+  const uint32_t top = *reinterpret_cast<const uint32_t*>(src);
+  const uint32_t bot = *reinterpret_cast<const uint32_t*>(src + W);
+  const size_t tok = (static_cast<size_t>(b) * Fp + fp) * Hp * Wp + static_cast<size_t>(i) * Wp + j;
+  const int kdim = C * pt * 4;
+  uint2 v;
+  v.x = top;
+  v.y = bot;
+  *reinterpret_cast<uint2*>(out + tok * kdim + (c * pt + t) * 4) = v;
+}
+
+__global__ void unpatchify_kernel(const bf16* __restrict__ y, bf16* __restrict__ out, int B, int F, int C, int H,
+                                  int W, int pt) {
+  const int Hp = H >> 1, Wp = W >> 1, Fp = F / pt;
+  const long total = static_cast<long>(B) * Fp * Hp * Wp * C * pt;
+  const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  int j = idx % Wp;
+  long r = idx / Wp;
+  int i = r % Hp; r /= Hp;
+  int t = r % pt; r /= pt;
+  int c = r % C; r /= C;
+  int fp = r % Fp;
+  int b = r / Fp;
+  const int f = fp * pt + t;
+  const size_t tok = (static_cast<size_t>(b) * Fp + fp) * Hp * Wp + static_cast<size_t>(i) * Wp + j;
+  const int kdim = C * pt * 4;
+  const uint2 v = *reinterpret_cast<const uint2*>(y + tok * kdim + (c * pt + t) * 4);
+  bf16* dst = out + ((((static_cast<size_t>(b) * F + f) * C + c) * H + 2 * i) * W + 2 * j);
+  *reinterpret_cast<uint32_t*>(dst) = v.x;
+  *reinterpret_cast<uint32_t*>(dst + W) = v.y;
+}
+
+static int patch_check(const void* a, const void* b, int B, int F, int C, int H, int W, int p, int patch_t,
+                       const char* what) {
+  ORVB_REQUIRE(a && b, ORVB_EINVAL, "%s: null pointer", what);
+  ORVB_REQUIRE(p == 2, ORVB_ESHAPE, "%s: only patch_size 2 is supported (got %d)", what, p);
+  ORVB_REQUIRE(B > 0 && F > 0 && C > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, ORVB_ESHAPE,
+               "%s: bad geometry B=%d F=%d C=%d H=%d W=%d", what, B, F, C, H, W);
+  ORVB_REQUIRE(patch_t == 0 || patch_t == 1 || F % patch_t == 0, ORVB_ESHAPE,
+               "%s: frames (%d) must be divisible by patch_size_t (%d)", what, F, patch_t);
+  return ORVB_OK;
+}
+
+int patchify_launch(const void* x, void* out, int B, int F, int C, int H, int W, int p, int patch_t,
+                    cudaStream_t stream) {
+  int rc = patch_check(x, out, B, F, C, H, W, p, patch_t, "orvb_patchify");
+  if (rc != ORVB_OK) return rc;
+  const int pt = patch_t > 0 ? patch_t : 1;
+  const long total = static_cast<long>(B) * F * C * (H / 2) * (W / 2);
+  patchify_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      static_cast<const bf16*>(x), static_cast<bf16*>(out), B, F, C, H, W, pt);
+  ORVB_CHECK_CUDA(cudaGetLastError());
+  return ORVB_OK;
+}
+
+int unpatchify_launch(const void* y, void* out, int B, int F, int C, int H, int W, int p, int patch_t,
+                      cudaStream_t stream) {
+  int rc = patch_check(y, out, B, F, C, H, W, p, patch_t, "orvb_unpatchify");
+  if (rc != ORVB_OK) return rc;
+  const int pt = patch_t > 0 ? patch_t : 1;
+  const long total = static_cast<long>(B) * F * C * (H / 2) * (W / 2);
+  unpatchify_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      static_cast<const bf16*>(y), static_cast<bf16*>(out), B, F, C, H, W, pt);
+  ORVB_CHECK_CUDA(cudaGetLastError());
+  return ORVB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Sampler step: CFG combine + v-prediction -> x0 + DDIM / DPM-Solver++(2M, SDE) update + bf16 cast, one pass.
+// Reference: cogvideox_control.py:1433-1459 and diffusers CogVideoX{DDIM,DPM}Scheduler.step.
+// The reference keeps `latents` (and the DPM noise) in bf16 and multiplies them by 0-dim float64 coefficients,
+// which rounds those products to bf16 before they meet the fp32 model output; `round_bf16_products` reproduces
+// that, so the step is bit-identical to the torch sequence given the same model output.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rbf(float v) { return __bfloat162float(__float2bfloat16(v)); }
+
+__global__ void sampler_step_kernel(const orvb_sampler_step_args a) {
+  const long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (i >= a.n) return;
+  const bf16* mo = static_cast<const bf16*>(a.model_out);
+  bf16* lat = static_cast<bf16*>(a.latents);
+  float v;
+  if (a.cfg_copies == 2) {
+    const float u = __bfloat162float(mo[i]);
+    const float c = __bfloat162float(mo[a.n + i]);
+    v = u + a.guidance_scale * (c - u);
+  } else {
+    v = __bfloat162float(mo[i]);
+  }
+  const float x = __bfloat162float(lat[i]);
+  // pred_original_sample = sqrt(alpha_t) * sample - sqrt(1 - alpha_t) * model_output
+  const float x0 = rbf(a.c_x * x) + a.c_v * v;
+  float d = x0;
+  if (a.k_old != 0.f) d = a.k_x0_cur * x0 + a.k_old * a.old_x0[i];
+  // prev = m1 * sample + k_d * d + m_noise * noise      (DDIM: k_noise = 0, d = x0)
+  float prev = rbf(a.k_x * x) + a.k_x0 * d;
+  if (a.noise != nullptr) prev += rbf(a.k_noise * __bfloat162float(static_cast<const bf16*>(a.noise)[i]));
+  if (a.old_x0 != nullptr) a.old_x0[i] = x0;
+  lat[i] = __float2bfloat16(prev);
+}
+
+int sampler_step_launch(const orvb_sampler_step_args* a, cudaStream_t stream) {
+  ORVB_REQUIRE(a && a->model_out && a->latents && a->n > 0, ORVB_EINVAL, "orvb_sampler_step: bad arguments");
+  ORVB_REQUIRE(a->cfg_copies == 1 || a->cfg_copies == 2, ORVB_EINVAL, "orvb_sampler_step: cfg_copies must be 1 or 2");
+  ORVB_REQUIRE(a->k_old == 0.f || a->old_x0 != nullptr, ORVB_EINVAL, "orvb_sampler_step: k_old needs old_x0");
+  sampler_step_kernel<<<static_cast<unsigned>((a->n + 255) / 256), 256, 0, stream>>>(*a);
+  ORVB_CHECK_CUDA(cudaGetLastError());
+  return ORVB_OK;
+}
+
+}  // namespace orvb
+
+extern "C" int orvb_ln_modulate(const orvb_ln_args* args, void* stream) {
+  int rc = orvb::check_arch();
+  if (rc != ORVB_OK) return rc;
+  return orvb::ln_modulate_launch(args, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int orvb_skinny_linear(const float* x, const void* w, const void* b, float* y, int32_t rows, int32_t n,
+                                  int32_t k, int32_t act, void* stream) {
+  int rc = orvb::check_arch();
+  if (rc != ORVB_OK) return rc;
+  ORVB_REQUIRE(w && y, ORVB_EINVAL, "orvb_skinny_linear: null pointer");
+  orvb::SkinnyJob job{static_cast<const orvb::bf16*>(w), static_cast<const orvb::bf16*>(b), y};
+  return orvb::skinny_linear_launch(x, job, nullptr, 1, rows, n, k, act, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int orvb_patchify(const void* x, void* out, int32_t b, int32_t f, int32_t c, int32_t h, int32_t w,
+                             int32_t p, int32_t patch_t, void* stream) {
+  int rc = orvb::check_arch();
+  if (rc != ORVB_OK) return rc;
+  return orvb::patchify_launch(x, out, b, f, c, h, w, p, patch_t, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int orvb_unpatchify(const void* y, void* out, int32_t b, int32_t f, int32_t c, int32_t h, int32_t w,
+                               int32_t p, int32_t patch_t, void* stream) {
+  int rc = orvb::check_arch();
+  if (rc != ORVB_OK) return rc;
+  return orvb::unpatchify_launch(y, out, b, f, c, h, w, p, patch_t, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int orvb_sampler_step(const orvb_sampler_step_args* a, void* stream) {
+  int rc = orvb::check_arch();
+  if (rc != ORVB_OK) return rc;
+  return orvb::sampler_step_launch(a, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,24 @@
+// Internal launch entry points of the kernels in pointwise.cu / gemm.cu / attention.cu, shared with forward.cu.
+#pragma once
+#include "common.cuh"
+
+namespace orvb {
+
+struct SkinnyJob {
+  const bf16* w;  // [n, k]
+  const bf16* b;  // [n] or null
+  float* y;       // [rows, n]
+};
+
+int ln_modulate_launch(const orvb_ln_args* a, cudaStream_t stream);
+int skinny_linear_launch(const float* x, const SkinnyJob& job, const SkinnyJob* jobs_dev, int num_jobs, int rows,
+                         int n, int k, int act, cudaStream_t stream);
+int patchify_launch(const void* x, void* out, int B, int F, int C, int H, int W, int p, int patch_t,
+                    cudaStream_t stream);
+int unpatchify_launch(const void* y, void* out, int B, int F, int C, int H, int W, int p, int patch_t,
+                      cudaStream_t stream);
+int sampler_step_launch(const orvb_sampler_step_args* a, cudaStream_t stream);
+int attention_launch(const void* qkv, void* out, int batch, int seq_len, int heads, float scale,
+                     cudaStream_t stream);
+
+}  // namespace orvb

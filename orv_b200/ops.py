@@ -23,7 +23,7 @@ def _req(t: torch.Tensor, dtype, name: str):
 
 
 def rowmap(seq_len=0, text_len=0, tokens_per_group=1, groups_per_batch=1) -> L.RowMap:
-    return L.RowMap(seq_len, text_len, max(tokens_per_group, 1), groups_per_batch)
+    return L.RowMap(seq_len, text_len, tokens_per_group, groups_per_batch)
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, epilogue: int = L.EPI_BIAS,

@@ -1,0 +1,77 @@
+"""GPU bring-up check for the tcgen05 attention kernel (run under gpurun)."""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from orv_b200 import ops  # noqa: E402
+
+torch.manual_seed(0)
+dev = "cuda"
+all_ok = True
+
+
+def ref_attn(qkv, B, S, H, scale):
+    D = H * 64
+    q, k, v = qkv.float().view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
+    o = torch.nn.functional.scaled_dot_product_attention(q, k, v, scale=scale)
+    return o.permute(0, 2, 1, 3).reshape(B * S, D)
+
+
+for (B, S, H) in [(1, 128, 1), (1, 256, 2), (1, 200, 1), (2, 384, 3), (1, 1000, 4), (1, 3226, 30), (2, 2026, 48)]:
+    qkv = torch.randn(B * S, 3 * H * 64, device=dev).bfloat16()
+    # make the logits non-trivial: scale q up so softmax is peaky in places
+    qkv[:, : H * 64] *= 2.0
+    try:
+        out = ops.attention(qkv, B, S, H, 0.125)
+        torch.cuda.synchronize()
+    except Exception as e:  # noqa: BLE001
+        print(f"[EXC] B={B} S={S} H={H}: {e}", flush=True)
+        all_ok = False
+        break
+    ref = ref_attn(qkv, B, S, H, 0.125)
+    err = (out.float() - ref).abs()
+    ok = err.max().item() < 2e-2 and torch.isfinite(out.float()).all().item()
+    print(f"[{'OK' if ok else 'FAIL'}] B={B} S={S} H={H}: max_abs_err={err.max().item():.4g} mean_abs_err={err.mean().item():.4g} "
+          f"ref_absmean={ref.abs().mean().item():.4g}", flush=True)
+    if not ok:
+        all_ok = False
+        e2 = err.view(B, S, H, 64)
+        print(" per-head max:", e2.amax(dim=(0, 1, 3)).tolist()[:8])
+        rows = e2.amax(dim=(0, 2, 3))
+        print(" per-row-block(32) max:", [round(rows[i:i + 32].max().item(), 3) for i in range(0, min(S, 512), 32)])
+        cols = e2.amax(dim=(0, 1, 2))
+        print(" per-d max:", [round(x, 3) for x in cols.tolist()])
+
+if all_ok:
+    for (B, S, H) in [(1, 3226, 30), (2, 3226, 30), (2, 2026, 48)]:
+        qkv = torch.randn(B * S, 3 * H * 64, device=dev).bfloat16()
+        out = ops.attention(qkv, B, S, H, 0.125)
+        for _ in range(3):
+            ops.attention(qkv, B, S, H, 0.125, out=out)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        iters = 20
+        e0.record()
+        for _ in range(iters):
+            ops.attention(qkv, B, S, H, 0.125, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        fl = 4.0 * B * H * S * S * 64
+        print(f"time B={B} S={S} H={H}: {ms*1e3:.1f} us  {fl/ms/1e9:.1f} TFLOP/s", flush=True)
+        q, k, v = qkv.view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        for _ in range(3):
+            torch.nn.functional.scaled_dot_product_attention(q, k, v)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            torch.nn.functional.scaled_dot_product_attention(q, k, v)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        print(f"time B={B} S={S} H={H} torch SDPA: {ms*1e3:.1f} us  {fl/ms/1e9:.1f} TFLOP/s", flush=True)
+
+print("ALL_OK" if all_ok else "SOME_FAILED", flush=True)
+sys.exit(0 if all_ok else 1)
