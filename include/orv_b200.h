@@ -204,7 +204,7 @@ typedef struct orvb_weights {
   const void* time2_w;  const void* time2_b;      /* [T, T], [T] */
   const void* ofs1_w;   const void* ofs1_b;       /* [T, ofs], [T] or NULL */
   const void* ofs2_w;   const void* ofs2_b;
-  const void* act1_w;   const void* act1_b;       /* [4T, 28*pt], [4T] */
+  const void* act1_w;   const void* act1_b;       /* [4T, align8(28*pt)] (columns zero-padded to a multiple of 8), [4T] */
   const void* act2_w;   const void* act2_b;       /* [T, 4T], [T] */
   const void* act_mask_embed;                     /* [T] */
   const void* combine_w; const void* combine_b;   /* [D, keys*D], [D] or NULL */
@@ -267,12 +267,15 @@ typedef struct orvb_sampler_step_args {
   const void* model_out;   /* bf16 [cfg_copies * n]  (uncond first, then cond, as torch.cat([latents]*2)) */
   void* latents;           /* bf16 [n] in/out                                                            */
   float* old_x0;           /* fp32 [n] in/out (DPM only; written every step)                             */
-  const float* noise;      /* fp32 [n] (DPM only) or NULL                                                */
+  const void* noise;       /* bf16 [n] (DPM only; the reference draws it in the latent dtype) or NULL    */
   int64_t n;
   int32_t cfg_copies;      /* 1 or 2 */
   float guidance_scale;
-  /* x0 = c_x * x + c_v * v ; x_prev = k_x * x + k_x0 * x0 + k_old * old_x0 + k_noise * noise */
-  float c_x, c_v, k_x, k_x0, k_old, k_noise;
+  /* v = CFG(model_out);  x0 = c_x * x + c_v * v;  d = d_cur * x0 + d_old * old_x0;
+   * x_prev = k_x * x + k_d * d + k_noise * noise.   (DDIM: d_cur = 1, d_old = 0, k_noise = 0.)
+   * Products with the bf16 tensors x and noise are rounded to bf16 first, as torch does for
+   * `float64_scalar * bf16_tensor`; no FMA contraction, so the result matches the torch op sequence bit for bit. */
+  float c_x, c_v, d_cur, d_old, k_x, k_d, k_noise;
 } orvb_sampler_step_args;
 int orvb_sampler_step(const orvb_sampler_step_args* a, void* stream);
 

@@ -109,8 +109,8 @@ class SamplerStepArgs(C.Structure):
     _fields_ = [
         ("model_out", c_void_p), ("latents", c_void_p), ("old_x0", c_void_p), ("noise", c_void_p),
         ("n", C.c_int64), ("cfg_copies", c_int), ("guidance_scale", c_float),
-        ("c_x", c_float), ("c_v", c_float), ("k_x", c_float), ("k_x0", c_float), ("k_old", c_float),
-        ("k_noise", c_float),
+        ("c_x", c_float), ("c_v", c_float), ("d_cur", c_float), ("d_old", c_float), ("k_x", c_float),
+        ("k_d", c_float), ("k_noise", c_float),
     ]
 
 

@@ -1,0 +1,487 @@
+// Whole-model forward: the kernel schedule that replaces CogVideoXTransformer3DModelTraj.forward
+// (reference orv/models/cogvideox_control.py:715-948) for modulate_encoder_hidden_states=True models.
+//
+// Data layout in HBM (all activations in the caller's workspace):
+//   x    [B*S, D]   bf16  joint hidden state, per sample: text rows [0,St) then video rows [St,S) in (f,h,w) order
+//   xn   [B*S, D]   bf16  LayerNorm+modulated copy (GEMM A operand)
+//   qkv  [B*S, 3D]  bf16  Q | K | V, heads are 64-column blocks (read by the attention kernel through TMA)
+//   att  [B*S, D]   bf16  attention output
+//   ffh  [B*S, FF]  bf16  GELU(ff1) activations
+//   mod  [sites][B*G][6D] fp32  AdaLN tables: row b*G is the text/time-only group, rows b*G+1+f the frame groups
+// Per layer: LN+mod -> QKV GEMM (+QK-LN, RoPE) -> attention -> out GEMM (+gate, residual) -> LN+mod ->
+//            FF1 GEMM (+GELU) -> FF2 GEMM (+gate, residual): 7 launches.
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "pointwise.cuh"
+#include "ptx.cuh"
+
+namespace orvb {
+int gemm_run(const orvb_gemm_args* a, cudaStream_t stream);
+}
+
+struct orvb_model {
+  orvb_config cfg;
+  orvb_weights w;
+  std::vector<orvb_block_weights> blocks;
+  std::vector<orvb_block_weights> mv_blocks;
+  bool bound = false;
+  orvb::SkinnyJob* jobs_dev = nullptr;  // [sites] AdaLN job table (device metadata owned by the library)
+  float* jobs_y_base = nullptr;         // modulation-table base the job table currently points at
+  size_t jobs_site_stride = 0;
+  int launches = 0;
+};
+
+namespace orvb {
+
+static size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+struct Geometry {
+  int B, V, F, Fp, H, W, Hp, Wp, St, Sv, S, R, D, FF, T, Kp, Nout, G, Fa, sites;
+};
+
+static int make_geometry(const orvb_config& c, const orvb_shape& s, Geometry* g) {
+  ORVB_REQUIRE(s.batch > 0 && s.frames > 0 && s.height > 0 && s.width > 0 && s.text_len >= 0, ORVB_ESHAPE,
+               "orvb_forward: bad shape batch=%d frames=%d h=%d w=%d text=%d", s.batch, s.frames, s.height, s.width,
+               s.text_len);
+  ORVB_REQUIRE(s.height % c.patch_size == 0 && s.width % c.patch_size == 0, ORVB_ESHAPE,
+               "orvb_forward: latent height/width must be divisible by the patch size");
+  const int pt = c.patch_size_t > 0 ? c.patch_size_t : 1;
+  ORVB_REQUIRE(s.frames % pt == 0, ORVB_ESHAPE, "orvb_forward: frames (%d) not divisible by patch_size_t (%d)",
+               s.frames, pt);
+  ORVB_REQUIRE(s.views <= 1, ORVB_ESHAPE, "orvb_forward: multiview (views=%d) is not built yet", s.views);
+  g->B = s.batch; g->V = s.views > 0 ? s.views : 1; g->F = s.frames; g->Fp = s.frames / pt;
+  g->H = s.height; g->W = s.width; g->Hp = s.height / c.patch_size; g->Wp = s.width / c.patch_size;
+  g->St = s.text_len; g->Sv = g->Fp * g->Hp * g->Wp; g->S = g->St + g->Sv; g->R = g->B * g->S;
+  g->D = c.dim; g->FF = c.ff_dim; g->T = c.time_embed_dim;
+  g->Kp = c.in_channels * pt * c.patch_size * c.patch_size;
+  g->Nout = c.out_channels * pt * c.patch_size * c.patch_size;
+  g->Fa = s.action_frames;
+  ORVB_REQUIRE(g->Fa == 0 || g->Sv % g->Fa == 0, ORVB_ESHAPE,
+               "orvb_forward: video tokens (%d) not divisible by action frames (%d)", g->Sv, g->Fa);
+  g->G = g->Fa + 1;
+  g->sites = 2 * c.layers + 1;
+  return ORVB_OK;
+}
+
+struct Workspace {
+  bf16 *x, *xn, *qkv, *att, *ffh, *patches, *ctrl, *yout;
+  float *tsin, *t1, *temb, *osin, *o1, *oemb, *act_in, *act_h, *act_emb, *emb, *mod;
+  size_t bytes;
+};
+
+static void carve(const orvb_config& c, const Geometry& g, uint8_t* base, Workspace* ws) {
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    uint8_t* p = base ? base + off : nullptr;
+    off += align_up(n);
+    return p;
+  };
+  const size_t R = g.R, D = g.D;
+  ws->x = reinterpret_cast<bf16*>(take(R * D * 2));
+  ws->xn = reinterpret_cast<bf16*>(take(R * D * 2));
+  ws->qkv = reinterpret_cast<bf16*>(take(R * 3 * D * 2));
+  ws->att = reinterpret_cast<bf16*>(take(R * D * 2));
+  ws->ffh = reinterpret_cast<bf16*>(take(R * static_cast<size_t>(g.FF) * 2));
+  ws->patches = reinterpret_cast<bf16*>(take(static_cast<size_t>(g.B) * g.Sv * g.Kp * 2));
+  const int keys = c.visual_guidance ? c.num_control_keys : 0;
+  ws->ctrl = reinterpret_cast<bf16*>(take(static_cast<size_t>(g.B) * g.Sv * D * keys * 2));
+  ws->yout = reinterpret_cast<bf16*>(take(static_cast<size_t>(g.B) * g.Sv * g.Nout * 2));
+  ws->tsin = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * D * 4));
+  ws->t1 = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * g.T * 4));
+  ws->temb = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * g.T * 4));
+  const int od = c.has_ofs ? c.ofs_embed_dim : 8;
+  ws->osin = reinterpret_cast<float*>(take(static_cast<size_t>(od) * 4));
+  ws->o1 = reinterpret_cast<float*>(take(static_cast<size_t>(g.T) * 4));
+  ws->oemb = reinterpret_cast<float*>(take(static_cast<size_t>(g.T) * 4));
+  const int pt = c.patch_size_t > 0 ? c.patch_size_t : 1;
+  const int act_k = c.action_state_dim * c.action_compress * pt;
+  const int fa = g.Fa > 0 ? g.Fa : 1;
+  ws->act_in = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * fa * align_up(act_k, 8) * 4));
+  ws->act_h = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * fa * c.action_hidden * 4));
+  ws->act_emb = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * fa * g.T * 4));
+  ws->emb = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * g.G * g.T * 4));
+  ws->mod = reinterpret_cast<float*>(take(static_cast<size_t>(g.sites) * g.B * g.G * 6 * D * 4));
+  ws->bytes = off;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// small prologue kernels
+// ---------------------------------------------------------------------------------------------------
+// diffusers get_timestep_embedding: emb = t * exp(-ln(1e4) * i / (half - shift)),
+// [sin | cos], flipped to [cos | sin] when flip_sin_to_cos.  The reference casts the result to the model
+// dtype (bf16) before time_embedding.linear_1 (cogvideox_control.py:768); that rounding is kept.
+__global__ void timestep_sinusoid_kernel(const float* __restrict__ t, float* __restrict__ out, int rows, int dim,
+                                         int flip, float shift, float scalar_t, int use_scalar) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = dim / 2;
+  if (idx >= rows * half) return;
+  const int r = idx / half, i = idx - r * half;
+  const float tv = use_scalar ? scalar_t : t[r];
+  const float freq = expf(-logf(10000.0f) * static_cast<float>(i) / (static_cast<float>(half) - shift));
+  const float a = tv * freq;
+  const float sn = __bfloat162float(__float2bfloat16(sinf(a)));
+  const float cs = __bfloat162float(__float2bfloat16(cosf(a)));
+  float* o = out + static_cast<size_t>(r) * dim;
+  if (flip) {
+    o[i] = cs;
+    o[half + i] = sn;
+  } else {
+    o[i] = sn;
+    o[half + i] = cs;
+  }
+}
+
+// actions bf16 [rows, k] -> fp32 [rows, kpad] (zero padded so the skinny linear can use 8-wide loads)
+__global__ void actions_to_f32_kernel(const bf16* __restrict__ a, float* __restrict__ out, int rows, int k, int kpad) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * kpad) return;
+  const int r = idx / kpad, c = idx - r * kpad;
+  out[idx] = c < k ? __bfloat162float(a[static_cast<size_t>(r) * k + c]) : 0.f;
+}
+
+// emb[b*G + 0]   = silu(temb[b] + ofs)                         (text / time-only group)
+// emb[b*G + 1+f] = silu(temb[b] + ofs + action_emb[b,f])       (frame groups; masked samples use mask_embed)
+// Reference: cogvideox_control.py:121-130 (LayerNormZero), :166-170 (AdaLayerNorm), components.py:66-69 (mask).
+__global__ void build_emb_kernel(const float* __restrict__ temb, const float* __restrict__ oemb,
+                                 const float* __restrict__ act_emb, const uint8_t* __restrict__ mask,
+                                 const bf16* __restrict__ mask_embed, float* __restrict__ emb, int B, int G, int T) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * G * T) return;
+  const int c = idx % T;
+  const int g = (idx / T) % G;
+  const int b = idx / (T * G);
+  float v = temb[b * T + c] + (oemb != nullptr ? oemb[c] : 0.f);
+  if (g > 0) {
+    float a;
+    if (mask != nullptr && mask[b] != 0) a = __bfloat162float(mask_embed[c]);
+    else a = act_emb[(static_cast<size_t>(b) * (G - 1) + (g - 1)) * T + c];
+    v += a;
+  }
+  emb[idx] = silu(v);
+}
+
+// ctrl[r, col_off + c] += x[video row r, c]   (hidden_states.repeat(1,1,keys) + controls, :853-855)
+__global__ void add_hidden_kernel(bf16* __restrict__ ctrl, const bf16* __restrict__ x, int rows, int D, int ld_ctrl,
+                                  int col_off, int Sv, int S, int St) {
+  const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  const int chunks = D / 8;
+  if (idx >= static_cast<long>(rows) * chunks) return;
+  const int r = static_cast<int>(idx / chunks), c = static_cast<int>(idx - static_cast<long>(r) * chunks);
+  const int b = r / Sv;
+  const size_t xr = static_cast<size_t>(b) * S + St + (r - b * Sv);
+  uint4 a = *reinterpret_cast<const uint4*>(ctrl + static_cast<size_t>(r) * ld_ctrl + col_off + c * 8);
+  const uint4 h = *reinterpret_cast<const uint4*>(x + xr * D + c * 8);
+  a.x = pack_bf16(bf16_lo(a.x) + bf16_lo(h.x), bf16_hi(a.x) + bf16_hi(h.x));
+  a.y = pack_bf16(bf16_lo(a.y) + bf16_lo(h.y), bf16_hi(a.y) + bf16_hi(h.y));
+  a.z = pack_bf16(bf16_lo(a.z) + bf16_lo(h.z), bf16_hi(a.z) + bf16_hi(h.z));
+  a.w = pack_bf16(bf16_lo(a.w) + bf16_lo(h.w), bf16_hi(a.w) + bf16_hi(h.w));
+  *reinterpret_cast<uint4*>(ctrl + static_cast<size_t>(r) * ld_ctrl + col_off + c * 8) = a;
+}
+
+#define ORVB_TRY(expr)            \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != ORVB_OK) return _rc; \
+    ++m->launches;                \
+  } while (0)
+
+static orvb_gemm_args gemm_base(const void* a, const void* w, const void* bias, void* out, int M, int N, int K,
+                                int lda, int ldo, int epi) {
+  orvb_gemm_args g;
+  memset(&g, 0, sizeof(g));
+  g.a = a; g.w = w; g.bias = bias; g.out = out;
+  g.m = M; g.n = N; g.k = K; g.lda = lda; g.ldw = K; g.ldo = ldo; g.epilogue = epi;
+  return g;
+}
+
+static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t st) {
+  const orvb_config& c = m->cfg;
+  const orvb_weights& w = m->w;
+  Geometry g;
+  int rc = make_geometry(c, a->shape, &g);
+  if (rc != ORVB_OK) return rc;
+  ORVB_REQUIRE(a->hidden_states && a->text && a->timesteps && a->out && a->workspace, ORVB_EINVAL,
+               "orvb_forward: null input/output/workspace pointer");
+  Workspace ws;
+  carve(c, g, static_cast<uint8_t*>(a->workspace), &ws);
+  ORVB_REQUIRE(a->workspace_bytes >= ws.bytes, ORVB_ENOMEM, "orvb_forward: workspace too small (%zu < %zu)",
+               a->workspace_bytes, ws.bytes);
+  ORVB_REQUIRE(reinterpret_cast<uintptr_t>(a->workspace) % 256 == 0, ORVB_ESHAPE,
+               "orvb_forward: workspace must be 256-byte aligned");
+  ORVB_REQUIRE(!c.use_rope || (a->rope_cos && a->rope_sin), ORVB_EINVAL,
+               "orvb_forward: this model uses rotary embeddings but rope_cos/rope_sin are NULL");
+  ORVB_REQUIRE((g.Fa > 0) == (a->actions != nullptr), ORVB_EINVAL,
+               "orvb_forward: shape.action_frames and the actions pointer disagree");
+  const int D = g.D, T = g.T;
+  const int pt = c.patch_size_t > 0 ? c.patch_size_t : 1;
+  m->launches = 0;
+
+  // ---- 1. time / ofs / action embeddings -> per-group conditioning rows -----------------------------
+  {
+    const int n = g.B * (D / 2);
+    timestep_sinusoid_kernel<<<(n + 255) / 256, 256, 0, st>>>(a->timesteps, ws.tsin, g.B, D, c.flip_sin_to_cos,
+                                                              c.freq_shift, 0.f, 0);
+    ORVB_CHECK_CUDA(cudaGetLastError());
+    ++m->launches;
+    ORVB_TRY(skinny_linear_launch(ws.tsin, SkinnyJob{static_cast<const bf16*>(w.time1_w), static_cast<const bf16*>(w.time1_b), ws.t1},
+                                  nullptr, 1, g.B, T, D, 1, st));
+    ORVB_TRY(skinny_linear_launch(ws.t1, SkinnyJob{static_cast<const bf16*>(w.time2_w), static_cast<const bf16*>(w.time2_b), ws.temb},
+                                  nullptr, 1, g.B, T, T, 0, st));
+  }
+  const float* oemb = nullptr;
+  if (c.has_ofs) {
+    ORVB_REQUIRE(w.ofs1_w && w.ofs2_w, ORVB_EINVAL, "orvb_forward: ofs embedding weights are not bound");
+    const int od = c.ofs_embed_dim;
+    timestep_sinusoid_kernel<<<(od / 2 + 255) / 256, 256, 0, st>>>(nullptr, ws.osin, 1, od, c.flip_sin_to_cos,
+                                                                    c.freq_shift, a->ofs, 1);
+    ORVB_CHECK_CUDA(cudaGetLastError());
+    ++m->launches;
+    ORVB_TRY(skinny_linear_launch(ws.osin, SkinnyJob{static_cast<const bf16*>(w.ofs1_w), static_cast<const bf16*>(w.ofs1_b), ws.o1},
+                                  nullptr, 1, 1, T, od, 1, st));
+    ORVB_TRY(skinny_linear_launch(ws.o1, SkinnyJob{static_cast<const bf16*>(w.ofs2_w), static_cast<const bf16*>(w.ofs2_b), ws.oemb},
+                                  nullptr, 1, 1, T, T, 0, st));
+    oemb = ws.oemb;
+  }
+  if (g.Fa > 0) {
+    ORVB_REQUIRE(w.act1_w && w.act2_w, ORVB_EINVAL, "orvb_forward: action_embed weights are not bound");
+    ORVB_REQUIRE(a->action_mask == nullptr || w.act_mask_embed != nullptr, ORVB_EINVAL,
+                 "orvb_forward: action_mask given but mask_embed is not bound");
+    const int act_k = c.action_state_dim * c.action_compress * pt;
+    const int kpad = static_cast<int>(align_up(act_k, 8));
+    const int rows = g.B * g.Fa;
+    actions_to_f32_kernel<<<(rows * kpad + 255) / 256, 256, 0, st>>>(static_cast<const bf16*>(a->actions), ws.act_in,
+                                                                     rows, act_k, kpad);
+    ORVB_CHECK_CUDA(cudaGetLastError());
+    ++m->launches;
+    ORVB_TRY(skinny_linear_launch(ws.act_in, SkinnyJob{static_cast<const bf16*>(w.act1_w), static_cast<const bf16*>(w.act1_b), ws.act_h},
+                                  nullptr, 1, rows, c.action_hidden, kpad, 2, st));
+    ORVB_TRY(skinny_linear_launch(ws.act_h, SkinnyJob{static_cast<const bf16*>(w.act2_w), static_cast<const bf16*>(w.act2_b), ws.act_emb},
+                                  nullptr, 1, rows, T, c.action_hidden, 0, st));
+  }
+  {
+    const int n = g.B * g.G * T;
+    build_emb_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws.temb, oemb, ws.act_emb, a->action_mask,
+                                                      static_cast<const bf16*>(w.act_mask_embed), ws.emb, g.B, g.G, T);
+    ORVB_CHECK_CUDA(cudaGetLastError());
+    ++m->launches;
+  }
+
+  // ---- 2. all AdaLN tables of the forward in one batched launch (they depend only on emb) ----------
+  const size_t site_stride = static_cast<size_t>(g.B) * g.G * 6 * D;
+  if (m->jobs_y_base != ws.mod || m->jobs_site_stride != site_stride) {
+    std::vector<SkinnyJob> jobs(2 * c.layers);
+    for (int l = 0; l < c.layers; ++l) {
+      const orvb_block_weights& bw = m->blocks[l];
+      jobs[2 * l] = SkinnyJob{static_cast<const bf16*>(bw.norm1_lin_w), static_cast<const bf16*>(bw.norm1_lin_b),
+                              ws.mod + (2 * l) * site_stride};
+      jobs[2 * l + 1] = SkinnyJob{static_cast<const bf16*>(bw.norm2_lin_w), static_cast<const bf16*>(bw.norm2_lin_b),
+                                  ws.mod + (2 * l + 1) * site_stride};
+    }
+    // synchronous small copy: happens once per (model, workspace) pair, outside any graph capture
+    ORVB_CHECK_CUDA(cudaMemcpy(m->jobs_dev, jobs.data(), jobs.size() * sizeof(SkinnyJob), cudaMemcpyHostToDevice));
+    m->jobs_y_base = ws.mod;
+    m->jobs_site_stride = site_stride;
+  }
+  ORVB_TRY(skinny_linear_launch(ws.emb, SkinnyJob{nullptr, nullptr, nullptr}, m->jobs_dev, 2 * c.layers, g.B * g.G,
+                                6 * D, T, 0, st));
+  float* mod_out = ws.mod + static_cast<size_t>(2 * c.layers) * site_stride;  // norm_out table, row pitch 6D
+  {
+    // norm_out.linear is [2D, T]; written with pitch 2D into its slot (mod_ld = 2D below)
+    ORVB_TRY(skinny_linear_launch(ws.emb, SkinnyJob{static_cast<const bf16*>(w.norm_out_lin_w), static_cast<const bf16*>(w.norm_out_lin_b), mod_out},
+                                  nullptr, 1, g.B * g.G, 2 * D, T, 0, st));
+  }
+
+  orvb_rowmap rm;
+  rm.seq_len = g.S; rm.text_len = g.St;
+  rm.tokens_per_group = g.Fa > 0 ? g.Sv / g.Fa : 0;
+  rm.groups_per_batch = g.G;
+
+  // ---- 3. patch embed + text projection into the joint sequence -----------------------------------
+  ORVB_TRY(patchify_launch(a->hidden_states, ws.patches, g.B, g.F, c.in_channels, g.H, g.W, c.patch_size,
+                           c.patch_size_t, st));
+  {
+    orvb_gemm_args ga = gemm_base(ws.patches, w.patch_w, w.patch_b, ws.x, g.B * g.Sv, D, g.Kp, g.Kp, D,
+                                  w.pos_embed ? ORVB_EPI_GATE_RESID : ORVB_EPI_BIAS);
+    ga.src_rows = g.Sv; ga.dst_rows = g.S; ga.dst_offset = g.St;
+    if (w.pos_embed) {
+      ga.resid = w.pos_embed; ga.ldr = D; ga.resid_mod = g.Sv; ga.resid_views = 1;
+    }
+    ORVB_TRY(gemm_run(&ga, st));
+  }
+  {
+    orvb_gemm_args ga = gemm_base(a->text, w.text_w, w.text_b, ws.x, g.B * g.St, D, c.text_embed_dim,
+                                  c.text_embed_dim, D, ORVB_EPI_BIAS);
+    ga.src_rows = g.St; ga.dst_rows = g.S; ga.dst_offset = 0;
+    if (g.St > 0) ORVB_TRY(gemm_run(&ga, st));
+  }
+
+  // ---- 4. visual controls (depth / semantic latents), cogvideox_control.py:827-858 -----------------
+  if (c.visual_guidance && (a->depths != nullptr || a->labels != nullptr)) {
+    const void* ctl[2] = {a->depths, a->labels};
+    int present = (a->depths != nullptr) + (a->labels != nullptr);
+    ORVB_REQUIRE(present == c.num_control_keys, ORVB_EINVAL,
+                 "orvb_forward: Mismatched number of controls: %d given but num_control_keys=%d", present,
+                 c.num_control_keys);
+    ORVB_REQUIRE(w.combine_w != nullptr, ORVB_EINVAL, "orvb_forward: initial_combine_linear is not bound");
+    const int ldc = c.num_control_keys * D;
+    int slot = 0;
+    for (int k = 0; k < 2; ++k) {
+      if (ctl[k] == nullptr) continue;
+      ORVB_TRY(patchify_launch(ctl[k], ws.patches, g.B, g.F, c.in_channels, g.H, g.W, c.patch_size, c.patch_size_t, st));
+      orvb_gemm_args ga = gemm_base(ws.patches, w.patch_w, w.patch_b, ws.ctrl + slot * D, g.B * g.Sv, D, g.Kp, g.Kp,
+                                    ldc, w.pos_embed ? ORVB_EPI_GATE_RESID : ORVB_EPI_BIAS);
+      if (w.pos_embed) {
+        ga.resid = w.pos_embed; ga.ldr = D; ga.resid_mod = g.Sv; ga.resid_views = 1;
+      }
+      ORVB_TRY(gemm_run(&ga, st));
+      const long n = static_cast<long>(g.B) * g.Sv * (D / 8);
+      add_hidden_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(ws.ctrl, ws.x, g.B * g.Sv, D, ldc,
+                                                                                slot * D, g.Sv, g.S, g.St);
+      ORVB_CHECK_CUDA(cudaGetLastError());
+      ++m->launches;
+      ++slot;
+    }
+    orvb_gemm_args ga = gemm_base(ws.ctrl, w.combine_w, w.combine_b, ws.x, g.B * g.Sv, D, ldc, ldc, D,
+                                  ORVB_EPI_GATE_RESID);
+    ga.src_rows = g.Sv; ga.dst_rows = g.S; ga.dst_offset = g.St;
+    ga.resid = ws.x; ga.ldr = D;  // hidden_states + combine(...)  (in place, row-aligned)
+    ORVB_TRY(gemm_run(&ga, st));
+  }
+
+  // ---- 5. transformer blocks -----------------------------------------------------------------------
+  const float scale = 1.0f / sqrtf(static_cast<float>(c.head_dim));
+  for (int l = 0; l < c.layers; ++l) {
+    const orvb_block_weights& bw = m->blocks[l];
+    const float* mod1 = ws.mod + (2 * l) * site_stride;
+    const float* mod2 = ws.mod + (2 * l + 1) * site_stride;
+    orvb_ln_args ln;
+    memset(&ln, 0, sizeof(ln));
+    ln.x = ws.x; ln.y = ws.xn; ln.ln_w = bw.norm1_ln_w; ln.ln_b = bw.norm1_ln_b;
+    ln.rows = g.R; ln.dim = D; ln.eps = c.norm_eps;
+    ln.mod = mod1; ln.mod_ld = 6 * D; ln.text_off = 3 * D; ln.video_off = 0; ln.rowmap = rm;
+    ORVB_TRY(ln_modulate_launch(&ln, st));
+
+    orvb_gemm_args q = gemm_base(ws.xn, bw.qkv_w, bw.qkv_b, ws.qkv, g.R, 3 * D, D, D, 3 * D, ORVB_EPI_QKV);
+    q.qk_dim = D; q.q_norm_w = bw.q_norm_w; q.q_norm_b = bw.q_norm_b; q.k_norm_w = bw.k_norm_w; q.k_norm_b = bw.k_norm_b;
+    q.qk_eps = 1e-6f; q.rowmap = rm;
+    if (c.use_rope) { q.rope_cos = a->rope_cos; q.rope_sin = a->rope_sin; }
+    ORVB_TRY(gemm_run(&q, st));
+
+    ORVB_TRY(attention_launch(ws.qkv, ws.att, g.B, g.S, c.heads, scale, st));
+
+    orvb_gemm_args o = gemm_base(ws.att, bw.out_w, bw.out_b, ws.x, g.R, D, D, D, D, ORVB_EPI_GATE_RESID);
+    o.resid = ws.x; o.ldr = D; o.gate = mod1; o.gate_ld = 6 * D; o.gate_text_off = 5 * D; o.gate_video_off = 2 * D;
+    o.rowmap = rm;
+    ORVB_TRY(gemm_run(&o, st));
+
+    ln.ln_w = bw.norm2_ln_w; ln.ln_b = bw.norm2_ln_b; ln.mod = mod2;
+    ORVB_TRY(ln_modulate_launch(&ln, st));
+
+    orvb_gemm_args f1 = gemm_base(ws.xn, bw.ff1_w, bw.ff1_b, ws.ffh, g.R, g.FF, D, D, g.FF, ORVB_EPI_GELU);
+    ORVB_TRY(gemm_run(&f1, st));
+    orvb_gemm_args f2 = gemm_base(ws.ffh, bw.ff2_w, bw.ff2_b, ws.x, g.R, D, g.FF, g.FF, D, ORVB_EPI_GATE_RESID);
+    f2.resid = ws.x; f2.ldr = D; f2.gate = mod2; f2.gate_ld = 6 * D; f2.gate_text_off = 5 * D; f2.gate_video_off = 2 * D;
+    f2.rowmap = rm;
+    ORVB_TRY(gemm_run(&f2, st));
+
+    if (a->tap_hidden != nullptr && a->tap_layer == l) {
+      ORVB_CHECK_CUDA(cudaMemcpyAsync(a->tap_hidden, ws.x, static_cast<size_t>(g.R) * D * 2, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+
+  // ---- 6. norm_final -> norm_out (AdaLN, shift first) -> proj_out -> unpatchify --------------------
+  {
+    orvb_ln_args ln;
+    memset(&ln, 0, sizeof(ln));
+    ln.x = ws.x; ln.y = ws.xn; ln.rows = g.B * g.Sv; ln.dim = D;
+    ln.pre_w = w.norm_final_w; ln.pre_b = w.norm_final_b; ln.pre_eps = c.norm_eps;
+    ln.ln_w = w.norm_out_ln_w; ln.ln_b = w.norm_out_ln_b; ln.eps = c.norm_eps;
+    ln.mod = mod_out; ln.mod_ld = 2 * D; ln.text_off = 0; ln.video_off = 0; ln.rowmap = rm; ln.in_video_only = 1;
+    ORVB_TRY(ln_modulate_launch(&ln, st));
+    orvb_gemm_args po = gemm_base(ws.xn, w.proj_out_w, w.proj_out_b, ws.yout, g.B * g.Sv, g.Nout, D, D, g.Nout,
+                                  ORVB_EPI_BIAS);
+    ORVB_TRY(gemm_run(&po, st));
+    ORVB_TRY(unpatchify_launch(ws.yout, a->out, g.B, g.F, c.out_channels, g.H, g.W, c.patch_size, c.patch_size_t, st));
+  }
+  return ORVB_OK;
+}
+
+}  // namespace orvb
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------
+extern "C" int orvb_model_create(const orvb_config* cfg, orvb_model** out) {
+  using namespace orvb;
+  ORVB_REQUIRE(cfg && out, ORVB_EINVAL, "orvb_model_create: null pointer");
+  ORVB_REQUIRE(cfg->head_dim == 64, ORVB_ESHAPE, "orvb_model_create: attention_head_dim must be 64 (got %d)", cfg->head_dim);
+  ORVB_REQUIRE(cfg->dim == cfg->heads * cfg->head_dim && cfg->dim % 64 == 0, ORVB_ESHAPE,
+               "orvb_model_create: dim must equal heads*head_dim");
+  ORVB_REQUIRE(cfg->layers > 0 && cfg->ff_dim % 8 == 0 && cfg->time_embed_dim % 8 == 0 && cfg->text_embed_dim % 8 == 0,
+               ORVB_ESHAPE, "orvb_model_create: bad layer/ff/time/text dims");
+  ORVB_REQUIRE(cfg->patch_size == 2, ORVB_ESHAPE, "orvb_model_create: patch_size must be 2");
+  ORVB_REQUIRE(!cfg->multiview, ORVB_EINVAL, "orvb_model_create: multiview models are not built yet (SURVEY §8 a11)");
+  int rc = check_arch();
+  if (rc != ORVB_OK) return rc;
+  orvb_model* m = new orvb_model();
+  m->cfg = *cfg;
+  cudaError_t e = cudaMalloc(&m->jobs_dev, sizeof(SkinnyJob) * 3 * cfg->layers);
+  if (e != cudaSuccess) {
+    delete m;
+    set_error("orvb_model_create: cudaMalloc(job table) failed: %s", cudaGetErrorString(e));
+    return ORVB_ECUDA;
+  }
+  *out = m;
+  return ORVB_OK;
+}
+
+extern "C" void orvb_model_destroy(orvb_model* m) {
+  if (m == nullptr) return;
+  if (m->jobs_dev) cudaFree(m->jobs_dev);
+  delete m;
+}
+
+extern "C" int orvb_model_bind_weights(orvb_model* m, const orvb_weights* w) {
+  using namespace orvb;
+  ORVB_REQUIRE(m && w && w->blocks_host, ORVB_EINVAL, "orvb_model_bind_weights: null pointer");
+  ORVB_REQUIRE(w->patch_w && w->text_w && w->time1_w && w->time2_w && w->norm_final_w && w->norm_out_lin_w &&
+                   w->norm_out_ln_w && w->proj_out_w,
+               ORVB_EINVAL, "orvb_model_bind_weights: a required top-level weight pointer is NULL");
+  m->w = *w;
+  m->blocks.assign(w->blocks_host, w->blocks_host + m->cfg.layers);
+  for (int l = 0; l < m->cfg.layers; ++l) {
+    const orvb_block_weights& b = m->blocks[l];
+    ORVB_REQUIRE(b.norm1_lin_w && b.norm1_ln_w && b.qkv_w && b.q_norm_w && b.k_norm_w && b.out_w && b.norm2_lin_w &&
+                     b.norm2_ln_w && b.ff1_w && b.ff2_w,
+                 ORVB_EINVAL, "orvb_model_bind_weights: block %d has a NULL weight pointer", l);
+  }
+  m->w.blocks_host = nullptr;
+  m->w.mv_blocks_host = nullptr;
+  m->jobs_y_base = nullptr;
+  m->bound = true;
+  return ORVB_OK;
+}
+
+extern "C" size_t orvb_workspace_bytes(const orvb_model* m, const orvb_shape* s) {
+  using namespace orvb;
+  if (m == nullptr || s == nullptr) return 0;
+  Geometry g;
+  if (make_geometry(m->cfg, *s, &g) != ORVB_OK) return 0;
+  Workspace ws;
+  carve(m->cfg, g, nullptr, &ws);
+  return ws.bytes;
+}
+
+extern "C" int orvb_forward(orvb_model* m, const orvb_forward_args* a, void* stream) {
+  using namespace orvb;
+  ORVB_REQUIRE(m && a, ORVB_EINVAL, "orvb_forward: null pointer");
+  ORVB_REQUIRE(m->bound, ORVB_EINVAL, "orvb_forward: weights are not bound");
+  int rc = check_arch();
+  if (rc != ORVB_OK) return rc;
+  return forward_impl(m, a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int orvb_last_launch_count(const orvb_model* m) { return m ? m->launches : 0; }

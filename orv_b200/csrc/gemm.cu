@@ -452,6 +452,15 @@ int gemm_prepare(const orvb_gemm_args* a, int bn_override, CUtensorMap* ta, CUte
   return ORVB_OK;
 }
 
+int gemm_run(const orvb_gemm_args* a, cudaStream_t stream) {
+  CUtensorMap ta, tb;
+  GemmDev p;
+  int bn;
+  int rc = gemm_prepare(a, 0, &ta, &tb, &p, &bn);
+  if (rc != ORVB_OK) return rc;
+  return gemm_launch_prepared(ta, tb, p, bn, a->epilogue, stream);
+}
+
 }  // namespace orvb
 
 extern "C" int orvb_gemm_bf16(const orvb_gemm_args* args, void* stream) {

@@ -107,8 +107,8 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const LnDev p) {
         unpack8(*reinterpret_cast<const uint4*>(p.pre_b + c * 8), b);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          // the reference materialises norm_final's output in bf16 before norm_out reads it
-          v[i][j] = __bfloat162float(__float2bfloat16((v[i][j] - mean) * rstd * w[j] + b[j]));
+          // kept in fp32 (the bf16 reference rounds here; the fp32 oracle does not)
+          v[i][j] = (v[i][j] - mean) * rstd * w[j] + b[j];
         }
       }
     }
@@ -371,18 +371,18 @@ __global__ void sampler_step_kernel(const orvb_sampler_step_args a) {
   if (a.cfg_copies == 2) {
     const float u = __bfloat162float(mo[i]);
     const float c = __bfloat162float(mo[a.n + i]);
-    v = u + a.guidance_scale * (c - u);
+    v = __fadd_rn(u, __fmul_rn(a.guidance_scale, __fsub_rn(c, u)));
   } else {
     v = __bfloat162float(mo[i]);
   }
   const float x = __bfloat162float(lat[i]);
   // pred_original_sample = sqrt(alpha_t) * sample - sqrt(1 - alpha_t) * model_output
-  const float x0 = rbf(a.c_x * x) + a.c_v * v;
+  const float x0 = __fadd_rn(rbf(__fmul_rn(a.c_x, x)), __fmul_rn(a.c_v, v));
   float d = x0;
-  if (a.k_old != 0.f) d = a.k_x0_cur * x0 + a.k_old * a.old_x0[i];
-  // prev = m1 * sample + k_d * d + m_noise * noise      (DDIM: k_noise = 0, d = x0)
-  float prev = rbf(a.k_x * x) + a.k_x0 * d;
-  if (a.noise != nullptr) prev += rbf(a.k_noise * __bfloat162float(static_cast<const bf16*>(a.noise)[i]));
+  if (a.d_old != 0.f) d = __fadd_rn(__fmul_rn(a.d_cur, x0), __fmul_rn(a.d_old, a.old_x0[i]));
+  float prev = __fadd_rn(rbf(__fmul_rn(a.k_x, x)), __fmul_rn(a.k_d, d));
+  if (a.noise != nullptr)
+    prev = __fadd_rn(prev, rbf(__fmul_rn(a.k_noise, __bfloat162float(static_cast<const bf16*>(a.noise)[i]))));
   if (a.old_x0 != nullptr) a.old_x0[i] = x0;
   lat[i] = __float2bfloat16(prev);
 }
@@ -390,7 +390,7 @@ __global__ void sampler_step_kernel(const orvb_sampler_step_args a) {
 int sampler_step_launch(const orvb_sampler_step_args* a, cudaStream_t stream) {
   ORVB_REQUIRE(a && a->model_out && a->latents && a->n > 0, ORVB_EINVAL, "orvb_sampler_step: bad arguments");
   ORVB_REQUIRE(a->cfg_copies == 1 || a->cfg_copies == 2, ORVB_EINVAL, "orvb_sampler_step: cfg_copies must be 1 or 2");
-  ORVB_REQUIRE(a->k_old == 0.f || a->old_x0 != nullptr, ORVB_EINVAL, "orvb_sampler_step: k_old needs old_x0");
+  ORVB_REQUIRE(a->d_old == 0.f || a->old_x0 != nullptr, ORVB_EINVAL, "orvb_sampler_step: d_old needs old_x0");
   sampler_step_kernel<<<static_cast<unsigned>((a->n + 255) / 256), 256, 0, stream>>>(*a);
   ORVB_CHECK_CUDA(cudaGetLastError());
   return ORVB_OK;

@@ -1,0 +1,637 @@
+"""`CogVideoXTransformer3DModelTraj` — drop-in for reference orv/models/cogvideox_control.py:448-1087.
+
+Same constructor keys (:453-494), `.config`, attribute names, `state_dict` keys, `forward` signature (:715-728)
+and return tuple (:944-948) as the reference class; the arithmetic runs in liborv_b200.so (hand-written sm_100a
+kernels, see orv_b200/csrc) through the C ABI of include/orv_b200.h.  There is no PyTorch fallback: without the
+library or off a B200 the forward raises.
+
+The nn.Modules below are parameter containers only (they give the checkpoint its diffusers key names); after
+packing, every bf16 parameter is a view into one contiguous weight arena (to_q/to_k/to_v rows of one fused
+[3D, D] matrix), which is what the kernels read and what `broadcast_weights` sends over NCCL.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import fnmatch
+import json
+import os
+from types import SimpleNamespace
+from typing import Any, Dict, Optional, Tuple, Union
+
+import torch
+from torch import nn
+
+from .. import _lib as L
+from .components import ActionEmbed, ActionRecon, Transformer3DModelTrajOutput
+from .embeddings import sincos_pos_embed_3d
+
+
+class FrozenConfig(dict):
+    """dict with attribute access, like diffusers' FrozenDict (`model.config.patch_size_t`, `dict(model.config)`)."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+
+# ------------------------------------------------------------------------------------------------------------
+# parameter containers (names = diffusers module attributes; reference cogvideox_control.py:290-305,378-391,531-606)
+# ------------------------------------------------------------------------------------------------------------
+class _TimestepEmbedding(nn.Module):
+    def __init__(self, in_dim, dim):
+        super().__init__()
+        self.linear_1 = nn.Linear(in_dim, dim)
+        self.linear_2 = nn.Linear(dim, dim)
+
+
+class _PatchEmbed(nn.Module):
+    def __init__(self, patch_size, patch_size_t, in_channels, embed_dim, text_embed_dim, bias, sample_width,
+                 sample_height, sample_frames, temporal_compression_ratio, max_text_seq_length,
+                 spatial_interpolation_scale, temporal_interpolation_scale, use_positional_embeddings,
+                 use_learned_positional_embeddings):
+        super().__init__()
+        self.patch_size, self.patch_size_t, self.embed_dim = patch_size, patch_size_t, embed_dim
+        self.sample_height, self.sample_width, self.sample_frames = sample_height, sample_width, sample_frames
+        self.temporal_compression_ratio = temporal_compression_ratio
+        self.max_text_seq_length = max_text_seq_length
+        self.spatial_interpolation_scale = spatial_interpolation_scale
+        self.temporal_interpolation_scale = temporal_interpolation_scale
+        self.use_positional_embeddings = use_positional_embeddings
+        self.use_learned_positional_embeddings = use_learned_positional_embeddings
+        if patch_size_t is None:
+            self.proj = nn.Conv2d(in_channels, embed_dim, kernel_size=(patch_size, patch_size), stride=patch_size,
+                                  bias=bias)
+        else:
+            self.proj = nn.Linear(in_channels * patch_size * patch_size * patch_size_t, embed_dim)
+        self.text_proj = nn.Linear(text_embed_dim, embed_dim)
+
+
+class _LayerNormZero(nn.Module):
+    def __init__(self, cond_dim, dim, affine, eps, modulate_encoder_hidden_states):
+        super().__init__()
+        self.modulate_encoder_hidden_states = modulate_encoder_hidden_states
+        self.silu = nn.SiLU()
+        self.linear = nn.Linear(cond_dim, (6 if modulate_encoder_hidden_states else 3) * dim, bias=True)
+        self.norm = nn.LayerNorm(dim, eps=eps, elementwise_affine=affine)
+
+
+class _AdaLayerNorm(nn.Module):
+    def __init__(self, cond_dim, out_dim, affine, eps):
+        super().__init__()
+        self.silu = nn.SiLU()
+        self.linear = nn.Linear(cond_dim, out_dim)
+        self.norm = nn.LayerNorm(out_dim // 2, eps, affine)
+
+
+class _Attention(nn.Module):
+    def __init__(self, dim, heads, dim_head, bias, out_bias):
+        super().__init__()
+        self.heads = heads
+        self.to_q = nn.Linear(dim, dim, bias=bias)
+        self.to_k = nn.Linear(dim, dim, bias=bias)
+        self.to_v = nn.Linear(dim, dim, bias=bias)
+        self.norm_q = nn.LayerNorm(dim_head, eps=1e-6)
+        self.norm_k = nn.LayerNorm(dim_head, eps=1e-6)
+        self.to_out = nn.ModuleList([nn.Linear(dim, dim, bias=out_bias), nn.Dropout(0.0)])
+
+
+class _GELUProj(nn.Module):
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out)
+
+
+class _FeedForward(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.net = nn.ModuleList([_GELUProj(dim, 4 * dim), nn.Dropout(0.0), nn.Linear(4 * dim, dim), nn.Dropout(0.0)])
+
+
+class CogVideoXBlock(nn.Module):
+    """Parameter layout of reference CogVideoXBlock (:351-392)."""
+
+    def __init__(self, dim, num_attention_heads, attention_head_dim, time_embed_dim, attention_bias,
+                 norm_elementwise_affine, norm_eps, modulate_encoder_hidden_states, attention_out_bias=True):
+        super().__init__()
+        self.norm1 = _LayerNormZero(time_embed_dim, dim, norm_elementwise_affine, norm_eps, modulate_encoder_hidden_states)
+        self.attn1 = _Attention(dim, num_attention_heads, attention_head_dim, attention_bias, attention_out_bias)
+        self.norm2 = _LayerNormZero(time_embed_dim, dim, norm_elementwise_affine, norm_eps, modulate_encoder_hidden_states)
+        self.ff = _FeedForward(dim)
+        self.modulate_encoder_hidden_states = modulate_encoder_hidden_states
+
+
+class MVBlock(nn.Module):
+    """Parameter layout of reference MVBlock (:273-311); `cam_encoder` exists only to load checkpoints."""
+
+    def __init__(self, dim, num_attention_heads, attention_head_dim, time_embed_dim, attention_bias,
+                 norm_elementwise_affine, norm_eps, modulate_encoder_hidden_states, attention_out_bias=True):
+        super().__init__()
+        self.norm1 = _LayerNormZero(time_embed_dim, dim, norm_elementwise_affine, norm_eps, modulate_encoder_hidden_states)
+        self.attn1 = _Attention(dim, num_attention_heads, attention_head_dim, attention_bias, attention_out_bias)
+        self.modulate_encoder_hidden_states = modulate_encoder_hidden_states
+        self.cam_encoder = nn.Linear(12, dim)
+        self.proj_out = nn.Linear(dim, dim)
+        for p in (self.cam_encoder.weight, self.cam_encoder.bias, self.proj_out.weight, self.proj_out.bias):
+            p.data.zero_()
+
+
+_CONFIG_DEFAULTS = dict(
+    num_attention_heads=30, attention_head_dim=64, in_channels=16, out_channels=16, flip_sin_to_cos=True,
+    freq_shift=0, time_embed_dim=512, ofs_embed_dim=None, text_embed_dim=4096, num_layers=30, dropout=0.0,
+    attention_bias=True, sample_width=90, sample_height=60, sample_frames=49, patch_size=2, patch_size_t=None,
+    temporal_compression_ratio=4, max_text_seq_length=226, activation_fn="gelu-approximate",
+    timestep_activation_fn="silu", norm_elementwise_affine=True, norm_eps=1e-5, spatial_interpolation_scale=1.875,
+    temporal_interpolation_scale=1.0, use_rotary_positional_embeddings=False,
+    use_learned_positional_embeddings=False, patch_bias=True, loaded_pretrained_model_name_or_path=None,
+    modulate_encoder_hidden_states=False, num_control_blocks=12, recon_action=False, visual_guidance=False,
+    num_control_keys=2, multiview=False, max_n_view=3, from_t2v=False,
+)
+
+
+class CogVideoXTransformer3DModelTraj(nn.Module):
+    """B200-native drop-in for the reference class of the same name (cogvideox_control.py:448)."""
+
+    config_name = "config.json"
+
+    def __init__(self, **kwargs):
+        super().__init__()
+        cfg = dict(_CONFIG_DEFAULTS)
+        extra = {k: v for k, v in kwargs.items() if k not in cfg}
+        cfg.update({k: v for k, v in kwargs.items() if k in cfg})
+        cfg.update({k: v for k, v in extra.items() if not k.startswith("_")})
+        self.config = FrozenConfig(cfg)
+        c = self.config
+        inner_dim = c.num_attention_heads * c.attention_head_dim
+        if not c.use_rotary_positional_embeddings and c.use_learned_positional_embeddings:
+            raise ValueError("There are no CogVideoX checkpoints available with disable rotary embeddings and "
+                             "learned positional embeddings.")
+        if c.activation_fn != "gelu-approximate" or c.timestep_activation_fn != "silu":
+            raise NotImplementedError("orv_b200 implements activation_fn='gelu-approximate', timestep 'silu'")
+        if fnmatch.fnmatch(str(c.loaded_pretrained_model_name_or_path), "THUDM*CogVideoX*"):
+            if not c.modulate_encoder_hidden_states:
+                raise RuntimeError(f"You're trying to load {c.loaded_pretrained_model_name_or_path} but"
+                                   "set modulate_encoder_hidden_states to False!")
+
+        self.patch_embed = _PatchEmbed(
+            c.patch_size, c.patch_size_t, c.in_channels, inner_dim, c.text_embed_dim, c.patch_bias, c.sample_width,
+            c.sample_height, c.sample_frames, c.temporal_compression_ratio, c.max_text_seq_length,
+            c.spatial_interpolation_scale, c.temporal_interpolation_scale,
+            not c.use_rotary_positional_embeddings, c.use_learned_positional_embeddings)
+        self.embedding_dropout = nn.Dropout(c.dropout)
+        self.time_embedding = _TimestepEmbedding(inner_dim, c.time_embed_dim)
+        self.ofs_embedding = None
+        if c.ofs_embed_dim:
+            self.ofs_embedding = _TimestepEmbedding(c.ofs_embed_dim, c.ofs_embed_dim)
+        self.transformer_blocks = nn.ModuleList([
+            CogVideoXBlock(inner_dim, c.num_attention_heads, c.attention_head_dim, c.time_embed_dim, c.attention_bias,
+                           c.norm_elementwise_affine, c.norm_eps, c.modulate_encoder_hidden_states)
+            for _ in range(c.num_layers)])
+        self.norm_final = nn.LayerNorm(inner_dim, c.norm_eps, c.norm_elementwise_affine)
+        self.norm_out = _AdaLayerNorm(c.time_embed_dim, 2 * inner_dim, c.norm_elementwise_affine, c.norm_eps)
+        out_dim = c.patch_size * c.patch_size * (c.patch_size_t or 1) * c.out_channels
+        self.proj_out = nn.Linear(inner_dim, out_dim)
+        # `mask=self.training` is evaluated at construction, i.e. True (reference :581-582).
+        self.action_embed = ActionEmbed(state_dim=7, hidden_size=c.time_embed_dim, compress_ratio=4,
+                                        patch_size_t=c.patch_size_t, mask=self.training)
+        self.action_recon = ActionRecon(7, c.time_embed_dim, 4) if c.recon_action else None
+        if c.visual_guidance:
+            if c.num_control_blocks > c.num_layers:
+                raise ValueError("num_tracking_blocks must be less than or equal to num_layers")
+            self.num_control_keys = c.num_control_keys
+            self.initial_combine_linear = nn.Linear(inner_dim * c.num_control_keys, inner_dim)
+        if c.multiview:
+            self.mv_blocks = nn.ModuleList([
+                MVBlock(inner_dim, c.num_attention_heads, c.attention_head_dim, c.time_embed_dim, c.attention_bias,
+                        c.norm_elementwise_affine, c.norm_eps, c.modulate_encoder_hidden_states)
+                for _ in range(c.num_layers)])
+        self.gradient_checkpointing = False
+        self._set_zeros()
+        self._set_trainable_parameters()
+        # native state
+        self._handle = None
+        self._pack = None
+        self._workspaces: Dict[Tuple, torch.Tensor] = {}
+        self._pos_cache: Dict[Tuple, torch.Tensor] = {}
+        self._bound_pos_key = None
+        self.last_launch_count = 0
+
+    # -------------------------------------------------------------------------------------------------------
+    # reference helpers
+    # -------------------------------------------------------------------------------------------------------
+    def _set_zeros(self):
+        if self.config.from_t2v:
+            self.patch_embed.proj.weight.data[:, -16:, ...].zero_()
+        if hasattr(self, "initial_combine_linear"):
+            self.initial_combine_linear.weight.data.zero_()
+            self.initial_combine_linear.bias.data.zero_()
+
+    def _set_trainable_parameters(self):
+        if self.config.multiview:
+            for p in self.parameters():
+                p.requires_grad_(False)
+            for p in self.mv_blocks.parameters():
+                p.requires_grad_(True)
+        else:
+            for p in self.parameters():
+                p.requires_grad_(True)
+
+    @property
+    def dtype(self):
+        return next(self.parameters()).dtype
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    # -------------------------------------------------------------------------------------------------------
+    # checkpoint I/O (diffusers layout: <dir>/[subfolder/]config.json + *.safetensors)
+    # -------------------------------------------------------------------------------------------------------
+    @classmethod
+    def from_config(cls, config: Dict[str, Any], **kwargs):
+        cfg = {k: v for k, v in dict(config).items() if not k.startswith("_")}
+        cfg.update(kwargs)
+        return cls(**cfg)
+
+    @classmethod
+    def load_config(cls, path, subfolder: Optional[str] = None, **_):
+        d = os.path.join(path, subfolder) if subfolder else path
+        with open(os.path.join(d, cls.config_name), "r", encoding="utf-8") as f:
+            return json.load(f)
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder: Optional[str] = None, torch_dtype=None,
+                        **kwargs):
+        """Loads a locally saved checkpoint.  Like the reference (:950-1054), a strict load is tried first; on
+        key/shape mismatch the 2B T2V->I2V widening (in_channels 16->32, zero-initialised extra channels) and the
+        temporal->multiview block copy are applied."""
+        from safetensors.torch import load_file
+        d = os.path.join(pretrained_model_name_or_path, subfolder) if subfolder else pretrained_model_name_or_path
+        config = cls.load_config(pretrained_model_name_or_path, subfolder)
+        for k in ("revision", "variant", "output_loading_info"):
+            kwargs.pop(k, None)
+        files = sorted(f for f in os.listdir(d) if f.endswith(".safetensors"))
+        if not files:
+            raise FileNotFoundError(f"no .safetensors weights under {d}")
+        sd: Dict[str, torch.Tensor] = {}
+        for f in files:
+            sd.update(load_file(os.path.join(d, f)))
+        same_class = config.get("_class_name") == cls.__name__
+        cfg = {k: v for k, v in config.items() if not k.startswith("_")}
+        cfg.update(kwargs)
+        widen = (not same_class) and cfg.get("in_channels") == 16 and sd["patch_embed.proj.weight"].shape[1] == 16 \
+            and fnmatch.fnmatch(str(pretrained_model_name_or_path), "*CogVideoX*-2b*")
+        if widen:
+            cfg["in_channels"] = 32
+            cfg["from_t2v"] = True
+        model = cls(**cfg)
+        if widen:
+            w = sd.pop("patch_embed.proj.weight")
+            model.load_state_dict(sd, strict=False)
+            model.patch_embed.proj.weight.data[:, :16, ...].copy_(w)
+        else:
+            missing, unexpected = model.load_state_dict(sd, strict=False)
+            missing = [k for k in missing if not k.startswith(("mv_blocks.", "action_embed.", "initial_combine_linear."))]
+            if same_class and (missing or unexpected):
+                raise RuntimeError(f"Some weights of {cls.__name__} are not found in pretrained weights: {missing}. "
+                                   f"Some weights may be lost in {cls.__name__}: {unexpected}.")
+        if model.config.multiview and not (same_class and config.get("multiview")):
+            for i in range(len(model.mv_blocks)):
+                model.mv_blocks[i].load_state_dict(model.transformer_blocks[i].state_dict(), strict=False)
+        if torch_dtype is not None:
+            model = model.to(torch_dtype)
+        model._set_trainable_parameters()
+        return model
+
+    def save_pretrained(self, save_directory, safe_serialization: bool = True, **_):
+        from safetensors.torch import save_file
+        os.makedirs(save_directory, exist_ok=True)
+        sd = {k: v.detach().cpu().contiguous().clone() for k, v in self.state_dict().items()}
+        save_file(sd, os.path.join(save_directory, "diffusion_pytorch_model.safetensors"))
+        config_dict = dict(self.config)
+        config_dict.pop("_name_or_path", None)
+        config_dict.pop("_use_default_values", None)
+        config_dict["_class_name"] = "CogVideoXTransformer3DModelTraj"
+        with open(os.path.join(save_directory, "config.json"), "w", encoding="utf-8") as f:
+            json.dump(config_dict, f, indent=2)
+
+    # -------------------------------------------------------------------------------------------------------
+    # weight arena + native handle
+    # -------------------------------------------------------------------------------------------------------
+    def _apply(self, fn, *a, **k):
+        self._invalidate()
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._invalidate()
+        return super().load_state_dict(*a, **k)
+
+    def _invalidate(self):
+        self.__dict__["_pack"] = None
+        self.__dict__["_bound_pos_key"] = None
+
+    def __del__(self):
+        h = self.__dict__.get("_handle")
+        if h:
+            try:
+                L.load().orvb_model_destroy(h)
+            except Exception:  # noqa: BLE001
+                pass
+
+    def _native_config(self) -> L.Config:
+        c = self.config
+        D = c.num_attention_heads * c.attention_head_dim
+        return L.Config(
+            dim=D, heads=c.num_attention_heads, head_dim=c.attention_head_dim, layers=c.num_layers, ff_dim=4 * D,
+            time_embed_dim=c.time_embed_dim, text_embed_dim=c.text_embed_dim, in_channels=c.in_channels,
+            out_channels=c.out_channels, patch_size=c.patch_size, patch_size_t=c.patch_size_t or 0,
+            use_rope=int(bool(c.use_rotary_positional_embeddings)), has_ofs=int(bool(c.ofs_embed_dim)),
+            ofs_embed_dim=c.ofs_embed_dim or 0, flip_sin_to_cos=int(bool(c.flip_sin_to_cos)),
+            freq_shift=float(c.freq_shift), norm_eps=float(c.norm_eps), visual_guidance=int(bool(c.visual_guidance)),
+            num_control_keys=c.num_control_keys, multiview=int(bool(c.multiview)), max_n_view=c.max_n_view,
+            action_state_dim=7, action_compress=4, action_hidden=4 * c.time_embed_dim)
+
+    def _build_pack(self):
+        """Copies every weight the kernels read into ONE contiguous bf16 arena (256-byte aligned slots, q/k/v
+        fused) and re-points the module's bf16 parameters at it, so the checkpoint lives in HBM exactly once."""
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError("CogVideoXTransformer3DModelTraj (orv_b200) runs on CUDA only: move the model to a "
+                               "B200 with .to('cuda') — there is no CPU path")
+        if not self.config.modulate_encoder_hidden_states:
+            raise NotImplementedError("orv_b200 implements modulate_encoder_hidden_states=True (all 2B/5B ORV "
+                                      "configs); the from-scratch 1.4B variants are out of scope")
+        entries = []  # (key, [(param, rows_slice or None)], shape, pad_cols)
+
+        def add(key, *params, pad_cols=0):
+            entries.append((key, params, pad_cols))
+
+        pe = self.patch_embed
+        add("patch_w", pe.proj.weight)
+        if pe.proj.bias is not None:
+            add("patch_b", pe.proj.bias)
+        add("text_w", pe.text_proj.weight); add("text_b", pe.text_proj.bias)
+        te = self.time_embedding
+        add("time1_w", te.linear_1.weight); add("time1_b", te.linear_1.bias)
+        add("time2_w", te.linear_2.weight); add("time2_b", te.linear_2.bias)
+        if self.ofs_embedding is not None:
+            oe = self.ofs_embedding
+            add("ofs1_w", oe.linear_1.weight); add("ofs1_b", oe.linear_1.bias)
+            add("ofs2_w", oe.linear_2.weight); add("ofs2_b", oe.linear_2.bias)
+        ae = self.action_embed
+        k_act = ae.mlp[0].weight.shape[1]
+        add("act1_w", ae.mlp[0].weight, pad_cols=(-k_act) % 8); add("act1_b", ae.mlp[0].bias)
+        add("act2_w", ae.mlp[3].weight); add("act2_b", ae.mlp[3].bias)
+        add("act_mask_embed", ae.mask_embed.weight)
+        if hasattr(self, "initial_combine_linear"):
+            add("combine_w", self.initial_combine_linear.weight); add("combine_b", self.initial_combine_linear.bias)
+        add("norm_final_w", self.norm_final.weight); add("norm_final_b", self.norm_final.bias)
+        add("norm_out_lin_w", self.norm_out.linear.weight); add("norm_out_lin_b", self.norm_out.linear.bias)
+        add("norm_out_ln_w", self.norm_out.norm.weight); add("norm_out_ln_b", self.norm_out.norm.bias)
+        add("proj_out_w", self.proj_out.weight); add("proj_out_b", self.proj_out.bias)
+
+        def add_block(prefix, blk, mv=False):
+            add(prefix + "norm1_lin_w", blk.norm1.linear.weight); add(prefix + "norm1_lin_b", blk.norm1.linear.bias)
+            add(prefix + "norm1_ln_w", blk.norm1.norm.weight); add(prefix + "norm1_ln_b", blk.norm1.norm.bias)
+            at = blk.attn1
+            add(prefix + "qkv_w", at.to_q.weight, at.to_k.weight, at.to_v.weight)
+            if at.to_q.bias is not None:
+                add(prefix + "qkv_b", at.to_q.bias, at.to_k.bias, at.to_v.bias)
+            add(prefix + "q_norm_w", at.norm_q.weight); add(prefix + "q_norm_b", at.norm_q.bias)
+            add(prefix + "k_norm_w", at.norm_k.weight); add(prefix + "k_norm_b", at.norm_k.bias)
+            add(prefix + "out_w", at.to_out[0].weight)
+            if at.to_out[0].bias is not None:
+                add(prefix + "out_b", at.to_out[0].bias)
+            if mv:
+                add(prefix + "proj_out_w", blk.proj_out.weight); add(prefix + "proj_out_b", blk.proj_out.bias)
+            else:
+                add(prefix + "norm2_lin_w", blk.norm2.linear.weight); add(prefix + "norm2_lin_b", blk.norm2.linear.bias)
+                add(prefix + "norm2_ln_w", blk.norm2.norm.weight); add(prefix + "norm2_ln_b", blk.norm2.norm.bias)
+                add(prefix + "ff1_w", blk.ff.net[0].proj.weight); add(prefix + "ff1_b", blk.ff.net[0].proj.bias)
+                add(prefix + "ff2_w", blk.ff.net[2].weight); add(prefix + "ff2_b", blk.ff.net[2].bias)
+
+        for i, blk in enumerate(self.transformer_blocks):
+            add_block(f"b{i}.", blk)
+        if self.config.multiview:
+            for i, blk in enumerate(self.mv_blocks):
+                add_block(f"m{i}.", blk, mv=True)
+
+        # layout
+        offsets, off = {}, 0
+        for key, params, pad_cols in entries:
+            n = 0
+            for p in params:
+                rows = p.shape[0] if p.dim() > 1 else 1
+                cols = p.numel() // rows
+                n += rows * (cols + pad_cols) if p.dim() > 1 else p.numel()
+            offsets[key] = (off, n)
+            off += (n + 127) // 128 * 128  # 256-byte aligned slots
+        arena = torch.zeros(off, dtype=torch.bfloat16, device=dev)
+        with torch.no_grad():
+            for key, params, pad_cols in entries:
+                o, _ = offsets[key]
+                for p in params:
+                    if p.dim() > 1 and pad_cols:
+                        rows = p.shape[0]
+                        cols = p.numel() // rows
+                        view = arena[o:o + rows * (cols + pad_cols)].view(rows, cols + pad_cols)
+                        view[:, :cols].copy_(p.detach().reshape(rows, cols))
+                        o += rows * (cols + pad_cols)
+                    else:
+                        n = p.numel()
+                        view = arena[o:o + n].view(p.shape)
+                        view.copy_(p.detach())
+                        if p.dtype == torch.bfloat16:
+                            p.data = view  # the parameter now lives in the arena
+                        o += n
+        self.__dict__["_pack"] = SimpleNamespace(arena=arena, offsets=offsets, keepalive=[])
+
+    def _ptr(self, key):
+        pk = self._pack
+        if key not in pk.offsets:
+            return None
+        return pk.arena.data_ptr() + pk.offsets[key][0] * 2
+
+    def _pos_table(self, frames: int, height: int, width: int) -> Optional[torch.Tensor]:
+        """Video rows of CogVideoXPatchEmbed's joint positional buffer for this latent geometry (bf16, HBM)."""
+        c = self.config
+        if c.use_rotary_positional_embeddings and not c.use_learned_positional_embeddings:
+            return None
+        key = (frames, height, width)
+        if key not in self._pos_cache:
+            D = c.num_attention_heads * c.attention_head_dim
+            pos = sincos_pos_embed_3d(D, width // c.patch_size, height // c.patch_size, frames,
+                                      c.spatial_interpolation_scale, c.temporal_interpolation_scale)
+            self._pos_cache[key] = pos.to(device=self.device, dtype=torch.bfloat16).contiguous()
+        return self._pos_cache[key]
+
+    def _ensure_native(self, pos_key):
+        lib = L.load()
+        L.check(lib.orvb_check_device(), "orvb_check_device")
+        if self._handle is None:
+            h = C.c_void_p()
+            cfg = self._native_config()
+            L.check(lib.orvb_model_create(C.byref(cfg), C.byref(h)), "orvb_model_create")
+            self.__dict__["_handle"] = h
+        if self._pack is None:
+            self._build_pack()
+            self.__dict__["_bound_pos_key"] = None
+        if self._bound_pos_key != pos_key:
+            w = L.Weights()
+            for name in L._WEIGHT_FIELDS:
+                if name != "pos_embed":
+                    setattr(w, name, self._ptr(name))
+            pos = self._pos_table(*pos_key)
+            w.pos_embed = pos.data_ptr() if pos is not None else None
+            n = self.config.num_layers
+            blocks = (L.BlockWeights * n)()
+            for i in range(n):
+                for f in L._BLOCK_FIELDS:
+                    setattr(blocks[i], f, self._ptr(f"b{i}.{f}"))
+            w.blocks_host = C.cast(blocks, C.POINTER(L.BlockWeights))
+            if self.config.multiview:
+                mv = (L.BlockWeights * n)()
+                for i in range(n):
+                    for f in L._BLOCK_FIELDS:
+                        setattr(mv[i], f, self._ptr(f"m{i}.{f}"))
+                w.mv_blocks_host = C.cast(mv, C.POINTER(L.BlockWeights))
+            L.check(lib.orvb_model_bind_weights(self._handle, C.byref(w)), "orvb_model_bind_weights")
+            self.__dict__["_bound_pos_key"] = pos_key
+
+    def weight_arena(self) -> torch.Tensor:
+        """The contiguous bf16 weight arena (built on first use) — the single tensor a multi-GPU launcher
+        broadcasts from rank 0."""
+        if self._pack is None:
+            self._build_pack()
+        return self._pack.arena
+
+    # -------------------------------------------------------------------------------------------------------
+    # forward (reference :715-948)
+    # -------------------------------------------------------------------------------------------------------
+    def forward(
+        self,
+        hidden_states: torch.Tensor,
+        encoder_hidden_states: torch.Tensor,
+        controls_or_guidances: Dict[str, torch.Tensor],
+        timestep: Union[int, float, torch.LongTensor],
+        timestep_cond: Optional[torch.Tensor] = None,
+        ofs: Optional[Union[int, float, torch.LongTensor]] = None,
+        image_rotary_emb: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+        attention_kwargs: Optional[Dict[str, Any]] = None,
+        return_dict: bool = True,
+        num_views: int = 1,
+        image_rotary_emb_view: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+        _tap: Optional[Tuple[int, torch.Tensor]] = None,
+    ):
+        c = self.config
+        if timestep_cond is not None:
+            raise NotImplementedError("timestep_cond is never passed on the ORV path (cogvideox_control.py:1421-1431)")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+            raise RuntimeError("orv_b200 implements the inference forward only; wrap the call in torch.no_grad() "
+                               "and call .eval() (training/backward is out of scope, SURVEY §2 row 8)")
+        if not hidden_states.is_cuda:
+            raise RuntimeError("orv_b200 forward needs CUDA tensors on a B200; there is no CPU fallback")
+        if num_views > 1 or c.multiview:
+            raise NotImplementedError("multiview (MVBlock, SURVEY §8 a11) is not built yet")
+        out_dtype = hidden_states.dtype
+        dev = hidden_states.device
+        B, Fr, Cin, H, W = hidden_states.shape
+        if Cin != c.in_channels:
+            raise RuntimeError(f"expected {c.in_channels} input channels, got {hidden_states.shape=}")
+        St = encoder_hidden_states.shape[1]
+        pos_key = (Fr, H, W)
+        if (not c.use_rotary_positional_embeddings) and St != c.max_text_seq_length:
+            raise RuntimeError(f"The size of tensor a ({St + (Fr // (c.patch_size_t or 1)) * (H // 2) * (W // 2)}) must "
+                               f"match the size of the positional table (text length {c.max_text_seq_length})")
+        self._ensure_native(pos_key)
+
+        hs = hidden_states.to(torch.bfloat16).contiguous()
+        text = encoder_hidden_states.to(torch.bfloat16).contiguous()
+        if not torch.is_tensor(timestep):
+            timestep = torch.tensor([timestep], device=dev)
+        ts = timestep.to(device=dev, dtype=torch.float32).reshape(-1)
+        if ts.numel() == 1 and B > 1:
+            ts = ts.expand(B)
+        ts = ts.contiguous()
+        if ts.numel() != B:
+            raise RuntimeError(f"timestep has {ts.numel()} entries for batch {B}")
+
+        # ---- actions: integer bookkeeping of :805-812 on the host, MLP on the device ----
+        act_in = mask_u8 = is_action_mask = None
+        action_frames = 0
+        actions = controls_or_guidances.get("actions", None)
+        if actions is not None:
+            res_frames = (actions.size(1) + 1) % 4
+            if res_frames > 0:
+                pad = actions.new_zeros((actions.shape[0], 4 - res_frames, actions.shape[2]))
+                actions = torch.cat([pad, actions], dim=1)
+            act_in, is_action_mask, apply = self.action_embed.prepare(actions.to(dev))
+            if act_in.shape[0] != B:
+                raise RuntimeError(f"The size of tensor a ({B}) must match the size of tensor b ({act_in.shape[0]}) at "
+                                   "non-singleton dimension 0")  # same failure the reference hits with CFG (P5)
+            action_frames = act_in.shape[1]
+            act_in = act_in.to(torch.bfloat16).contiguous()
+            mask_u8 = apply.contiguous() if bool(self.action_embed.mask) else None
+
+        depths = labels = None
+        if c.visual_guidance:
+            depths = controls_or_guidances.get("depths", None)
+            labels = controls_or_guidances.get("labels", None)
+            n_ctrl = (depths is not None) + (labels is not None)
+            if n_ctrl and n_ctrl != self.num_control_keys:
+                raise AssertionError(f"Mismatched number of controls: len(controls_hidden_states)={n_ctrl} but "
+                                     f"self.num_control_keys={self.num_control_keys}.")
+            if depths is not None:
+                depths = depths.to(device=dev, dtype=torch.bfloat16).contiguous()
+                if depths.shape != hs.shape:
+                    raise RuntimeError(f"Sizes of tensors must match: depths {tuple(depths.shape)} vs {tuple(hs.shape)}")
+            if labels is not None:
+                labels = labels.to(device=dev, dtype=torch.bfloat16).contiguous()
+                if labels.shape != hs.shape:
+                    raise RuntimeError(f"Sizes of tensors must match: labels {tuple(labels.shape)} vs {tuple(hs.shape)}")
+
+        rope_cos = rope_sin = None
+        if image_rotary_emb is not None:
+            rope_cos = image_rotary_emb[0].to(device=dev, dtype=torch.float32).contiguous()
+            rope_sin = image_rotary_emb[1].to(device=dev, dtype=torch.float32).contiguous()
+        ofs_val = 0.0
+        if self.ofs_embedding is not None:
+            if ofs is None:
+                raise RuntimeError("this model has an ofs embedding; pass `ofs`")
+            ofs_val = float(ofs.reshape(-1)[0].item()) if torch.is_tensor(ofs) else float(ofs)
+
+        shape = L.Shape(batch=B, views=1, frames=Fr, height=H, width=W, text_len=St, action_frames=action_frames)
+        lib = L.load()
+        wkey = (B, Fr, H, W, St, action_frames, dev.index)
+        ws = self._workspaces.get(wkey)
+        if ws is None:
+            nbytes = lib.orvb_workspace_bytes(self._handle, C.byref(shape))
+            if nbytes == 0:
+                raise RuntimeError("orvb_workspace_bytes: " + lib.orvb_last_error().decode())
+            ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+            self._workspaces[wkey] = ws
+        ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+        out = torch.empty((B, Fr, c.out_channels, H, W), dtype=torch.bfloat16, device=dev)
+
+        a = L.ForwardArgs()
+        a.shape = shape
+        a.hidden_states, a.text, a.timesteps = hs.data_ptr(), text.data_ptr(), ts.data_ptr()
+        a.ofs = ofs_val
+        a.actions, a.action_mask = L.ptr(act_in), L.ptr(mask_u8)
+        a.depths, a.labels = L.ptr(depths), L.ptr(labels)
+        a.rope_cos, a.rope_sin = L.ptr(rope_cos), L.ptr(rope_sin)
+        a.out = out.data_ptr()
+        a.workspace, a.workspace_bytes = ws_ptr, ws.numel() - (ws_ptr - ws.data_ptr())
+        if _tap is not None:
+            a.tap_layer, a.tap_hidden = _tap[0], _tap[1].data_ptr()
+        else:
+            a.tap_layer = -1
+        L.check(lib.orvb_forward(self._handle, C.byref(a), L.current_stream()), "orvb_forward")
+        self.last_launch_count = lib.orvb_last_launch_count(self._handle)
+
+        output = out if out_dtype == torch.bfloat16 else out.to(out_dtype)
+        actions_recon = None
+        if not return_dict:
+            return (output, is_action_mask, actions_recon)
+        return Transformer3DModelTrajOutput(sample=output, is_action_mask=is_action_mask, actions_recon=actions_recon)

@@ -1,0 +1,83 @@
+"""Parity of the CUDA forward (through the module API -> C ABI) against the fp32 CPU oracle."""
+import pytest
+import torch
+
+from oracle import flat_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def small_cfg(**over):
+    base = dict(num_attention_heads=2, attention_head_dim=64, in_channels=32, out_channels=16, num_layers=2,
+                sample_width=8, sample_height=6, sample_frames=9, modulate_encoder_hidden_states=True,
+                text_embed_dim=64, max_text_seq_length=10, num_control_blocks=2)
+    base.update(over)
+    return O.default_config(**base)
+
+
+def build_model(cfg, sd):
+    from orv_b200.models.cogvideox_control import CogVideoXTransformer3DModelTraj
+    m = CogVideoXTransformer3DModelTraj(**cfg)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert not [k for k in missing if "action_recon" not in k], missing
+    m.action_embed.mask = False
+    return m.to("cuda", torch.bfloat16).eval()
+
+
+def rel_err(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).abs().mean() / b.abs().mean()).item()
+
+
+def run_case(cfg, B, Fr, H, W, controls=False, rope=False, ofs=None, n_actions=8, use_actions=True):
+    sd32 = O.synthetic_state_dict(cfg, seed=0, std=0.05)
+    sd = {k: v.bfloat16().float() for k, v in sd32.items()}  # oracle sees the same bf16-rounded weights
+    inp = O.synthetic_inputs(cfg, B, Fr, H, W, seed=1, with_controls=controls, n_actions=n_actions)
+    hs = inp["hidden_states"].bfloat16().float()
+    text = inp["text"].bfloat16().float()
+    acts = inp["actions"].bfloat16().float() if use_actions else None
+    dep = inp["depths"].bfloat16().float() if controls else None
+    lab = inp["labels"].bfloat16().float() if controls else None
+    t = torch.full((B,), 499, dtype=torch.int64)
+    rp = None
+    if rope:
+        rp = O.pipeline_rope(cfg, H * 8, W * 8, Fr)
+    ofs_t = torch.tensor([ofs]) if ofs is not None else None
+    ref = O.forward(sd, cfg, hs, text, t, actions=acts, depths=dep, labels=lab, ofs=ofs_t, rope=rp)
+    m = build_model(cfg, sd32)
+    cg = {}
+    if use_actions:
+        cg["actions"] = acts.cuda().bfloat16()
+    if controls:
+        cg["depths"], cg["labels"] = dep.cuda().bfloat16(), lab.cuda().bfloat16()
+    with torch.no_grad():
+        out, is_mask, recon = m(hs.cuda().bfloat16(), text.cuda().bfloat16(), cg, t.cuda(),
+                                ofs=ofs_t.cuda() if ofs_t is not None else None,
+                                image_rotary_emb=(rp[0].cuda(), rp[1].cuda()) if rp else None, return_dict=False)
+    torch.cuda.synchronize()
+    assert out.shape == ref.shape
+    assert torch.isfinite(out.float()).all()
+    return rel_err(out, ref), m
+
+
+def test_forward_small_actions():
+    e, m = run_case(small_cfg(), 1, 3, 6, 8)
+    assert m.last_launch_count > 0
+    assert e < 1.5e-2, e
+
+
+def test_forward_small_no_actions_batch2():
+    e, _ = run_case(small_cfg(), 2, 3, 6, 8, use_actions=False)
+    assert e < 1.5e-2, e
+
+
+def test_forward_small_controls():
+    e, _ = run_case(small_cfg(visual_guidance=True), 2, 3, 6, 8, controls=True)
+    assert e < 1.5e-2, e
+
+
+def test_forward_small_rope_pt2_ofs():
+    cfg = small_cfg(patch_size_t=2, use_rotary_positional_embeddings=True, ofs_embed_dim=512, patch_bias=False)
+    e, _ = run_case(cfg, 2, 4, 6, 8, rope=True, ofs=2.0, n_actions=12)
+    assert e < 1.5e-2, e
