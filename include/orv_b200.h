@@ -260,6 +260,25 @@ int orvb_forward(orvb_model* m, const orvb_forward_args* a, void* stream);
  * `gpu_launches`). */
 int orvb_last_launch_count(const orvb_model* m);
 
+/* Optional per-kernel-class timing of orvb_forward (CUDA events recorded on the launch stream around every
+ * launch; the forward then synchronises at its end, so enable it for measurement only).  orvb_model_set_profile
+ * also clears the accumulators; orvb_model_get_profile copies accumulated milliseconds / launch counts per class
+ * into arrays of ORVB_PROFILE_CLASSES entries. */
+enum {
+  ORVB_PC_PROLOGUE = 0, /* time/ofs/action MLPs + AdaLN tables (skinny linears)  */
+  ORVB_PC_EMBED = 1,    /* patchify, patch/text/control projections              */
+  ORVB_PC_LN = 2,       /* LayerNorm + modulate                                  */
+  ORVB_PC_QKV = 3,      /* QKV GEMM (+QK-LN, RoPE)                               */
+  ORVB_PC_ATTN = 4,     /* attention                                             */
+  ORVB_PC_OUT = 5,      /* attention out-projection GEMM (+gate, residual)       */
+  ORVB_PC_FF1 = 6,      /* FF up GEMM (+GELU)                                    */
+  ORVB_PC_FF2 = 7,      /* FF down GEMM (+gate, residual)                        */
+  ORVB_PC_HEAD = 8,     /* norm_final/norm_out, proj_out, unpatchify             */
+  ORVB_PROFILE_CLASSES = 9
+};
+int orvb_model_set_profile(orvb_model* m, int enable);
+int orvb_model_get_profile(const orvb_model* m, float* ms_out, int32_t* launches_out);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Sampler step (reference a14: CFG combine + CogVideoXDDIMScheduler/CogVideoXDPMScheduler.step + bf16 cast)
  * ------------------------------------------------------------------------------------------------------------ */

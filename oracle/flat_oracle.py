@@ -450,18 +450,28 @@ class Scheduler:
         a_prev = self.alphas_cumprod[prev] if prev >= 0 else self.final_alpha_cumprod
         return a_t, a_prev, prev
 
+    @staticmethod
+    def _smul(scalar, x: Tensor) -> Tensor:
+        """`float64 0-dim CPU tensor * tensor` as torch evaluates it when the tensor lives on CUDA (the reference's
+        deployment): the scalar is taken in fp32 ("opmath"), the product is rounded to the tensor's dtype.
+        (torch's CPU kernels instead round the scalar to the tensor dtype first; tests/test_gpu_ops.py checks the
+        CUDA behaviour against real torch-CUDA ops on the B200.)"""
+        return (x.float() * torch.tensor(float(scalar), dtype=torch.float32)).to(x.dtype)
+
     def step_ddim(self, v: Tensor, t: int, x: Tensor) -> Tensor:
+        """CogVideoXDDIMScheduler.step (v-prediction); x may be bf16 (the pipeline keeps latents in bf16), v fp32."""
         a_t, a_prev, _ = self._alphas(t)
-        x0 = (a_t ** 0.5) * x - ((1 - a_t) ** 0.5) * v
+        x0 = self._smul(a_t ** 0.5, x) - self._smul((1 - a_t) ** 0.5, v)
         a = ((1 - a_prev) / (1 - a_t)) ** 0.5
         b = a_prev ** 0.5 - a_t ** 0.5 * a
-        return a * x + b * x0
+        return self._smul(a, x) + self._smul(b, x0)
 
     def step_dpm(self, v: Tensor, old_x0: Optional[Tensor], t: int, t_back: Optional[int], x: Tensor,
-                 generator: Optional[torch.Generator]):
+                 generator: Optional[torch.Generator], noises: Optional[list] = None):
+        """CogVideoXDPMScheduler.step.  `noises` (optional) collects the noise tensors actually used."""
         a_t, a_prev, prev = self._alphas(t)
         a_back = self.alphas_cumprod[t_back] if t_back is not None else None
-        x0 = (a_t ** 0.5) * x - ((1 - a_t) ** 0.5) * v
+        x0 = self._smul(a_t ** 0.5, x) - self._smul((1 - a_t) ** 0.5, v)
         lamb = ((a_t / (1 - a_t)) ** 0.5).log()
         lamb_next = ((a_prev / (1 - a_prev)) ** 0.5).log()
         h = lamb_next - lamb
@@ -469,15 +479,18 @@ class Scheduler:
         m2 = (-2 * h).expm1() * a_prev ** 0.5
         m_noise = (1 - a_prev) ** 0.5 * (1 - (-2 * h).exp()) ** 0.5
         noise = torch.randn(x.shape, generator=generator, dtype=x.dtype)
-        prev_sample = m1 * x - m2 * x0 + m_noise * noise
         if old_x0 is None or prev < 0:
-            return prev_sample, x0
+            if noises is not None:
+                noises.append(noise)
+            return self._smul(m1, x) - self._smul(m2, x0) + self._smul(m_noise, noise), x0
         lamb_prev = ((a_back / (1 - a_back)) ** 0.5).log()
         r = (lamb - lamb_prev) / h
         m3, m4 = 1 + 1 / (2 * r), 1 / (2 * r)
-        d = m3 * x0 - m4 * old_x0
+        d = self._smul(m3, x0) - self._smul(m4, old_x0)
         noise = torch.randn(x.shape, generator=generator, dtype=x.dtype)  # diffusers draws a second time here
-        return m1 * x - m2 * d + m_noise * noise, x0
+        if noises is not None:
+            noises.append(noise)
+        return self._smul(m1, x) - self._smul(m2, d) + self._smul(m_noise, noise), x0
 
 
 def sample_loop(sd, cfg, sched: Scheduler, latents: Tensor, image_latents: Tensor, prompt_embeds: Tensor,

@@ -120,7 +120,8 @@ EXPORTED_SYMBOLS = [
     "orvb_gemm_bf16", "orvb_attention_bf16", "orvb_ln_modulate", "orvb_skinny_linear",
     "orvb_patchify", "orvb_unpatchify",
     "orvb_model_create", "orvb_model_destroy", "orvb_model_bind_weights", "orvb_workspace_bytes",
-    "orvb_forward", "orvb_last_launch_count", "orvb_sampler_step",
+    "orvb_forward", "orvb_last_launch_count", "orvb_model_set_profile", "orvb_model_get_profile",
+    "orvb_sampler_step",
 ]
 
 _lib = None
@@ -173,6 +174,10 @@ def load() -> C.CDLL:
         lib.orvb_forward.restype = c_int
         lib.orvb_last_launch_count.argtypes = [c_void_p]
         lib.orvb_last_launch_count.restype = c_int
+        lib.orvb_model_set_profile.argtypes = [c_void_p, c_int]
+        lib.orvb_model_set_profile.restype = c_int
+        lib.orvb_model_get_profile.argtypes = [c_void_p, C.POINTER(c_float), C.POINTER(c_int)]
+        lib.orvb_model_get_profile.restype = c_int
     if hasattr(lib, "orvb_sampler_step"):
         lib.orvb_sampler_step.argtypes = [C.POINTER(SamplerStepArgs), c_void_p]
         lib.orvb_sampler_step.restype = c_int

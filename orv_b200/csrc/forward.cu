@@ -32,6 +32,14 @@ struct orvb_model {
   float* jobs_y_base = nullptr;         // modulation-table base the job table currently points at
   size_t jobs_site_stride = 0;
   int launches = 0;
+  // optional per-kernel-class timing (orvb_model_set_profile): CUDA events around every launch
+  bool profile = false;
+  int cur_cls = 0;
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> ev_cls;
+  size_t ev_used = 0;
+  float cls_ms[ORVB_PROFILE_CLASSES] = {0};
+  int cls_launches[ORVB_PROFILE_CLASSES] = {0};
 };
 
 namespace orvb {
@@ -181,12 +189,31 @@ __global__ void add_hidden_kernel(bf16* __restrict__ ctrl, const bf16* __restric
   *reinterpret_cast<uint4*>(ctrl + static_cast<size_t>(r) * ld_ctrl + col_off + c * 8) = a;
 }
 
-#define ORVB_TRY(expr)            \
-  do {                            \
-    int _rc = (expr);             \
+static void prof_begin(orvb_model* m, cudaStream_t st) {
+  if (!m->profile) return;
+  if (m->ev_used + 2 > m->ev.size()) {
+    size_t old = m->ev.size();
+    m->ev.resize(old + 64);
+    for (size_t i = old; i < m->ev.size(); ++i) cudaEventCreate(&m->ev[i]);
+  }
+  cudaEventRecord(m->ev[m->ev_used], st);
+}
+static void prof_end(orvb_model* m, cudaStream_t st) {
+  if (!m->profile) return;
+  cudaEventRecord(m->ev[m->ev_used + 1], st);
+  m->ev_cls.push_back(m->cur_cls);
+  m->ev_used += 2;
+}
+
+#define ORVB_TRY(expr)              \
+  do {                              \
+    prof_begin(m, st);              \
+    int _rc = (expr);               \
     if (_rc != ORVB_OK) return _rc; \
-    ++m->launches;                \
+    prof_end(m, st);                \
+    ++m->launches;                  \
   } while (0)
+#define ORVB_CLS(c) (m->cur_cls = (c))
 
 static orvb_gemm_args gemm_base(const void* a, const void* w, const void* bias, void* out, int M, int N, int K,
                                 int lda, int ldo, int epi) {
@@ -218,6 +245,9 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
   const int D = g.D, T = g.T;
   const int pt = c.patch_size_t > 0 ? c.patch_size_t : 1;
   m->launches = 0;
+  m->ev_used = 0;
+  m->ev_cls.clear();
+  ORVB_CLS(ORVB_PC_PROLOGUE);
 
   // ---- 1. time / ofs / action embeddings -> per-group conditioning rows -----------------------------
   {
@@ -300,6 +330,7 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
   rm.groups_per_batch = g.G;
 
   // ---- 3. patch embed + text projection into the joint sequence -----------------------------------
+  ORVB_CLS(ORVB_PC_EMBED);
   ORVB_TRY(patchify_launch(a->hidden_states, ws.patches, g.B, g.F, c.in_channels, g.H, g.W, c.patch_size,
                            c.patch_size_t, st));
   {
@@ -362,29 +393,36 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
     ln.x = ws.x; ln.y = ws.xn; ln.ln_w = bw.norm1_ln_w; ln.ln_b = bw.norm1_ln_b;
     ln.rows = g.R; ln.dim = D; ln.eps = c.norm_eps;
     ln.mod = mod1; ln.mod_ld = 6 * D; ln.text_off = 3 * D; ln.video_off = 0; ln.rowmap = rm;
+    ORVB_CLS(ORVB_PC_LN);
     ORVB_TRY(ln_modulate_launch(&ln, st));
 
     orvb_gemm_args q = gemm_base(ws.xn, bw.qkv_w, bw.qkv_b, ws.qkv, g.R, 3 * D, D, D, 3 * D, ORVB_EPI_QKV);
     q.qk_dim = D; q.q_norm_w = bw.q_norm_w; q.q_norm_b = bw.q_norm_b; q.k_norm_w = bw.k_norm_w; q.k_norm_b = bw.k_norm_b;
     q.qk_eps = 1e-6f; q.rowmap = rm;
     if (c.use_rope) { q.rope_cos = a->rope_cos; q.rope_sin = a->rope_sin; }
+    ORVB_CLS(ORVB_PC_QKV);
     ORVB_TRY(gemm_run(&q, st));
 
+    ORVB_CLS(ORVB_PC_ATTN);
     ORVB_TRY(attention_launch(ws.qkv, ws.att, g.B, g.S, c.heads, scale, st));
 
     orvb_gemm_args o = gemm_base(ws.att, bw.out_w, bw.out_b, ws.x, g.R, D, D, D, D, ORVB_EPI_GATE_RESID);
     o.resid = ws.x; o.ldr = D; o.gate = mod1; o.gate_ld = 6 * D; o.gate_text_off = 5 * D; o.gate_video_off = 2 * D;
     o.rowmap = rm;
+    ORVB_CLS(ORVB_PC_OUT);
     ORVB_TRY(gemm_run(&o, st));
 
     ln.ln_w = bw.norm2_ln_w; ln.ln_b = bw.norm2_ln_b; ln.mod = mod2;
+    ORVB_CLS(ORVB_PC_LN);
     ORVB_TRY(ln_modulate_launch(&ln, st));
 
     orvb_gemm_args f1 = gemm_base(ws.xn, bw.ff1_w, bw.ff1_b, ws.ffh, g.R, g.FF, D, D, g.FF, ORVB_EPI_GELU);
+    ORVB_CLS(ORVB_PC_FF1);
     ORVB_TRY(gemm_run(&f1, st));
     orvb_gemm_args f2 = gemm_base(ws.ffh, bw.ff2_w, bw.ff2_b, ws.x, g.R, D, g.FF, g.FF, D, ORVB_EPI_GATE_RESID);
     f2.resid = ws.x; f2.ldr = D; f2.gate = mod2; f2.gate_ld = 6 * D; f2.gate_text_off = 5 * D; f2.gate_video_off = 2 * D;
     f2.rowmap = rm;
+    ORVB_CLS(ORVB_PC_FF2);
     ORVB_TRY(gemm_run(&f2, st));
 
     if (a->tap_hidden != nullptr && a->tap_layer == l) {
@@ -399,12 +437,22 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
     ln.x = ws.x; ln.y = ws.xn; ln.rows = g.B * g.Sv; ln.dim = D;
     ln.pre_w = w.norm_final_w; ln.pre_b = w.norm_final_b; ln.pre_eps = c.norm_eps;
     ln.ln_w = w.norm_out_ln_w; ln.ln_b = w.norm_out_ln_b; ln.eps = c.norm_eps;
+    ORVB_CLS(ORVB_PC_HEAD);
     ln.mod = mod_out; ln.mod_ld = 2 * D; ln.text_off = 0; ln.video_off = 0; ln.rowmap = rm; ln.in_video_only = 1;
     ORVB_TRY(ln_modulate_launch(&ln, st));
     orvb_gemm_args po = gemm_base(ws.xn, w.proj_out_w, w.proj_out_b, ws.yout, g.B * g.Sv, g.Nout, D, D, g.Nout,
                                   ORVB_EPI_BIAS);
     ORVB_TRY(gemm_run(&po, st));
     ORVB_TRY(unpatchify_launch(ws.yout, a->out, g.B, g.F, c.out_channels, g.H, g.W, c.patch_size, c.patch_size_t, st));
+  }
+  if (m->profile && m->ev_used > 0) {
+    ORVB_CHECK_CUDA(cudaEventSynchronize(m->ev[m->ev_used - 1]));
+    for (size_t i = 0; i < m->ev_cls.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, m->ev[2 * i], m->ev[2 * i + 1]);
+      m->cls_ms[m->ev_cls[i]] += ms;
+      m->cls_launches[m->ev_cls[i]] += 1;
+    }
   }
   return ORVB_OK;
 }
@@ -441,6 +489,7 @@ extern "C" int orvb_model_create(const orvb_config* cfg, orvb_model** out) {
 extern "C" void orvb_model_destroy(orvb_model* m) {
   if (m == nullptr) return;
   if (m->jobs_dev) cudaFree(m->jobs_dev);
+  for (cudaEvent_t e : m->ev) cudaEventDestroy(e);
   delete m;
 }
 
@@ -485,3 +534,24 @@ extern "C" int orvb_forward(orvb_model* m, const orvb_forward_args* a, void* str
 }
 
 extern "C" int orvb_last_launch_count(const orvb_model* m) { return m ? m->launches : 0; }
+
+extern "C" int orvb_model_set_profile(orvb_model* m, int enable) {
+  using namespace orvb;
+  ORVB_REQUIRE(m != nullptr, ORVB_EINVAL, "orvb_model_set_profile: null model");
+  m->profile = enable != 0;
+  for (int i = 0; i < ORVB_PROFILE_CLASSES; ++i) {
+    m->cls_ms[i] = 0.f;
+    m->cls_launches[i] = 0;
+  }
+  return ORVB_OK;
+}
+
+extern "C" int orvb_model_get_profile(const orvb_model* m, float* ms_out, int32_t* launches_out) {
+  using namespace orvb;
+  ORVB_REQUIRE(m != nullptr && ms_out != nullptr, ORVB_EINVAL, "orvb_model_get_profile: null pointer");
+  for (int i = 0; i < ORVB_PROFILE_CLASSES; ++i) {
+    ms_out[i] = m->cls_ms[i];
+    if (launches_out) launches_out[i] = m->cls_launches[i];
+  }
+  return ORVB_OK;
+}
