@@ -178,8 +178,6 @@ def run_ours(args):
                           CogVideoXTransformer3DModelTraj, _lib as L)
     from orv_b200 import dist as D
     from orv_b200.models.pipeline_control import default_vae_config
-    import ctypes as C
-
     rank, local_rank, world = D.init_from_env("nccl")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -249,18 +247,15 @@ def run_ours(args):
     d2h = 5 * 16 * 40 * 60 * 2
 
     # ---- per-kernel-class timing inside the real step (CUDA events on the launch stream) ----
-    lib = L.load()
-    lib.orvb_model_set_profile(model._handle, 1)
+    model.set_profile(True)
     hs = torch.randn(1, 5, 32, 40, 60, device=dev).bfloat16()
     tt = torch.full((1,), 499, device=dev, dtype=torch.int64)
     nprof = 3
     with torch.no_grad():
         for _ in range(nprof):
             model(hs, text_d, {"actions": act_d}, tt, return_dict=False)
-    ms = (C.c_float * 9)()
-    cnt = (C.c_int32 * 9)()
-    lib.orvb_model_get_profile(model._handle, ms, cnt)
-    lib.orvb_model_set_profile(model._handle, 0)
+    ms, cnt = model.get_profile()
+    model.set_profile(False)
     names = ["prologue_adaln", "embed", "ln_modulate", "gemm_qkv", "attention", "gemm_out", "gemm_ff1", "gemm_ff2",
              "head"]
     S, Dm, FF, H = 3226, 1920, 7680, 30

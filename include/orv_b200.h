@@ -295,6 +295,11 @@ typedef struct orvb_sampler_step_args {
    * Products with the bf16 tensors x and noise are rounded to bf16 first, as torch does for
    * `float64_scalar * bf16_tensor`; no FMA contraction, so the result matches the torch op sequence bit for bit. */
   float c_x, c_v, d_cur, d_old, k_x, k_d, k_noise;
+  /* Optional: also scatter the new latents into the next iteration's transformer input
+   * bf16 [cfg_copies*B, F, lat_channels + img_channels, h, w] (channels [0, lat_channels) of every copy), which
+   * replaces the reference's per-step torch.cat (cogvideox_control.py:1409-1413).  NULL = skip. */
+  void* next_input;
+  int32_t lat_channels, img_channels, hw;
 } orvb_sampler_step_args;
 int orvb_sampler_step(const orvb_sampler_step_args* a, void* stream);
 

@@ -111,6 +111,7 @@ class SamplerStepArgs(C.Structure):
         ("n", C.c_int64), ("cfg_copies", c_int), ("guidance_scale", c_float),
         ("c_x", c_float), ("c_v", c_float), ("d_cur", c_float), ("d_old", c_float), ("k_x", c_float),
         ("k_d", c_float), ("k_noise", c_float),
+        ("next_input", c_void_p), ("lat_channels", c_int), ("img_channels", c_int), ("hw", c_int),
     ]
 
 

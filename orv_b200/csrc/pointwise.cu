@@ -384,7 +384,18 @@ __global__ void sampler_step_kernel(const orvb_sampler_step_args a) {
   if (a.noise != nullptr)
     prev = __fadd_rn(prev, rbf(__fmul_rn(a.k_noise, __bfloat162float(static_cast<const bf16*>(a.noise)[i]))));
   if (a.old_x0 != nullptr) a.old_x0[i] = x0;
-  lat[i] = __float2bfloat16(prev);
+  const bf16 pb = __float2bfloat16(prev);
+  lat[i] = pb;
+  if (a.next_input != nullptr) {
+    // next iteration's transformer input: cat([latents] * cfg_copies) placed in channels [0, C) of
+    // [cfg*B, F, C + C_img, h, w] (cogvideox_control.py:1409-1413); the image-latent channels are written once.
+    bf16* ni = static_cast<bf16*>(a.next_input);
+    const long chw = static_cast<long>(a.lat_channels) * a.hw;
+    const long bf = i / chw;
+    const long o = bf * (chw + static_cast<long>(a.img_channels) * a.hw) + (i - bf * chw);
+    ni[o] = pb;
+    if (a.cfg_copies == 2) ni[o + (a.n / chw) * (chw + static_cast<long>(a.img_channels) * a.hw)] = pb;
+  }
 }
 
 int sampler_step_launch(const orvb_sampler_step_args* a, cudaStream_t stream) {

@@ -74,6 +74,7 @@ class CogVideoXImageToVideoPipelineTraj:
         self._interrupt = False
         self._num_timesteps = 0
         self.last_step_launches = 0
+        self._staging: Dict[Tuple, torch.Tensor] = {}
 
     # ---- diffusers DiffusionPipeline surface the reference programs touch ----
     @property
@@ -334,46 +335,89 @@ class CogVideoXImageToVideoPipelineTraj:
         fused = latents.is_cuda and latents.dtype == torch.bfloat16 and callback_on_step_end is None
         ts_list = timesteps.tolist()
         n_cfg = 2 if do_cfg else 1
-        noises = None
+        draws = noise_dev = noise_pin = noise_evt = None
         if is_dpm and fused:
-            # Same generator stream as diffusers' step(): every draw happens, the discarded ones included.
+            # Same generator stream as diffusers' step(): every draw happens, the discarded ones included
+            # (`noise_draws`).  A CPU generator (the reference's, inference_control_to_video.py:144) makes this host
+            # work of a few ms per step; it is issued AFTER the step's forward has been enqueued, so it overlaps the
+            # GPU, and reaches the device through a double-buffered pinned staging area.
             draws = self.scheduler.noise_draws(len(ts_list))
-            host = []
-            for nd in draws:
-                for _ in range(nd):
-                    nz = randn_tensor(latents.shape, generator, "cpu" if _is_cpu_gen(generator) else device, latents.dtype)
-                host.append(nz)
-            noises = [n.to(device, non_blocking=True) for n in host]
-        latents = latents.contiguous()
-        model_input = torch.empty((n_cfg * latents.shape[0],) + tuple(latents.shape[1:2]) +
-                                  (latents.shape[2] + image_latents.shape[2],) + tuple(latents.shape[3:]),
-                                  dtype=latents.dtype, device=device)
+            nk = ("noise", tuple(latents.shape), latents.dtype)
+            if nk not in self._staging:
+                self._staging[nk] = ([torch.empty(latents.shape, dtype=latents.dtype, device=device) for _ in range(2)],
+                                     [torch.empty(latents.shape, dtype=latents.dtype).pin_memory() for _ in range(2)],
+                                     [torch.cuda.Event(), torch.cuda.Event()])
+            noise_dev, noise_pin, noise_evt = self._staging[nk]
+        # Persistent device staging (keyed by shape): the transformer reads its large inputs in place, so stable
+        # addresses let one captured CUDA graph serve every iteration of every clip.
+        def stage(name, t):
+            key = (name, tuple(t.shape), t.dtype)
+            buf = self._staging.get(key)
+            if buf is None or buf.device != device:
+                buf = torch.empty(t.shape, dtype=t.dtype, device=device)
+                self._staging[key] = buf
+            if buf.data_ptr() != t.data_ptr():
+                buf.copy_(t, non_blocking=True)
+            return buf
+
+        latents = stage("latents", latents.contiguous())
+        prompt_embeds = stage("prompt_embeds", prompt_embeds.contiguous())
+        controls_or_guidances = {k: (stage(k, v.to(latents.dtype).contiguous()) if torch.is_tensor(v) else v)
+                                 for k, v in controls_or_guidances.items()}
+        if image_rotary_emb is not None:
+            image_rotary_emb = (stage("rope_cos", image_rotary_emb[0].float().contiguous()),
+                                stage("rope_sin", image_rotary_emb[1].float().contiguous()))
         Cl = latents.shape[2]
+        mi_shape = (n_cfg * latents.shape[0], latents.shape[1], Cl + image_latents.shape[2]) + tuple(latents.shape[3:])
+        model_input = self._staging.get(("model_input", mi_shape))
+        if model_input is None or model_input.device != device:
+            model_input = torch.empty(mi_shape, dtype=latents.dtype, device=device)
+            self._staging[("model_input", mi_shape)] = model_input
         model_input[:, :, Cl:] = torch.cat([image_latents] * n_cfg) if do_cfg else image_latents
-        old_x0 = torch.empty(latents.shape, dtype=torch.float32, device=device) if is_dpm else None
+        model_input[:, :, :Cl] = torch.cat([latents] * 2) if do_cfg else latents
+        old_x0 = None
+        if is_dpm:
+            old_x0 = self._staging.get(("old_x0", tuple(latents.shape)))
+            if old_x0 is None or old_x0.device != device:
+                old_x0 = torch.empty(latents.shape, dtype=torch.float32, device=device)
+                self._staging[("old_x0", tuple(latents.shape))] = old_x0
         have_old = False
         launches = 0
         with self.progress_bar(total=num_inference_steps) as progress_bar:
             for i, t in enumerate(ts_list):
                 if self.interrupt:
                     continue
-                model_input[:, :, :Cl] = torch.cat([latents] * 2) if do_cfg else latents
+                if not fused:
+                    model_input[:, :, :Cl] = torch.cat([latents] * 2) if do_cfg else latents
                 timestep = timesteps[i].expand(model_input.shape[0])
                 noise_pred = self.transformer(
                     hidden_states=model_input, encoder_hidden_states=prompt_embeds, timestep=timestep, ofs=ofs_emb,
                     image_rotary_emb=image_rotary_emb, attention_kwargs=attention_kwargs,
-                    controls_or_guidances=controls_or_guidances, return_dict=False, num_views=num_views)[0]
+                    controls_or_guidances=controls_or_guidances, return_dict=False, num_views=num_views,
+                    _static_out=fused)[0]
                 launches += self.transformer.last_launch_count + 2
                 if use_dynamic_cfg:
                     self._guidance_scale = 1 + guidance_scale * (
                         (1 - math.cos(math.pi * ((num_inference_steps - t) / num_inference_steps) ** 5.0)) / 2)
                 if fused:
                     if is_dpm:
+                        slot = i & 1
+                        if _is_cpu_gen(generator):
+                            for _ in range(draws[i]):
+                                nz = randn_tensor(latents.shape, generator, "cpu", latents.dtype)
+                            noise_evt[slot].synchronize()  # the H2D that last used this pinned slot has finished
+                            noise_pin[slot].copy_(nz)
+                            noise_dev[slot].copy_(noise_pin[slot], non_blocking=True)
+                            noise_evt[slot].record()
+                        else:
+                            for _ in range(draws[i]):
+                                nz = randn_tensor(latents.shape, generator, device, latents.dtype)
+                            noise_dev[slot].copy_(nz)
                         self.scheduler.fused_step(noise_pred, old_x0, have_old, t, ts_list[i - 1] if i > 0 else None,
-                                                  latents, noises[i], n_cfg, self.guidance_scale)
+                                                  latents, noise_dev[slot], n_cfg, self.guidance_scale, model_input)
                         have_old = True
                     else:
-                        self.scheduler.fused_step(noise_pred, t, latents, n_cfg, self.guidance_scale)
+                        self.scheduler.fused_step(noise_pred, t, latents, n_cfg, self.guidance_scale, model_input)
                 else:
                     noise_pred = noise_pred.float()
                     if do_cfg:
@@ -395,6 +439,7 @@ class CogVideoXImageToVideoPipelineTraj:
         self.last_step_launches = launches
 
         B = latents.shape[0]
+        latents = latents.clone()
         latents = latents.reshape(B * num_views, latent_frames if patch_size_t is None else latents.shape[1] // num_views,
                                   *latents.shape[2:])
         if not output_type == "latent":

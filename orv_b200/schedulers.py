@@ -105,7 +105,7 @@ class _CogVideoXSchedulerBase:
             return float(1.0 / a_t ** 0.5), float(-((1 - a_t) ** 0.5) / a_t ** 0.5)
         raise ValueError(f"prediction_type given as {p} must be one of `epsilon` or `v_prediction`")
 
-    def _launch(self, model_out, latents, old_x0, noise, cfg_copies, guidance_scale, coeffs):
+    def _launch(self, model_out, latents, old_x0, noise, cfg_copies, guidance_scale, coeffs, next_input=None):
         if not (latents.is_cuda and latents.dtype == torch.bfloat16 and latents.is_contiguous()):
             raise RuntimeError("fused_step needs contiguous bf16 CUDA latents (the resident latents of the sampler)")
         if model_out.dtype != torch.bfloat16 or not model_out.is_contiguous():
@@ -119,6 +119,16 @@ class _CogVideoXSchedulerBase:
         a.noise = L.ptr(noise)
         a.n, a.cfg_copies, a.guidance_scale = n, cfg_copies, float(guidance_scale)
         a.c_x, a.c_v, a.d_cur, a.d_old, a.k_x, a.k_d, a.k_noise = [float(x) for x in coeffs]
+        if next_input is not None:
+            # [cfg*B, F, C_lat + C_img, h, w]: the new latents are also written into channels [0, C_lat)
+            if not (next_input.is_cuda and next_input.dtype == torch.bfloat16 and next_input.is_contiguous()):
+                raise RuntimeError("next_input must be a contiguous bf16 CUDA tensor")
+            c_lat = latents.shape[2]
+            if next_input.shape[0] != cfg_copies * latents.shape[0] or next_input.shape[2] <= c_lat:
+                raise RuntimeError(f"next_input shape {tuple(next_input.shape)} does not match latents {tuple(latents.shape)}")
+            a.next_input = next_input.data_ptr()
+            a.lat_channels, a.img_channels = c_lat, next_input.shape[2] - c_lat
+            a.hw = latents.shape[3] * latents.shape[4]
         L.check(L.load().orvb_sampler_step(C.byref(a), L.current_stream()), "orvb_sampler_step")
 
 
@@ -146,8 +156,10 @@ class CogVideoXDDIMScheduler(_CogVideoXSchedulerBase):
             return (prev, x0)
         return SimpleNamespace(prev_sample=prev, pred_original_sample=x0)
 
-    def fused_step(self, model_out, timestep: int, latents, cfg_copies: int = 1, guidance_scale: float = 1.0):
-        self._launch(model_out, latents, None, None, cfg_copies, guidance_scale, self.coefficients(int(timestep)))
+    def fused_step(self, model_out, timestep: int, latents, cfg_copies: int = 1, guidance_scale: float = 1.0,
+                   next_input=None):
+        self._launch(model_out, latents, None, None, cfg_copies, guidance_scale, self.coefficients(int(timestep)),
+                     next_input)
 
 
 class CogVideoXDPMScheduler(_CogVideoXSchedulerBase):
@@ -201,9 +213,9 @@ class CogVideoXDPMScheduler(_CogVideoXSchedulerBase):
         return SimpleNamespace(prev_sample=prev, pred_original_sample=x0)
 
     def fused_step(self, model_out, old_x0, have_old: bool, timestep: int, timestep_back: Optional[int], latents,
-                   noise, cfg_copies: int = 1, guidance_scale: float = 1.0):
+                   noise, cfg_copies: int = 1, guidance_scale: float = 1.0, next_input=None):
         coeffs, _ = self.coefficients(int(timestep), timestep_back, have_old)
-        self._launch(model_out, latents, old_x0, noise, cfg_copies, guidance_scale, coeffs)
+        self._launch(model_out, latents, old_x0, noise, cfg_copies, guidance_scale, coeffs, next_input)
 
 
 def _randn(shape, generator, device, dtype):
