@@ -518,6 +518,31 @@ def sample_loop(sd, cfg, sched: Scheduler, latents: Tensor, image_latents: Tenso
     return latents
 
 
+def pipeline_call(sd, cfg, kind: str, moments: Tensor, prompt_embeds: Tensor, num_frames: int, height: int,
+                  width: int, num_steps: int, guidance_scale: float, generator: torch.Generator,
+                  actions: Optional[Tensor] = None, negative_prompt_embeds: Optional[Tensor] = None,
+                  scaling_factor: float = 1.15258426, **fwd_kwargs) -> Tensor:
+    """CogVideoXImageToVideoPipelineTraj.__call__ for latent-moment inputs and output_type='latent', patch_size_t
+    None (:1227-1489): prepare_latents (:1115-1225: sample first-frame moments, scale, zero-pad to F frames, initial
+    noise) followed by the denoise loop.  RNG draws happen in the reference's order on `generator`."""
+    dt = prompt_embeds.dtype
+    B = prompt_embeds.shape[0]
+    if guidance_scale > 1.0:
+        prompt_embeds = torch.cat([negative_prompt_embeds, prompt_embeds], dim=0)
+    lat_frames = (num_frames - 1) // 4 + 1
+    moments = moments.to(dt)
+    mean, logvar = torch.chunk(moments, 2, dim=1)
+    std = torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0))
+    img = mean + std * torch.randn(mean.shape, generator=generator, dtype=dt)
+    img = (scaling_factor * img).permute(0, 2, 1, 3, 4)  # [B, F_img, C, h, w]
+    pad = torch.zeros(B, lat_frames - img.shape[1], img.shape[2], height // 8, width // 8, dtype=dt)
+    image_latents = torch.cat([img, pad], dim=1)
+    latents = torch.randn((B, lat_frames, img.shape[2], height // 8, width // 8), generator=generator, dtype=dt)
+    sched = Scheduler(kind)
+    return sample_loop(sd, cfg, sched, latents, image_latents, prompt_embeds, num_steps, guidance_scale, generator,
+                       actions=actions, **fwd_kwargs)
+
+
 # ------------------------------------------------------------------------------------------------------------
 # synthetic weights (SURVEY §8d): every path contributes, small std so 30 layers stay well-conditioned
 # ------------------------------------------------------------------------------------------------------------

@@ -1,0 +1,89 @@
+"""CPU: the flat oracle against the golden vectors produced by the reference's OWN code (oracle/make_golden.py
+runs /root/reference/orv/models/cogvideox_control.py unmodified on oracle/shim).  fp32 on both sides: the bound is
+the north-star's rtol=1e-3 / atol=1e-4 (observed differences are ~1e-6, pure summation-order noise)."""
+import hashlib
+import os
+
+import pytest
+import torch
+
+from oracle import flat_oracle as O
+from oracle import make_golden as G
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RTOL, ATOL = 1e-3, 1e-4
+
+
+def load(name):
+    return torch.load(os.path.join(GOLDEN, name + ".pt"), weights_only=False)
+
+
+@pytest.mark.parametrize("name", sorted(G.FORWARD_CASES))
+def test_forward_matches_reference_golden(name):
+    blob = load(name)
+    cfg, sd, inp, rope, ofs, t, V = G.build_case(name)
+    assert G.digest(sd) == blob["weights_sha256"], "seeded weights differ from the ones the golden was made with"
+    assert G.digest({k: v for k, v in inp.items() if v is not None}) == blob["inputs_sha256"]
+    with torch.no_grad():
+        out = O.forward(sd, cfg, inp["hidden_states"], inp["text"], t, actions=inp["actions"],
+                        depths=inp.get("depths"), labels=inp.get("labels"), ofs=ofs, rope=rope, num_views=V)
+    torch.testing.assert_close(out, blob["output"], rtol=RTOL, atol=ATOL)
+
+
+def test_action_embed_mask_matches_reference_golden():
+    """Bug-compatibility vector: the reference masks ~10 % of samples even in eval."""
+    blob = load("action_embed_mask")
+    assert blob["mask_attr"] is True
+    cfg = O.default_config(**G.BASE)
+    sd = O.synthetic_state_dict(cfg, seed=0, std=0.05)
+    acts = O.synthetic_inputs(cfg, 16, 3, 6, 8, seed=1, n_actions=8)["actions"]
+    torch.manual_seed(5)
+    is_mask = torch.rand(16) < 0.1
+    assert torch.equal(is_mask, blob["is_mask"])
+    emb = O.action_embed(sd, cfg, acts, is_mask)
+    torch.testing.assert_close(emb, blob["emb"], rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("kind,steps,guidance", [("ddim", 2, 1.0), ("dpm", 4, 1.0), ("dpm", 3, 6.0)])
+def test_sampler_matches_reference_pipeline_golden(kind, steps, guidance):
+    blob = load(f"sampler_{kind}_{steps}steps_g{int(guidance)}")
+    cfg = O.default_config(**G.BASE)
+    sd = O.synthetic_state_dict(cfg, seed=0, std=0.05)
+    assert G.digest(sd) == blob["weights_sha256"]
+    inp = O.synthetic_inputs(cfg, 1, 3, 6, 8, seed=1, n_actions=8)
+    gen = torch.Generator().manual_seed(42)
+    with torch.no_grad():
+        lat = O.pipeline_call(sd, cfg, kind, blob["moments"], inp["text"], 9, 48, 64, steps, guidance, gen,
+                              actions=None if guidance > 1.0 else inp["actions"],
+                              negative_prompt_embeds=torch.zeros_like(inp["text"]))
+    torch.testing.assert_close(lat, blob["latents"], rtol=RTOL, atol=ATOL)
+
+
+def test_patchify_closed_form_matches_reshape_chain():
+    """Integer index maps: bit-exact."""
+    for (Fr, C, H, W, pt) in [(3, 4, 6, 8, None), (4, 4, 6, 8, 2), (5, 32, 40, 60, None)]:
+        x = torch.arange(Fr * C * H * W, dtype=torch.int64).reshape(1, Fr, C, H, W)
+        idx = O.patchify_index_map(Fr, C, H, W, 2, pt)
+        if pt is None:
+            # conv2d(k=2,s=2) as unfold: K index = c*4 + kh*2 + kw, tokens (f, i, j)
+            u = x.reshape(Fr, C, H // 2, 2, W // 2, 2).permute(0, 2, 4, 1, 3, 5).reshape(Fr * (H // 2) * (W // 2), C * 4)
+        else:
+            u = x.permute(0, 1, 3, 4, 2).reshape(1, Fr // pt, pt, H // 2, 2, W // 2, 2, C)
+            u = u.permute(0, 1, 3, 5, 7, 2, 4, 6).flatten(4, 7).flatten(1, 3)[0]
+        assert torch.equal(x.flatten()[idx], u)
+
+
+def test_scheduler_timesteps_and_terminal_snr():
+    s = O.Scheduler("dpm")
+    s.set_timesteps(50)
+    assert s.timesteps.tolist() == list(range(999, 0, -20))
+    assert float(s.alphas_cumprod[-1]) == 0.0          # zero terminal SNR
+    a0 = 1 - 0.00085
+    assert abs(float(s.alphas_cumprod[0]) - a0 / (3.0 - 2.0 * a0)) < 1e-12  # snr_shift_scale = 3
+    s.set_timesteps(2)
+    assert s.timesteps.tolist() == [999, 499]
+
+
+def test_golden_files_are_small():
+    total = sum(os.path.getsize(os.path.join(GOLDEN, f)) for f in os.listdir(GOLDEN))
+    assert total < 2 * 1024 * 1024
