@@ -130,6 +130,11 @@ typedef struct orvb_ln_args {
   const void* pre_w; const void* pre_b; /* optional first LayerNorm (norm_final, cogvideox_control.py:909-916)
                                            applied before the modulated one; bf16 [dim] or NULL */
   float pre_eps;
+  /* Optional pre-combined table (bf16, row pitch ab_ld >= 4*dim): per group row
+   * [text A | text B | video A | video B] with A = ln_w*(1+scale), B = ln_b*(1+scale)+shift.  When set, ln_w/ln_b/mod
+   * are ignored and y = xhat*A + B (what orvb_forward uses: one table build per forward instead of four vector
+   * loads per element). */
+  const void* ab; int32_t ab_ld;
 } orvb_ln_args;
 int orvb_ln_modulate(const orvb_ln_args* args, void* stream);
 

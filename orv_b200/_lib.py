@@ -51,6 +51,7 @@ class LnArgs(C.Structure):
         ("rowmap", RowMap),
         ("in_video_only", c_int),
         ("pre_w", c_void_p), ("pre_b", c_void_p), ("pre_eps", c_float),
+        ("ab", c_void_p), ("ab_ld", c_int),
     ]
 
 

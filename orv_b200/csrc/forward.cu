@@ -29,6 +29,7 @@ struct orvb_model {
   std::vector<orvb_block_weights> mv_blocks;
   bool bound = false;
   orvb::SkinnyJob* jobs_dev = nullptr;  // [sites] AdaLN job table (device metadata owned by the library)
+  orvb::AbSite* ab_sites_dev = nullptr; // [sites] LayerNorm A/B-table build descriptors
   float* jobs_y_base = nullptr;         // modulation-table base the job table currently points at
   size_t jobs_site_stride = 0;
   int launches = 0;
@@ -77,6 +78,7 @@ static int make_geometry(const orvb_config& c, const orvb_shape& s, Geometry* g)
 struct Workspace {
   bf16 *x, *xn, *qkv, *att, *ffh, *patches, *ctrl, *yout;
   float *tsin, *t1, *temb, *osin, *o1, *oemb, *act_in, *act_h, *act_emb, *emb, *mod;
+  bf16* ab;
   size_t bytes;
 };
 
@@ -112,6 +114,7 @@ static void carve(const orvb_config& c, const Geometry& g, uint8_t* base, Worksp
   ws->act_emb = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * fa * g.T * 4));
   ws->emb = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * g.G * g.T * 4));
   ws->mod = reinterpret_cast<float*>(take(static_cast<size_t>(g.sites) * g.B * g.G * 6 * D * 4));
+  ws->ab = reinterpret_cast<bf16*>(take(static_cast<size_t>(g.sites) * g.B * g.G * 4 * D * 2));
   ws->bytes = off;
 }
 
@@ -312,17 +315,34 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
     }
     // synchronous small copy: happens once per (model, workspace) pair, outside any graph capture
     ORVB_CHECK_CUDA(cudaMemcpy(m->jobs_dev, jobs.data(), jobs.size() * sizeof(SkinnyJob), cudaMemcpyHostToDevice));
+    const size_t ab_stride = static_cast<size_t>(g.B) * g.G * 4 * D;
+    std::vector<AbSite> sites(2 * c.layers + 1);
+    for (int l = 0; l < c.layers; ++l) {
+      const orvb_block_weights& bw = m->blocks[l];
+      sites[2 * l] = AbSite{static_cast<const bf16*>(bw.norm1_ln_w), static_cast<const bf16*>(bw.norm1_ln_b),
+                            ws.mod + (2 * l) * site_stride, 6 * D, 3 * D, 0, ws.ab + (2 * l) * ab_stride};
+      sites[2 * l + 1] = AbSite{static_cast<const bf16*>(bw.norm2_ln_w), static_cast<const bf16*>(bw.norm2_ln_b),
+                                ws.mod + (2 * l + 1) * site_stride, 6 * D, 3 * D, 0, ws.ab + (2 * l + 1) * ab_stride};
+    }
+    // norm_out (AdaLayerNorm, shift first, pitch 2D): only the video variant is ever read
+    sites[2 * c.layers] = AbSite{static_cast<const bf16*>(w.norm_out_ln_w), static_cast<const bf16*>(w.norm_out_ln_b),
+                                 ws.mod + static_cast<size_t>(2 * c.layers) * site_stride, 2 * D, 0, 0,
+                                 ws.ab + static_cast<size_t>(2 * c.layers) * ab_stride};
+    ORVB_CHECK_CUDA(cudaMemcpy(m->ab_sites_dev, sites.data(), sites.size() * sizeof(AbSite), cudaMemcpyHostToDevice));
     m->jobs_y_base = ws.mod;
     m->jobs_site_stride = site_stride;
   }
   ORVB_TRY(skinny_linear_launch(ws.emb, SkinnyJob{nullptr, nullptr, nullptr}, m->jobs_dev, 2 * c.layers, g.B * g.G,
                                 6 * D, T, 0, st));
-  float* mod_out = ws.mod + static_cast<size_t>(2 * c.layers) * site_stride;  // norm_out table, row pitch 6D
+  float* mod_out = ws.mod + static_cast<size_t>(2 * c.layers) * site_stride;  // norm_out table, row pitch 2D
   {
-    // norm_out.linear is [2D, T]; written with pitch 2D into its slot (mod_ld = 2D below)
+    // norm_out.linear is [2D, T]; written with pitch 2D into its slot
     ORVB_TRY(skinny_linear_launch(ws.emb, SkinnyJob{static_cast<const bf16*>(w.norm_out_lin_w), static_cast<const bf16*>(w.norm_out_lin_b), mod_out},
                                   nullptr, 1, g.B * g.G, 2 * D, T, 0, st));
   }
+  // fold LayerNorm affine + (shift, scale) of every site into bf16 A/B tables for the LN kernels
+  ORVB_TRY(ab_combine_launch(m->ab_sites_dev, 2 * c.layers + 1, g.B * g.G, D, st));
+  const size_t ab_stride = static_cast<size_t>(g.B) * g.G * 4 * D;
 
   orvb_rowmap rm;
   rm.seq_len = g.S; rm.text_len = g.St;
@@ -392,7 +412,8 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
     memset(&ln, 0, sizeof(ln));
     ln.x = ws.x; ln.y = ws.xn; ln.ln_w = bw.norm1_ln_w; ln.ln_b = bw.norm1_ln_b;
     ln.rows = g.R; ln.dim = D; ln.eps = c.norm_eps;
-    ln.mod = mod1; ln.mod_ld = 6 * D; ln.text_off = 3 * D; ln.video_off = 0; ln.rowmap = rm;
+    ln.rowmap = rm;
+    ln.ab = ws.ab + (2 * l) * ab_stride; ln.ab_ld = 4 * D;
     ORVB_CLS(ORVB_PC_LN);
     ORVB_TRY(ln_modulate_launch(&ln, st));
 
@@ -412,7 +433,7 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
     ORVB_CLS(ORVB_PC_OUT);
     ORVB_TRY(gemm_run(&o, st));
 
-    ln.ln_w = bw.norm2_ln_w; ln.ln_b = bw.norm2_ln_b; ln.mod = mod2;
+    ln.ab = ws.ab + (2 * l + 1) * ab_stride;
     ORVB_CLS(ORVB_PC_LN);
     ORVB_TRY(ln_modulate_launch(&ln, st));
 
@@ -438,7 +459,8 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
     ln.pre_w = w.norm_final_w; ln.pre_b = w.norm_final_b; ln.pre_eps = c.norm_eps;
     ln.ln_w = w.norm_out_ln_w; ln.ln_b = w.norm_out_ln_b; ln.eps = c.norm_eps;
     ORVB_CLS(ORVB_PC_HEAD);
-    ln.mod = mod_out; ln.mod_ld = 2 * D; ln.text_off = 0; ln.video_off = 0; ln.rowmap = rm; ln.in_video_only = 1;
+    ln.rowmap = rm; ln.in_video_only = 1;
+    ln.ab = ws.ab + static_cast<size_t>(2 * c.layers) * ab_stride; ln.ab_ld = 4 * D;
     ORVB_TRY(ln_modulate_launch(&ln, st));
     orvb_gemm_args po = gemm_base(ws.xn, w.proj_out_w, w.proj_out_b, ws.yout, g.B * g.Sv, g.Nout, D, D, g.Nout,
                                   ORVB_EPI_BIAS);
@@ -482,6 +504,13 @@ extern "C" int orvb_model_create(const orvb_config* cfg, orvb_model** out) {
     set_error("orvb_model_create: cudaMalloc(job table) failed: %s", cudaGetErrorString(e));
     return ORVB_ECUDA;
   }
+  e = cudaMalloc(&m->ab_sites_dev, sizeof(AbSite) * (3 * cfg->layers + 1));
+  if (e != cudaSuccess) {
+    cudaFree(m->jobs_dev);
+    delete m;
+    set_error("orvb_model_create: cudaMalloc(site table) failed: %s", cudaGetErrorString(e));
+    return ORVB_ECUDA;
+  }
   *out = m;
   return ORVB_OK;
 }
@@ -489,6 +518,7 @@ extern "C" int orvb_model_create(const orvb_config* cfg, orvb_model** out) {
 extern "C" void orvb_model_destroy(orvb_model* m) {
   if (m == nullptr) return;
   if (m->jobs_dev) cudaFree(m->jobs_dev);
+  if (m->ab_sites_dev) cudaFree(m->ab_sites_dev);
   for (cudaEvent_t e : m->ev) cudaEventDestroy(e);
   delete m;
 }

@@ -372,20 +372,21 @@ static int launch_gemm_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb
 
 // Picks the N tile that minimises (waves x tile cost) on this GPU for a persistent 1-CTA/SM launch.
 int gemm_pick_bn(int m, int n) {
+  // Cost model fitted to B200 measurements of this kernel (profiles/r01_gemm_tiles.md): one wave of 128 x BN
+  // tiles costs ~ (7.6 + 0.0184 * BN) units, nearly independent of how full the wave is (the mainloop is
+  // L2->SM bandwidth bound: 16 KB of A + BN*128 B of B per 128 x BN x 64 step).
   const int sms = sm_count();
   const int mt = (m + BM - 1) / BM;
-  int best_bn = 128;
+  int best_bn = 64;
   double best = 1e30;
-  const int cands[3] = {256, 128, 64};
-  for (int i = 0; i < 3; ++i) {
+  const int cands[4] = {256, 192, 128, 64};
+  for (int i = 0; i < 4; ++i) {
     int bn = cands[i];
     if (bn > 64 && n < bn) continue;
     int nt = (n + bn - 1) / bn;
     long tiles = static_cast<long>(mt) * nt;
     long waves = (tiles + sms - 1) / sms;
-    // per-tile cost model: MMA time ~ bn, plus a fixed per-tile overhead; small tiles are smem-bandwidth bound
-    double tile_cost = bn * (bn >= 256 ? 1.0 : (bn >= 128 ? 1.12 : 1.5)) + 8.0;
-    double cost = waves * tile_cost;
+    double cost = waves * (7.6 + 0.0184 * bn);
     if (cost < best) {
       best = cost;
       best_bn = bn;
@@ -398,6 +399,7 @@ int gemm_launch_prepared(const CUtensorMap& ta, const CUtensorMap& tb, const Gem
                          cudaStream_t stream) {
   switch (bn) {
     case 256: return launch_gemm_epi<256>(epi, ta, tb, p, stream);
+    case 192: return launch_gemm_epi<192>(epi, ta, tb, p, stream);
     case 128: return launch_gemm_epi<128>(epi, ta, tb, p, stream);
     case 64: return launch_gemm_epi<64>(epi, ta, tb, p, stream);
   }

@@ -45,6 +45,8 @@ struct LnDev {
   int mod_ld, text_off, video_off, scale_first;
   orvb_rowmap rm;
   int in_video_only;
+  const bf16* ab;  // optional pre-combined table: per group row [text A | text B | video A | video B], each `dim`
+  int ab_ld;
 };
 
 template <int MAXC>
@@ -113,6 +115,40 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const LnDev p) {
       }
     }
   }
+  bf16* yr = p.y + static_cast<size_t>(row) * p.dim;
+  if (p.ab != nullptr) {
+    // y = xhat * A_g + B_g with A = w * (1 + scale), B = b * (1 + scale) + shift folded once per forward
+    // (ab_combine_kernel): one memory phase, every load issued before the reductions.
+    int is_text;
+    const int g = row_group_pw(p.rm, in_row, &is_text);
+    const bf16* ap = p.ab + static_cast<size_t>(g) * p.ab_ld + (is_text ? 0 : 2 * p.dim);
+    uint4 av[MAXC], bv[MAXC];
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nchunks) {
+        av[i] = *reinterpret_cast<const uint4*>(ap + c * 8);
+        bv[i] = *reinterpret_cast<const uint4*>(ap + p.dim + c * 8);
+      }
+    }
+    ln_stats<MAXC>(v, nchunks, lane, p.dim, p.eps, &mean, &rstd);
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nchunks) {
+        float a8[8], b8[8], o[8];
+        unpack8(av[i], a8);
+        unpack8(bv[i], b8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * a8[j] + b8[j];
+        uint4 u;
+        u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]);
+        u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
+        *reinterpret_cast<uint4*>(yr + c * 8) = u;
+      }
+    }
+    return;
+  }
   ln_stats<MAXC>(v, nchunks, lane, p.dim, p.eps, &mean, &rstd);
 
   const float* shift = nullptr;
@@ -124,7 +160,6 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const LnDev p) {
     shift = p.scale_first ? base + p.dim : base;
     scale = p.scale_first ? base : base + p.dim;
   }
-  bf16* yr = p.y + static_cast<size_t>(row) * p.dim;
 #pragma unroll
   for (int i = 0; i < MAXC; ++i) {
     const int c = lane + 32 * i;
@@ -157,6 +192,34 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const LnDev p) {
   }
 }
 
+// A/B table for the LayerNorm+modulate kernel, built once per forward from the fp32 AdaLN tables:
+//   text  variant: A = w (1 + mod[g][text_off + D ..]),  B = b (1 + ...) + mod[g][text_off ..]
+//   video variant: A = w (1 + mod[g][video_off + D ..]), B = b (1 + ...) + mod[g][video_off ..]
+// One block row per (site, group); sites are described by a device array (weights differ per site).
+__global__ void ab_combine_kernel(const AbSite* __restrict__ sites, int groups, int dim) {
+  const AbSite st = sites[blockIdx.z];
+  const int g = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= dim) return;
+  const float w = st.ln_w ? __bfloat162float(st.ln_w[c]) : 1.f;
+  const float b = st.ln_b ? __bfloat162float(st.ln_b[c]) : 0.f;
+  const float* m = st.mod + static_cast<size_t>(g) * st.mod_ld;
+  bf16* o = st.ab + static_cast<size_t>(g) * 4 * dim;
+  const float ts = 1.f + m[st.text_off + dim + c], th = m[st.text_off + c];
+  const float vs = 1.f + m[st.video_off + dim + c], vh = m[st.video_off + c];
+  o[c] = __float2bfloat16(w * ts);
+  o[dim + c] = __float2bfloat16(b * ts + th);
+  o[2 * dim + c] = __float2bfloat16(w * vs);
+  o[3 * dim + c] = __float2bfloat16(b * vs + vh);
+}
+
+int ab_combine_launch(const AbSite* sites_dev, int num_sites, int groups, int dim, cudaStream_t stream) {
+  dim3 grid((dim + 255) / 256, groups, num_sites);
+  ab_combine_kernel<<<grid, 256, 0, stream>>>(sites_dev, groups, dim);
+  ORVB_CHECK_CUDA(cudaGetLastError());
+  return ORVB_OK;
+}
+
 int ln_modulate_launch(const orvb_ln_args* a, cudaStream_t stream) {
   ORVB_REQUIRE(a && a->x && a->y, ORVB_EINVAL, "orvb_ln_modulate: null pointer");
   ORVB_REQUIRE(a->rows > 0 && a->dim > 0 && a->dim % 8 == 0 && a->dim <= 4096, ORVB_ESHAPE,
@@ -173,6 +236,9 @@ int ln_modulate_launch(const orvb_ln_args* a, cudaStream_t stream) {
   d.rows = a->rows; d.dim = a->dim; d.eps = a->eps; d.pre_eps = a->pre_eps;
   d.mod = a->mod; d.mod_ld = a->mod_ld; d.text_off = a->text_off; d.video_off = a->video_off;
   d.scale_first = a->scale_first; d.rm = a->rowmap; d.in_video_only = a->in_video_only;
+  d.ab = static_cast<const bf16*>(a->ab); d.ab_ld = a->ab_ld;
+  ORVB_REQUIRE(d.ab == nullptr || (a->ab_ld % 8 == 0 && a->ab_ld >= 4 * a->dim), ORVB_ESHAPE,
+               "orvb_ln_modulate: ab_ld must be a multiple of 8 and >= 4*dim");
   const int rows_per_block = 8;
   dim3 grid((a->rows + rows_per_block - 1) / rows_per_block);
   const int nchunks = a->dim / 8;
@@ -189,19 +255,24 @@ int ln_modulate_launch(const orvb_ln_args* a, cudaStream_t stream) {
 // with 16-byte loads and reuses the fp32 activations (L1-resident) across them.
 // ---------------------------------------------------------------------------------------------------
 constexpr int SK_ROWS = 8;
-constexpr int SK_COLS = 4;
+constexpr int SK_COLS = 8;
+constexpr int SK_WARPS = 8;
 
 template <bool BATCHED>
 __global__ void __launch_bounds__(256) skinny_linear_kernel(const float* __restrict__ x, SkinnyJob single,
                                                             const SkinnyJob* __restrict__ jobs, int rows, int n,
                                                             int k, int act) {
+  extern __shared__ float sx[];  // [nr][k] activations of this row chunk, shared by the 64 columns of the block
   const SkinnyJob job = BATCHED ? jobs[blockIdx.z] : single;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int n0 = (blockIdx.x * (blockDim.x >> 5) + warp) * SK_COLS;
-  if (n0 >= n) return;
   const int r0 = blockIdx.y * SK_ROWS;
   const int nr = min(SK_ROWS, rows - r0);
+  for (int i = threadIdx.x * 4; i < nr * k; i += blockDim.x * 4)
+    *reinterpret_cast<float4*>(sx + i) = *reinterpret_cast<const float4*>(x + static_cast<size_t>(r0) * k + i);
+  __syncthreads();
+  const int n0 = (blockIdx.x * SK_WARPS + warp) * SK_COLS;
+  if (n0 >= n) return;
   float acc[SK_ROWS][SK_COLS];
 #pragma unroll
   for (int r = 0; r < SK_ROWS; ++r)
@@ -209,26 +280,25 @@ __global__ void __launch_bounds__(256) skinny_linear_kernel(const float* __restr
     for (int c = 0; c < SK_COLS; ++c) acc[r][c] = 0.f;
 
   for (int k0 = lane * 8; k0 < k; k0 += 256) {
-    float w[SK_COLS][8];
+    uint4 wq[SK_COLS];
 #pragma unroll
-    for (int c = 0; c < SK_COLS; ++c) {
-      if (n0 + c < n) {
-        unpack8(*reinterpret_cast<const uint4*>(job.w + static_cast<size_t>(n0 + c) * k + k0), w[c]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) w[c][j] = 0.f;
-      }
+    for (int c = 0; c < SK_COLS; ++c) {  // all weight loads of this step in flight before any math
+      if (n0 + c < n) wq[c] = *reinterpret_cast<const uint4*>(job.w + static_cast<size_t>(n0 + c) * k + k0);
+      else wq[c] = make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
     for (int r = 0; r < SK_ROWS; ++r) {
       if (r < nr) {
-        const float4 a0 = *reinterpret_cast<const float4*>(x + static_cast<size_t>(r0 + r) * k + k0);
-        const float4 a1 = *reinterpret_cast<const float4*>(x + static_cast<size_t>(r0 + r) * k + k0 + 4);
+        const float4 a0 = *reinterpret_cast<const float4*>(sx + r * k + k0);
+        const float4 a1 = *reinterpret_cast<const float4*>(sx + r * k + k0 + 4);
         const float xv[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-        for (int c = 0; c < SK_COLS; ++c)
+        for (int c = 0; c < SK_COLS; ++c) {
+          float w[8];
+          unpack8(wq[c], w);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[r][c] = fmaf(xv[j], w[c][j], acc[r][c]);
+          for (int j = 0; j < 8; ++j) acc[r][c] = fmaf(xv[j], w[j], acc[r][c]);
+        }
       }
     }
   }
@@ -257,11 +327,19 @@ __global__ void __launch_bounds__(256) skinny_linear_kernel(const float* __restr
 int skinny_linear_launch(const float* x, const SkinnyJob& job, const SkinnyJob* jobs_dev, int num_jobs, int rows,
                          int n, int k, int act, cudaStream_t stream) {
   ORVB_REQUIRE(x != nullptr && rows > 0 && n > 0 && k > 0, ORVB_EINVAL, "orvb_skinny_linear: bad arguments");
-  ORVB_REQUIRE(k % 8 == 0, ORVB_ESHAPE, "orvb_skinny_linear: k must be a multiple of 8 (got %d)", k);
-  const int cols_per_block = 8 * SK_COLS;
+  ORVB_REQUIRE(k % 8 == 0 && k <= 12288, ORVB_ESHAPE, "orvb_skinny_linear: k must be a multiple of 8 and <= 12288 (got %d)", k);
+  const int cols_per_block = SK_WARPS * SK_COLS;
+  const int smem = SK_ROWS * k * static_cast<int>(sizeof(float));
   dim3 grid((n + cols_per_block - 1) / cols_per_block, (rows + SK_ROWS - 1) / SK_ROWS, jobs_dev ? num_jobs : 1);
-  if (jobs_dev != nullptr) skinny_linear_kernel<true><<<grid, 256, 0, stream>>>(x, job, jobs_dev, rows, n, k, act);
-  else skinny_linear_kernel<false><<<grid, 256, 0, stream>>>(x, job, nullptr, rows, n, k, act);
+  static bool attr_set = false;
+  if (!attr_set) {
+    ORVB_CHECK_CUDA(cudaFuncSetAttribute(skinny_linear_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    ORVB_CHECK_CUDA(cudaFuncSetAttribute(skinny_linear_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  ORVB_REQUIRE(smem <= 200 * 1024, ORVB_ESHAPE, "orvb_skinny_linear: k too large for the shared-memory staging");
+  if (jobs_dev != nullptr) skinny_linear_kernel<true><<<grid, 256, smem, stream>>>(x, job, jobs_dev, rows, n, k, act);
+  else skinny_linear_kernel<false><<<grid, 256, smem, stream>>>(x, job, nullptr, rows, n, k, act);
   ORVB_CHECK_CUDA(cudaGetLastError());
   return ORVB_OK;
 }

@@ -10,6 +10,17 @@ struct SkinnyJob {
   float* y;       // [rows, n]
 };
 
+// one AdaLN site for ab_combine: LayerNorm affine (bf16 [dim] or null), its fp32 modulation table and the bf16
+// output table [groups][4*dim]
+struct AbSite {
+  const bf16* ln_w;
+  const bf16* ln_b;
+  const float* mod;
+  int mod_ld, text_off, video_off;
+  bf16* ab;
+};
+int ab_combine_launch(const AbSite* sites_dev, int num_sites, int groups, int dim, cudaStream_t stream);
+
 int ln_modulate_launch(const orvb_ln_args* a, cudaStream_t stream);
 int skinny_linear_launch(const float* x, const SkinnyJob& job, const SkinnyJob* jobs_dev, int num_jobs, int rows,
                          int n, int k, int act, cudaStream_t stream);
