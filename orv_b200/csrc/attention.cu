@@ -4,18 +4,21 @@
 //                         B = V smem MN-major, D accumulates in TMEM)
 // replacing F.scaled_dot_product_attention at reference orv/models/cogvideox_control.py:256-258.
 //
-// One CTA per (128-query tile, head, batch); two CTAs are co-resident per SM.  Warp roles (320 threads):
-//   warps 0-3  softmax stream A: key columns [0,64) of every 128-key tile, one query row per thread
-//   warps 4-7  softmax stream B: key columns [64,128)
-//   warp  8    TMA producer (Q once, K/V double-buffered through one 3-D tensor map over the packed QKV buffer)
-//   warp  9    TMEM allocator + single-thread MMA issuer
-// The two streams are independent flash-attention accumulations (own running max / sum and own TMEM output
+// One CTA per (PAIR of 128-query tiles, head, batch), one CTA per SM.  Warp roles (576 threads):
+//   warps 0-7   query tile 0: warps 0-3 softmax stream A (key columns [0,64) of every 128-key tile, one query row
+//               per thread), warps 4-7 stream B (key columns [64,128))
+//   warps 8-15  query tile 1, same split
+//   warp  16    TMA producer (both Q tiles once, K/V triple-buffered, shared by the two query tiles)
+//   warp  17    TMEM allocator + MMA issuer, alternating between the two query tiles
+// The two streams of a tile are independent flash-attention accumulations (own running max / sum and own TMEM output
 // accumulator, combined once at the end like a split-KV reduction), which doubles the number of softmax warps
 // hiding MUFU / TMEM latency without any per-tile cross-thread reduction.  Output accumulators stay in TMEM; the
 // running max is only raised when a tile exceeds it by more than 2^8 (lazy rescale), so the TMEM read-modify-write
-// correction is rare.
+// correction is rare.  Rows past seq_len are zero-filled by TMA and masked in the softmax.
 //
-// Rows past seq_len are zero-filled by TMA and masked in the softmax.
+// Measured structure notes (profiles/r01_attention_notes.md): at head_dim 64 the kernel is bound by the per-tile
+// chain  QK^T -> s_full hop -> max pass -> exp pass (MUFU, 16/clk/SM) -> p_full hop -> MMA issue, not by the tensor
+// pipe; two query tiles per SM give two chains in flight.
 #include "common.cuh"
 #include "pointwise.cuh"
 #include "ptx.cuh"
@@ -25,11 +28,13 @@ namespace orvb {
 constexpr int ATT_BQ = 128;
 constexpr int ATT_BK = 128;
 constexpr int ATT_D = 64;
-constexpr int ATT_THREADS = 320;
-constexpr int ATT_STAGES = 2;
+constexpr int ATT_THREADS = 576;
+constexpr int ATT_STAGES = 3;
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: one [128 x 64] bf16 tile
-constexpr int ATT_SMEM_BYTES = ATT_TILE_BYTES /*Q*/ + ATT_STAGES * 2 * ATT_TILE_BYTES /*K,V*/ + 2 * ATT_TILE_BYTES /*P*/ + 256;
-constexpr int ATT_TMEM_COLS = 256;  // S: [0,128)  O_A: [128,192)  O_B: [192,256)
+// per query tile: [Q 16 KB][P 32 KB] contiguous (reused for the end-of-kernel stream exchange), then K/V stages
+constexpr int ATT_QP_BYTES = 3 * ATT_TILE_BYTES;
+constexpr int ATT_SMEM_BYTES = 2 * ATT_QP_BYTES + ATT_STAGES * 2 * ATT_TILE_BYTES + 256;
+constexpr int ATT_TMEM_COLS = 512;  // S_t: [t*128, +128)   O_{t,stream}: [256 + t*128 + stream*64, +64)
 constexpr int ATT_XCH_STRIDE = 67;  // floats per row of the end-of-kernel stream exchange (conflict-free)
 constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units
 
@@ -45,33 +50,32 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+__global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttDev p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + ATT_TILE_BYTES;                    // [stage]
+  // [Q0 | P0 (2 sub-tiles)] [Q1 | P1] [K stages] [V stages] [barriers]
+  uint8_t* sK = smem + 2 * ATT_QP_BYTES;                // [stage]
   uint8_t* sV = sK + ATT_STAGES * ATT_TILE_BYTES;       // [stage]
-  uint8_t* sP = sV + ATT_STAGES * ATT_TILE_BYTES;       // two [128 x 64] K-major sub-tiles (stream A, stream B)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * ATT_TILE_BYTES);
-  uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;              // [2]
-  uint64_t* v_full = bars + 3;              // [2]
-  uint64_t* kv_empty = bars + 5;            // [2]
-  uint64_t* s_full = bars + 7;
-  uint64_t* p_full = bars + 8;
-  uint64_t* o_full = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT_STAGES * ATT_TILE_BYTES);
+  uint64_t* q_full = bars;                  // both Q tiles
+  uint64_t* k_full = bars + 1;              // [3]
+  uint64_t* v_full = bars + 4;              // [3]
+  uint64_t* kv_empty = bars + 7;            // [3]
+  uint64_t* s_full = bars + 10;             // [2] per query tile
+  uint64_t* p_full = bars + 12;             // [2]
+  uint64_t* o_full = bars + 14;             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q_tile = blockIdx.x;
+  const int q_pair = blockIdx.x;
   const int head = blockIdx.y;
   const int batch = blockIdx.z;
   const int n_kv = (p.seq_len + ATT_BK - 1) / ATT_BK;
 
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128B-swizzle atoms need 1024-byte aligned tiles
 
-  if (warp == 8 && lane == 0) {
+  if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&tma_qkv);
     mbar_init(q_full, 1);
     for (int i = 0; i < ATT_STAGES; ++i) {
@@ -79,12 +83,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttDev p) {
       mbar_init(&v_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 256);
-    mbar_init(o_full, 1);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_full[t], 256);
+      mbar_init(&o_full[t], 1);
+    }
     fence_barrier_init();
   }
-  if (warp == 9) {
+  if (warp == 17) {
     tmem_alloc(tmem_slot, ATT_TMEM_COLS);
     tmem_relinquish();
   }
@@ -92,17 +98,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttDev p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base;        // columns [0,128)
-  const uint32_t tmem_o = tmem_base + 128;  // columns [128,256): O_A | O_B
 
-  if (warp == 8) {
+  if (warp == 16) {
     // ======================================= TMA producer =======================================
     if (lane == 0) {
       const int q_col = head * ATT_D;
       const int k_col = p.dim + head * ATT_D;
       const int v_col = 2 * p.dim + head * ATT_D;
-      mbar_expect_tx(q_full, ATT_TILE_BYTES);
-      tma_load_3d(sQ, &tma_qkv, q_full, q_col, q_tile * ATT_BQ, batch);
+      mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
+      tma_load_3d(smem, &tma_qkv, q_full, q_col, (2 * q_pair) * ATT_BQ, batch);
+      tma_load_3d(smem + ATT_QP_BYTES, &tma_qkv, q_full, q_col, (2 * q_pair + 1) * ATT_BQ, batch);
       for (int j = 0; j < n_kv; ++j) {
         const int st = j % ATT_STAGES;
         const uint32_t ph = static_cast<uint32_t>((j / ATT_STAGES) & 1);
@@ -113,63 +118,75 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttDev p) {
         tma_load_3d(sV + st * ATT_TILE_BYTES, &tma_qkv, &v_full[st], v_col, j * ATT_BK, batch);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 17) {
     // ======================================= MMA issuer =========================================
+    // (One lane owns the loop here: with this kernel's short MMAs the warp-uniform form used in gemm.cu issues
+    //  faster but lets the two query tiles fall into lockstep, which measured slower end to end.)
     if (lane == 0) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128, 0, 0);  // A, B K-major
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);   // B (= V) MN-major
-      const uint64_t q_desc = umma_desc_sw128(smem_u32(sQ));
-      const uint64_t p_desc = umma_desc_sw128(smem_u32(sP));
-      auto issue_qk = [&](int j) {
+      auto issue_qk = [&](int t, int j) {
         const int st = j % ATT_STAGES;
         mbar_wait(&k_full[st], static_cast<uint32_t>((j / ATT_STAGES) & 1));
         tc_fence_after();
+        const uint64_t q_desc = umma_desc_sw128(smem_u32(smem + t * ATT_QP_BYTES));
         const uint64_t k_desc = umma_desc_sw128(smem_u32(sK + st * ATT_TILE_BYTES));
 #pragma unroll
         for (int k = 0; k < ATT_D / 16; ++k)
-          umma_f16_ss(tmem_s, q_desc + static_cast<uint64_t>(k * 2), k_desc + static_cast<uint64_t>(k * 2), idesc_qk,
-                      static_cast<uint32_t>(k != 0));
-        tc_commit(s_full);
+          umma_f16_ss(tmem_base + static_cast<uint32_t>(t * 128), q_desc + static_cast<uint64_t>(k * 2),
+                      k_desc + static_cast<uint64_t>(k * 2), idesc_qk, static_cast<uint32_t>(k != 0));
+        tc_commit(&s_full[t]);
       };
       mbar_wait(q_full, 0);
-      issue_qk(0);
+      issue_qk(0, 0);
+      issue_qk(1, 0);
       for (int j = 0; j < n_kv; ++j) {
         const int st = j % ATT_STAGES;
-        mbar_wait(p_full, static_cast<uint32_t>(j & 1));  // P_j in smem; S_j read; O rescaled if needed
-        tc_fence_after();
-        // S is free again: start the next QK^T first so the next softmax is not held up by P_j V_j.
-        if (j + 1 < n_kv) issue_qk(j + 1);
-        mbar_wait(&v_full[st], static_cast<uint32_t>((j / ATT_STAGES) & 1));
-        tc_fence_after();
-        const uint64_t v_desc = umma_desc_sw128(smem_u32(sV + st * ATT_TILE_BYTES));
+#pragma unroll 1
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&p_full[t], static_cast<uint32_t>(j & 1));  // P_{t,j} in smem; S_t read; O_t rescaled if needed
+          tc_fence_after();
+          // S_t is free again: queue the next QK^T of this query tile first, so its softmax warps can go on while
+          // the tensor core still works on the P V products.
+          if (j + 1 < n_kv) issue_qk(t, j + 1);
+          mbar_wait(&v_full[st], static_cast<uint32_t>((j / ATT_STAGES) & 1));
+          tc_fence_after();
+          const uint64_t p_desc = umma_desc_sw128(smem_u32(smem + t * ATT_QP_BYTES + ATT_TILE_BYTES));
+          const uint64_t v_desc = umma_desc_sw128(smem_u32(sV + st * ATT_TILE_BYTES));
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
+          for (int s = 0; s < 2; ++s) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // A: P sub-tile s (16 KB apart), 32 bytes per K step.  B: keys s*64 + k*16 .. +16 = rows of 128 B.
-            const uint64_t a = p_desc + static_cast<uint64_t>((s * ATT_TILE_BYTES + k * 32) >> 4);
-            const uint64_t b = v_desc + static_cast<uint64_t>(((s * 64 + k * 16) * 128) >> 4);
-            umma_f16_ss(tmem_o + static_cast<uint32_t>(s * 64), a, b, idesc_pv, static_cast<uint32_t>((j | k) != 0));
+            for (int k = 0; k < 4; ++k) {
+              // A: P sub-tile s (16 KB apart), 32 bytes per K step.  B: keys s*64 + k*16 .. +16 = rows of 128 B.
+              const uint64_t a = p_desc + static_cast<uint64_t>((s * ATT_TILE_BYTES + k * 32) >> 4);
+              const uint64_t b = v_desc + static_cast<uint64_t>(((s * 64 + k * 16) * 128) >> 4);
+              umma_f16_ss(tmem_base + static_cast<uint32_t>(256 + t * 128 + s * 64), a, b, idesc_pv,
+                          static_cast<uint32_t>((j | k) != 0));
+            }
           }
+          tc_commit(&o_full[t]);
         }
-        tc_commit(o_full);
-        tc_commit(&kv_empty[st]);
+        tc_commit(&kv_empty[st]);  // K_j / V_j consumed by both query tiles
       }
     }
   } else {
     // ======================================= softmax streams ====================================
-    const int stream = warp >> 2;                    // 0: key columns [0,64) of each tile, 1: [64,128)
+    const int t = warp >> 3;                         // query tile of this warp
+    const int stream = (warp >> 2) & 1;              // 0: key columns [0,64) of each tile, 1: [64,128)
     const int row_in_tile = (warp & 3) * 32 + lane;  // TMEM lane == query row
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t my_s = tmem_s + lane_off + static_cast<uint32_t>(stream * 64);
-    const uint32_t my_o = tmem_o + lane_off + static_cast<uint32_t>(stream * 64);
+    const uint32_t my_s = tmem_base + lane_off + static_cast<uint32_t>(t * 128 + stream * 64);
+    const uint32_t my_o = tmem_base + lane_off + static_cast<uint32_t>(256 + t * 128 + stream * 64);
+    uint64_t* my_s_full = &s_full[t];
+    uint64_t* my_p_full = &p_full[t];
+    uint64_t* my_o_full = &o_full[t];
     float m_run = -INFINITY;  // running (lazy) max in the scaled log2 domain
     float l_run = 0.f;
-    uint8_t* p_row = sP + stream * ATT_TILE_BYTES + row_in_tile * 128;
+    uint8_t* p_row = smem + t * ATT_QP_BYTES + ATT_TILE_BYTES + stream * ATT_TILE_BYTES + row_in_tile * 128;
     const int sw = row_in_tile & 7;
 
     for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(s_full, static_cast<uint32_t>(j & 1));
+      mbar_wait(my_s_full, static_cast<uint32_t>(j & 1));
       tc_fence_after();
       const int valid = p.seq_len - (j * ATT_BK + stream * 64);  // my columns >= valid are padding
       // ---- pass 1: row max over my 64 columns ----
@@ -180,8 +197,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttDev p) {
         tmem_ld_32x32b_x32(my_s + static_cast<uint32_t>(c), r);
         tmem_ld_wait();
         if (valid >= 64) {
+          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;  // 4 chains: no serial FMNMX latency
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+          for (int i = 0; i < 32; i += 4) {
+            m0 = fmaxf(m0, __uint_as_float(r[i]));
+            m1 = fmaxf(m1, __uint_as_float(r[i + 1]));
+            m2 = fmaxf(m2, __uint_as_float(r[i + 2]));
+            m3 = fmaxf(m3, __uint_as_float(r[i + 3]));
+          }
+          mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
@@ -189,9 +213,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttDev p) {
         }
       }
       const float m_tile = mx * p.scale_log2;
-      // PV_{j-1} must have retired before O is corrected or the P buffer is overwritten
+      // PV_{t,j-1} must have retired before O is corrected or the P buffer is overwritten
       if (j > 0) {
-        mbar_wait(o_full, static_cast<uint32_t>((j - 1) & 1));
+        mbar_wait(my_o_full, static_cast<uint32_t>((j - 1) & 1));
         tc_fence_after();
       }
       // ---- lazy rescale: raise the running max only when this tile exceeds it by > 2^8 ----
@@ -216,19 +240,28 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttDev p) {
       }
 
       // ---- pass 2: P = exp2(S * scale_log2 - m_run), bf16, K-major / 128B-swizzled into my smem sub-tile ----
-      float l_add = 0.f;
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+      const float neg_m = -m_run;
 #pragma unroll 1
       for (int c = 0; c < 64; c += 32) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(my_s + static_cast<uint32_t>(c), r);
         tmem_ld_wait();
         float pv[32];
+        if (valid >= 64) {  // tile-uniform fast path: no per-element masking instructions
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float e = ex2(fmaf(__uint_as_float(r[i]), p.scale_log2, -m_run));
-          if (valid < 64 && c + i >= valid) e = 0.f;
-          pv[i] = e;
-          l_add += e;
+          for (int i = 0; i < 32; ++i) pv[i] = ex2(fmaf(__uint_as_float(r[i]), p.scale_log2, neg_m));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            pv[i] = (c + i < valid) ? ex2(fmaf(__uint_as_float(r[i]), p.scale_log2, neg_m)) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          l0 += pv[i];
+          l1 += pv[i + 1];
+          l2 += pv[i + 2];
+          l3 += pv[i + 3];
         }
         const int chunk0 = c >> 3;  // first 16-byte chunk of this 32-column group inside the 128-byte row
 #pragma unroll
@@ -241,55 +274,57 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttDev p) {
           *reinterpret_cast<uint4*>(p_row + (((chunk0 + q) ^ sw) << 4)) = v;
         }
       }
-      l_run += l_add;
+      l_run += (l0 + l1) + (l2 + l3);
       fence_proxy_async_smem();  // make the P stores visible to the tensor-core (async) proxy
       tc_fence_before();         // order our TMEM loads / stores before the MMAs that follow
-      mbar_arrive(p_full);
+      mbar_arrive(my_p_full);
     }
 
-    // ---- combine the two streams, normalise, store ----
-    mbar_wait(o_full, static_cast<uint32_t>((n_kv - 1) & 1));
+    // ---- combine the two streams of this query tile, normalise, store ----
+    mbar_wait(my_o_full, static_cast<uint32_t>((n_kv - 1) & 1));
     tc_fence_after();
-    float acc[ATT_D];
-    {
-      uint32_t o0[32], o1[32];
-      tmem_ld_32x32b_x32(my_o, o0);
-      tmem_ld_32x32b_x32(my_o + 32, o1);
-      tmem_ld_wait();
-#pragma unroll
-      for (int d = 0; d < 32; ++d) {
-        acc[d] = __uint_as_float(o0[d]);
-        acc[32 + d] = __uint_as_float(o1[d]);
-      }
-    }
-    float* xch = reinterpret_cast<float*>(sK) + row_in_tile * ATT_XCH_STRIDE;  // K/V smem is idle by now
+    // this tile's Q/P smem (48 KB) is idle once its last PV retired; O moves in 32-column halves
+    float* xch = reinterpret_cast<float*>(smem + t * ATT_QP_BYTES) + row_in_tile * ATT_XCH_STRIDE;
     if (stream == 1) {
       xch[0] = m_run;
       xch[1] = l_run;
+#pragma unroll 1
+      for (int c = 0; c < ATT_D; c += 32) {
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(my_o + static_cast<uint32_t>(c), o);
+        tmem_ld_wait();
 #pragma unroll
-      for (int d = 0; d < ATT_D; ++d) xch[2 + d] = acc[d];
+        for (int d = 0; d < 32; ++d) xch[2 + c + d] = __uint_as_float(o[d]);
+      }
     }
-    named_bar_sync(1, 256);
+    named_bar_sync(1 + t, 256);
     if (stream == 0) {
       const float m_b = xch[0], l_b = xch[1];
       const float m = fmaxf(m_run, m_b);
       const float wa = (l_run > 0.f) ? ex2(m_run - m) : 0.f;
       const float wb = (l_b > 0.f) ? ex2(m_b - m) : 0.f;
       const float inv = 1.0f / (l_run * wa + l_b * wb);
-      const int q_row = q_tile * ATT_BQ + row_in_tile;
-      if (q_row < p.seq_len) {
-        bf16* op = p.out + (static_cast<size_t>(batch) * p.seq_len + q_row) * p.dim + head * ATT_D;
+      const float ca = wa * inv, cb = wb * inv;
+      const int q_row = (2 * q_pair + t) * ATT_BQ + row_in_tile;
+      bf16* op = p.out + (static_cast<size_t>(batch) * p.seq_len + q_row) * p.dim + head * ATT_D;
+#pragma unroll 1
+      for (int c = 0; c < ATT_D; c += 32) {
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(my_o + static_cast<uint32_t>(c), o);
+        tmem_ld_wait();
+        if (q_row < p.seq_len) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float o[8];
+          for (int q = 0; q < 4; ++q) {
+            float f[8];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) o[t] = (acc[q * 8 + t] * wa + xch[2 + q * 8 + t] * wb) * inv;
-          uint4 v;
-          v.x = pack_bf16(o[0], o[1]);
-          v.y = pack_bf16(o[2], o[3]);
-          v.z = pack_bf16(o[4], o[5]);
-          v.w = pack_bf16(o[6], o[7]);
-          *reinterpret_cast<uint4*>(op + q * 8) = v;
+            for (int u = 0; u < 8; ++u) f[u] = __uint_as_float(o[q * 8 + u]) * ca + xch[2 + c + q * 8 + u] * cb;
+            uint4 v;
+            v.x = pack_bf16(f[0], f[1]);
+            v.y = pack_bf16(f[2], f[3]);
+            v.z = pack_bf16(f[4], f[5]);
+            v.w = pack_bf16(f[6], f[7]);
+            *reinterpret_cast<uint4*>(op + c + q * 8) = v;
+          }
         }
       }
     }
@@ -297,7 +332,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttDev p) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == 17) {
     tc_fence_after();
     tmem_dealloc(tmem_base, ATT_TMEM_COLS);
   }
@@ -323,7 +358,7 @@ int attention_launch(const void* qkv, void* out, int batch, int seq_len, int hea
   p.heads = heads;
   p.dim = dim;
   p.scale_log2 = scale * 1.4426950408889634f;
-  dim3 grid((seq_len + ATT_BQ - 1) / ATT_BQ, heads, batch);
+  dim3 grid((seq_len + 2 * ATT_BQ - 1) / (2 * ATT_BQ), heads, batch);
   attention_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tm, p);
   ORVB_CHECK_CUDA(cudaGetLastError());
   return ORVB_OK;
@@ -337,3 +372,4 @@ extern "C" int orvb_attention_bf16(const void* qkv, void* out, int32_t batch, in
   if (rc != ORVB_OK) return rc;
   return orvb::attention_launch(qkv, out, batch, seq_len, heads, scale, static_cast<cudaStream_t>(stream));
 }
+

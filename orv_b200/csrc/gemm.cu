@@ -229,46 +229,51 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // The producer and MMA warps run their loops warp-uniformly and elect one lane only around the issuing
+  // instructions: descriptor / coordinate arithmetic then stays in the uniform datapath (UR registers feed
+  // UTMALDG / UTCHMMA directly).  Wrapping the whole loop in `if (lane == 0)` makes every operand a per-thread
+  // value that must be moved with R2UR before each issue, which costs ~100 clk per tcgen05.mma (measured).
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % p.num_m_tiles;
-        const int n_blk = tile / p.num_m_tiles;
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + Cfg::A_BYTES;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % p.num_m_tiles;
+      const int n_blk = tile / p.num_m_tiles;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+        uint8_t* sb = sa + Cfg::A_BYTES;
+        if (elect_one()) {
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
           tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint64_t a_desc = umma_desc_sw128(sa);
-          const uint64_t b_desc = umma_desc_sw128(sa + Cfg::A_BYTES);
+        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint64_t a_desc = umma_desc_sw128(sa);
+        const uint64_t b_desc = umma_desc_sw128(sa + Cfg::A_BYTES);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the swizzle span: +2 in the (addr >> 4) field
@@ -276,16 +281,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                         static_cast<uint32_t>((kb | k) != 0));
           }
           tc_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+          if (kb == num_k - 1) tc_commit(&tfull_bar[acc]);  // accumulator complete
         }
-        tc_commit(&tfull_bar[acc]);  // accumulator complete
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
       }
     }
   } else if (warp >= 4) {

@@ -58,13 +58,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as a trapped kernel (cudaErrorLaunchFailure), never
-// as a hung GPU.  The bound (~4 s at 2 GHz) is far above any legitimate wait in these kernels.
+// Bounded wait: a protocol bug must surface as a trapped kernel (cudaErrorLaunchFailure), never as a hung GPU.
+// try_wait suspends the thread in hardware for a while before returning false, so the loop body runs rarely; it is
+// kept to three instructions (waiting warps share issue slots with the working ones) and only looks at the clock
+// every 64K polls.  The bound (~4 s) is far above any legitimate wait in these kernels.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t polls = 0;
+  long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 8000000000LL) __trap();
+    if ((++polls & 0xFFFFu) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000LL) __trap();
+    }
   }
 }
 
@@ -165,6 +172,18 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
 }
 __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// 8-column variants (rare correction paths where register pressure matters more than issue count)
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
 }
 // named barrier among a subset of the CTA's warps (id 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
