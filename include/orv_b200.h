@@ -81,6 +81,9 @@ typedef struct orvb_gemm_args {
   /* Output-row remap: out_row = (row / src_rows) * dst_rows + dst_offset + row % src_rows.
    * src_rows == 0 -> identity. Used to scatter per-batch blocks into the joint sequence. */
   int32_t src_rows, dst_rows, dst_offset;
+  /* Multiview scatter (MVBlock, cogvideox_control.py:345): when mv_tokens > 0 the GEMM rows are in '(b f)(v s)' order
+   * and out_row = (b*mv_views + v) * dst_rows + dst_offset + f*mv_tokens + i. */
+  int32_t mv_tokens, mv_frames, mv_views;
 
   /* GATE_RESID: resid may alias out.  resid row = resid_mod > 0 ? (row % resid_mod) + resid_view_stride *
    * ((row / resid_mod) % resid_views) : out_row (a positional table broadcast over the batch when resid_mod>0).
@@ -204,7 +207,8 @@ typedef struct orvb_block_weights {
 typedef struct orvb_weights {
   const void* patch_w;  const void* patch_b;      /* [D, C*pt*p*p] (conv weight flattened), [D] or NULL */
   const void* text_w;   const void* text_b;       /* [D, text_dim], [D] */
-  const void* pos_embed;                          /* bf16 [views or 1, video_tokens, D] joint sin-cos rows, or NULL */
+  const void* pos_embed;                          /* bf16 [views or 1, video_tokens, D] sin-cos rows (+ view table when views > 1), or NULL */
+  const void* pos_embed_plain;                    /* bf16 [video_tokens, D] without the view table (control latents); NULL = pos_embed */
   const void* time1_w;  const void* time1_b;      /* [T, D], [T] */
   const void* time2_w;  const void* time2_b;      /* [T, T], [T] */
   const void* ofs1_w;   const void* ofs1_b;       /* [T, ofs], [T] or NULL */

@@ -31,6 +31,7 @@ class GemmArgs(C.Structure):
         ("lda", c_int), ("ldw", c_int), ("ldo", c_int),
         ("epilogue", c_int),
         ("src_rows", c_int), ("dst_rows", c_int), ("dst_offset", c_int),
+        ("mv_tokens", c_int), ("mv_frames", c_int), ("mv_views", c_int),
         ("resid", c_void_p), ("ldr", c_int),
         ("resid_mod", c_int), ("resid_views", c_int), ("resid_view_stride", c_int),
         ("gate", c_void_p),
@@ -78,7 +79,7 @@ class BlockWeights(C.Structure):
 
 
 _WEIGHT_FIELDS = [
-    "patch_w", "patch_b", "text_w", "text_b", "pos_embed", "time1_w", "time1_b", "time2_w", "time2_b",
+    "patch_w", "patch_b", "text_w", "text_b", "pos_embed", "pos_embed_plain", "time1_w", "time1_b", "time2_w", "time2_b",
     "ofs1_w", "ofs1_b", "ofs2_w", "ofs2_b", "act1_w", "act1_b", "act2_w", "act2_b", "act_mask_embed",
     "combine_w", "combine_b", "norm_final_w", "norm_final_b", "norm_out_lin_w", "norm_out_lin_b",
     "norm_out_ln_w", "norm_out_ln_b", "proj_out_w", "proj_out_b",

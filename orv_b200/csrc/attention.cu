@@ -42,6 +42,7 @@ struct AttDev {
   bf16* out;
   int seq_len, heads, dim;  // dim = heads * 64
   float scale_log2;         // softmax scale * log2(e)
+  int q_row0, q_rows;       // queries = rows [q_row0, q_row0 + q_rows) of every sequence; output is compact
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -106,8 +107,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttDev p) {
       const int k_col = p.dim + head * ATT_D;
       const int v_col = 2 * p.dim + head * ATT_D;
       mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
-      tma_load_3d(smem, &tma_qkv, q_full, q_col, (2 * q_pair) * ATT_BQ, batch);
-      tma_load_3d(smem + ATT_QP_BYTES, &tma_qkv, q_full, q_col, (2 * q_pair + 1) * ATT_BQ, batch);
+      tma_load_3d(smem, &tma_qkv, q_full, q_col, p.q_row0 + (2 * q_pair) * ATT_BQ, batch);
+      tma_load_3d(smem + ATT_QP_BYTES, &tma_qkv, q_full, q_col, p.q_row0 + (2 * q_pair + 1) * ATT_BQ, batch);
       for (int j = 0; j < n_kv; ++j) {
         const int st = j % ATT_STAGES;
         const uint32_t ph = static_cast<uint32_t>((j / ATT_STAGES) & 1);
@@ -306,13 +307,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttDev p) {
       const float inv = 1.0f / (l_run * wa + l_b * wb);
       const float ca = wa * inv, cb = wb * inv;
       const int q_row = (2 * q_pair + t) * ATT_BQ + row_in_tile;
-      bf16* op = p.out + (static_cast<size_t>(batch) * p.seq_len + q_row) * p.dim + head * ATT_D;
+      bf16* op = p.out + (static_cast<size_t>(batch) * p.q_rows + q_row) * p.dim + head * ATT_D;
 #pragma unroll 1
       for (int c = 0; c < ATT_D; c += 32) {
         uint32_t o[32];
         tmem_ld_32x32b_x32(my_o + static_cast<uint32_t>(c), o);
         tmem_ld_wait();
-        if (q_row < p.seq_len) {
+        if (q_row < p.q_rows) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float f[8];
@@ -338,10 +339,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttDev p) {
   }
 }
 
-int attention_launch(const void* qkv, void* out, int batch, int seq_len, int heads, float scale,
-                     cudaStream_t stream) {
+int attention_launch(const void* qkv, void* out, int batch, int seq_len, int heads, float scale, int q_row0,
+                     int q_rows, cudaStream_t stream) {
   ORVB_REQUIRE(qkv && out, ORVB_EINVAL, "orvb_attention_bf16: null pointer");
   ORVB_REQUIRE(batch > 0 && seq_len > 0 && heads > 0, ORVB_ESHAPE, "orvb_attention_bf16: empty problem");
+  if (q_rows <= 0) {
+    q_row0 = 0;
+    q_rows = seq_len;
+  }
+  ORVB_REQUIRE(q_row0 >= 0 && q_row0 + q_rows <= seq_len, ORVB_ESHAPE, "orvb_attention_bf16: query window out of range");
   const int dim = heads * ATT_D;
   CUtensorMap tm;
   int rc = make_tmap_3d_bf16(&tm, qkv, batch, seq_len, 3 * dim, 3 * dim, static_cast<uint64_t>(seq_len) * 3 * dim,
@@ -358,7 +364,9 @@ int attention_launch(const void* qkv, void* out, int batch, int seq_len, int hea
   p.heads = heads;
   p.dim = dim;
   p.scale_log2 = scale * 1.4426950408889634f;
-  dim3 grid((seq_len + 2 * ATT_BQ - 1) / (2 * ATT_BQ), heads, batch);
+  p.q_row0 = q_row0;
+  p.q_rows = q_rows;
+  dim3 grid((q_rows + 2 * ATT_BQ - 1) / (2 * ATT_BQ), heads, batch);
   attention_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, stream>>>(tm, p);
   ORVB_CHECK_CUDA(cudaGetLastError());
   return ORVB_OK;
@@ -370,6 +378,6 @@ extern "C" int orvb_attention_bf16(const void* qkv, void* out, int32_t batch, in
                                    float scale, void* stream) {
   int rc = orvb::check_arch();
   if (rc != ORVB_OK) return rc;
-  return orvb::attention_launch(qkv, out, batch, seq_len, heads, scale, static_cast<cudaStream_t>(stream));
+  return orvb::attention_launch(qkv, out, batch, seq_len, heads, scale, 0, seq_len, static_cast<cudaStream_t>(stream));
 }
 

@@ -60,7 +60,8 @@ static int make_geometry(const orvb_config& c, const orvb_shape& s, Geometry* g)
   const int pt = c.patch_size_t > 0 ? c.patch_size_t : 1;
   ORVB_REQUIRE(s.frames % pt == 0, ORVB_ESHAPE, "orvb_forward: frames (%d) not divisible by patch_size_t (%d)",
                s.frames, pt);
-  ORVB_REQUIRE(s.views <= 1, ORVB_ESHAPE, "orvb_forward: multiview (views=%d) is not built yet", s.views);
+  ORVB_REQUIRE(s.views <= 1 || (c.multiview && s.batch % s.views == 0), ORVB_ESHAPE,
+               "orvb_forward: views=%d needs a multiview model and batch (%d) divisible by views", s.views, s.batch);
   g->B = s.batch; g->V = s.views > 0 ? s.views : 1; g->F = s.frames; g->Fp = s.frames / pt;
   g->H = s.height; g->W = s.width; g->Hp = s.height / c.patch_size; g->Wp = s.width / c.patch_size;
   g->St = s.text_len; g->Sv = g->Fp * g->Hp * g->Wp; g->S = g->St + g->Sv; g->R = g->B * g->S;
@@ -71,12 +72,12 @@ static int make_geometry(const orvb_config& c, const orvb_shape& s, Geometry* g)
   ORVB_REQUIRE(g->Fa == 0 || g->Sv % g->Fa == 0, ORVB_ESHAPE,
                "orvb_forward: video tokens (%d) not divisible by action frames (%d)", g->Sv, g->Fa);
   g->G = g->Fa + 1;
-  g->sites = 2 * c.layers + 1;
+  g->sites = 2 * c.layers + 1 + (c.multiview ? c.layers : 0);
   return ORVB_OK;
 }
 
 struct Workspace {
-  bf16 *x, *xn, *qkv, *att, *ffh, *patches, *ctrl, *yout;
+  bf16 *x, *xn, *qkv, *att, *ffh, *patches, *ctrl, *yout, *qkv_mv, *att_mv, *tmp_mv;
   float *tsin, *t1, *temb, *osin, *o1, *oemb, *act_in, *act_h, *act_emb, *emb, *mod;
   bf16* ab;
   size_t bytes;
@@ -99,6 +100,14 @@ static void carve(const orvb_config& c, const Geometry& g, uint8_t* base, Worksp
   const int keys = c.visual_guidance ? c.num_control_keys : 0;
   ws->ctrl = reinterpret_cast<bf16*>(take(static_cast<size_t>(g.B) * g.Sv * D * keys * 2));
   ws->yout = reinterpret_cast<bf16*>(take(static_cast<size_t>(g.B) * g.Sv * g.Nout * 2));
+  {
+    // multiview attention operands in '(b f)(v text | v s)' order (clips = B / V sequences of F frames)
+    const size_t mv = (c.multiview && g.V > 1) ? 1 : 0;
+    const size_t tok = static_cast<size_t>(g.Hp) * g.Wp;
+    ws->qkv_mv = reinterpret_cast<bf16*>(take(mv * (g.B / g.V) * g.Fp * g.V * (g.St + tok) * 3 * D * 2));
+    ws->att_mv = reinterpret_cast<bf16*>(take(mv * (g.B / g.V) * g.Fp * g.V * tok * D * 2));
+    ws->tmp_mv = reinterpret_cast<bf16*>(take(mv * (g.B / g.V) * g.Fp * g.V * tok * D * 2));
+  }
   ws->tsin = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * D * 4));
   ws->t1 = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * g.T * 4));
   ws->temb = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * g.T * 4));
@@ -305,7 +314,8 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
   // ---- 2. all AdaLN tables of the forward in one batched launch (they depend only on emb) ----------
   const size_t site_stride = static_cast<size_t>(g.B) * g.G * 6 * D;
   if (m->jobs_y_base != ws.mod || m->jobs_site_stride != site_stride) {
-    std::vector<SkinnyJob> jobs(2 * c.layers);
+    const int n_jobs = 2 * c.layers + (c.multiview ? c.layers : 0);
+    std::vector<SkinnyJob> jobs(n_jobs);
     for (int l = 0; l < c.layers; ++l) {
       const orvb_block_weights& bw = m->blocks[l];
       jobs[2 * l] = SkinnyJob{static_cast<const bf16*>(bw.norm1_lin_w), static_cast<const bf16*>(bw.norm1_lin_b),
@@ -316,7 +326,7 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
     // synchronous small copy: happens once per (model, workspace) pair, outside any graph capture
     ORVB_CHECK_CUDA(cudaMemcpy(m->jobs_dev, jobs.data(), jobs.size() * sizeof(SkinnyJob), cudaMemcpyHostToDevice));
     const size_t ab_stride = static_cast<size_t>(g.B) * g.G * 4 * D;
-    std::vector<AbSite> sites(2 * c.layers + 1);
+    std::vector<AbSite> sites(g.sites);
     for (int l = 0; l < c.layers; ++l) {
       const orvb_block_weights& bw = m->blocks[l];
       sites[2 * l] = AbSite{static_cast<const bf16*>(bw.norm1_ln_w), static_cast<const bf16*>(bw.norm1_ln_b),
@@ -328,12 +338,24 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
     sites[2 * c.layers] = AbSite{static_cast<const bf16*>(w.norm_out_ln_w), static_cast<const bf16*>(w.norm_out_ln_b),
                                  ws.mod + static_cast<size_t>(2 * c.layers) * site_stride, 2 * D, 0, 0,
                                  ws.ab + static_cast<size_t>(2 * c.layers) * ab_stride};
+    if (c.multiview) {
+      // MVBlock.norm1 sites live after the norm_out slot: site index 2L + 1 + l, job index 2L + l
+      for (int l = 0; l < c.layers; ++l) {
+        const orvb_block_weights& mw = m->mv_blocks[l];
+        const size_t site = static_cast<size_t>(2 * c.layers + 1 + l);
+        jobs[2 * c.layers + l] = SkinnyJob{static_cast<const bf16*>(mw.norm1_lin_w), static_cast<const bf16*>(mw.norm1_lin_b),
+                                           ws.mod + site * site_stride};
+        sites[site] = AbSite{static_cast<const bf16*>(mw.norm1_ln_w), static_cast<const bf16*>(mw.norm1_ln_b),
+                             ws.mod + site * site_stride, 6 * D, 3 * D, 0, ws.ab + site * ab_stride};
+      }
+      ORVB_CHECK_CUDA(cudaMemcpy(m->jobs_dev, jobs.data(), jobs.size() * sizeof(SkinnyJob), cudaMemcpyHostToDevice));
+    }
     ORVB_CHECK_CUDA(cudaMemcpy(m->ab_sites_dev, sites.data(), sites.size() * sizeof(AbSite), cudaMemcpyHostToDevice));
     m->jobs_y_base = ws.mod;
     m->jobs_site_stride = site_stride;
   }
-  ORVB_TRY(skinny_linear_launch(ws.emb, SkinnyJob{nullptr, nullptr, nullptr}, m->jobs_dev, 2 * c.layers, g.B * g.G,
-                                6 * D, T, 0, st));
+  ORVB_TRY(skinny_linear_launch(ws.emb, SkinnyJob{nullptr, nullptr, nullptr}, m->jobs_dev,
+                                2 * c.layers + (c.multiview ? c.layers : 0), g.B * g.G, 6 * D, T, 0, st));
   float* mod_out = ws.mod + static_cast<size_t>(2 * c.layers) * site_stride;  // norm_out table, row pitch 2D
   {
     // norm_out.linear is [2D, T]; written with pitch 2D into its slot
@@ -341,7 +363,7 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
                                   nullptr, 1, g.B * g.G, 2 * D, T, 0, st));
   }
   // fold LayerNorm affine + (shift, scale) of every site into bf16 A/B tables for the LN kernels
-  ORVB_TRY(ab_combine_launch(m->ab_sites_dev, 2 * c.layers + 1, g.B * g.G, D, st));
+  ORVB_TRY(ab_combine_launch(m->ab_sites_dev, g.sites, g.B * g.G, D, st));
   const size_t ab_stride = static_cast<size_t>(g.B) * g.G * 4 * D;
 
   orvb_rowmap rm;
@@ -358,7 +380,7 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
                                   w.pos_embed ? ORVB_EPI_GATE_RESID : ORVB_EPI_BIAS);
     ga.src_rows = g.Sv; ga.dst_rows = g.S; ga.dst_offset = g.St;
     if (w.pos_embed) {
-      ga.resid = w.pos_embed; ga.ldr = D; ga.resid_mod = g.Sv; ga.resid_views = 1;
+      ga.resid = w.pos_embed; ga.ldr = D; ga.resid_mod = g.Sv; ga.resid_views = g.V; ga.resid_view_stride = g.Sv;
     }
     ORVB_TRY(gemm_run(&ga, st));
   }
@@ -385,7 +407,7 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
       orvb_gemm_args ga = gemm_base(ws.patches, w.patch_w, w.patch_b, ws.ctrl + slot * D, g.B * g.Sv, D, g.Kp, g.Kp,
                                     ldc, w.pos_embed ? ORVB_EPI_GATE_RESID : ORVB_EPI_BIAS);
       if (w.pos_embed) {
-        ga.resid = w.pos_embed; ga.ldr = D; ga.resid_mod = g.Sv; ga.resid_views = 1;
+        ga.resid = w.pos_embed_plain ? w.pos_embed_plain : w.pos_embed; ga.ldr = D; ga.resid_mod = g.Sv; ga.resid_views = 1;
       }
       ORVB_TRY(gemm_run(&ga, st));
       const long n = static_cast<long>(g.B) * g.Sv * (D / 8);
@@ -405,6 +427,39 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
   // ---- 5. transformer blocks -----------------------------------------------------------------------
   const float scale = 1.0f / sqrtf(static_cast<float>(c.head_dim));
   for (int l = 0; l < c.layers; ++l) {
+    if (c.multiview && g.V > 1) {
+      // ---- MVBlock (cogvideox_control.py:313-348): cross-view attention per (clip, frame) ----
+      const orvb_block_weights& mw = m->mv_blocks[l];
+      const size_t site = static_cast<size_t>(2 * c.layers + 1 + l);
+      const float* modv = ws.mod + site * site_stride;
+      const int clips = g.B / g.V, tok = g.Hp * g.Wp, Smv = g.V * (g.St + tok);
+      orvb_rowmap rm0 = rm;
+      rm0.tokens_per_group = 0;  // norm1(temb) only: every row of a sample uses its time-only group
+      orvb_ln_args lnv;
+      memset(&lnv, 0, sizeof(lnv));
+      lnv.x = ws.x; lnv.y = ws.xn; lnv.rows = g.R; lnv.dim = D; lnv.eps = c.norm_eps; lnv.rowmap = rm0;
+      lnv.ab = ws.ab + site * ab_stride; lnv.ab_ld = 4 * D;
+      ORVB_CLS(ORVB_PC_LN);
+      ORVB_TRY(ln_modulate_launch(&lnv, st));
+      orvb_gemm_args q = gemm_base(ws.xn, mw.qkv_w, mw.qkv_b, ws.qkv, g.R, 3 * D, D, D, 3 * D, ORVB_EPI_QKV);
+      q.qk_dim = D; q.q_norm_w = mw.q_norm_w; q.q_norm_b = mw.q_norm_b; q.k_norm_w = mw.k_norm_w; q.k_norm_b = mw.k_norm_b;
+      q.qk_eps = 1e-6f; q.rowmap = rm0;  // image_rotary_emb_view is never passed on the ORV path
+      ORVB_CLS(ORVB_PC_QKV);
+      ORVB_TRY(gemm_run(&q, st));
+      ORVB_CLS(ORVB_PC_ATTN);
+      ORVB_TRY(mv_gather_launch(ws.qkv, ws.qkv_mv, clips, g.V, g.Fp, g.St, tok, 3 * D, st));
+      // only the video rows are queries: the reference discards the text outputs of this attention (:333)
+      ORVB_TRY(attention_launch(ws.qkv_mv, ws.att_mv, clips * g.Fp, Smv, c.heads, scale, g.V * g.St, g.V * tok, st));
+      const int Mv = clips * g.Fp * g.V * tok;
+      ORVB_CLS(ORVB_PC_OUT);
+      orvb_gemm_args o1 = gemm_base(ws.att_mv, mw.out_w, mw.out_b, ws.tmp_mv, Mv, D, D, D, D, ORVB_EPI_BIAS);
+      ORVB_TRY(gemm_run(&o1, st));
+      orvb_gemm_args o2 = gemm_base(ws.tmp_mv, mw.proj_out_w, mw.proj_out_b, ws.x, Mv, D, D, D, D, ORVB_EPI_GATE_RESID);
+      o2.mv_tokens = tok; o2.mv_frames = g.Fp; o2.mv_views = g.V; o2.dst_rows = g.S; o2.dst_offset = g.St;
+      o2.resid = ws.x; o2.ldr = D; o2.gate = modv; o2.gate_ld = 6 * D; o2.gate_text_off = 5 * D; o2.gate_video_off = 2 * D;
+      o2.rowmap = rm0;
+      ORVB_TRY(gemm_run(&o2, st));
+    }
     const orvb_block_weights& bw = m->blocks[l];
     const float* mod1 = ws.mod + (2 * l) * site_stride;
     const float* mod2 = ws.mod + (2 * l + 1) * site_stride;
@@ -425,7 +480,7 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
     ORVB_TRY(gemm_run(&q, st));
 
     ORVB_CLS(ORVB_PC_ATTN);
-    ORVB_TRY(attention_launch(ws.qkv, ws.att, g.B, g.S, c.heads, scale, st));
+    ORVB_TRY(attention_launch(ws.qkv, ws.att, g.B, g.S, c.heads, scale, 0, g.S, st));
 
     orvb_gemm_args o = gemm_base(ws.att, bw.out_w, bw.out_b, ws.x, g.R, D, D, D, D, ORVB_EPI_GATE_RESID);
     o.resid = ws.x; o.ldr = D; o.gate = mod1; o.gate_ld = 6 * D; o.gate_text_off = 5 * D; o.gate_video_off = 2 * D;
@@ -493,7 +548,6 @@ extern "C" int orvb_model_create(const orvb_config* cfg, orvb_model** out) {
   ORVB_REQUIRE(cfg->layers > 0 && cfg->ff_dim % 8 == 0 && cfg->time_embed_dim % 8 == 0 && cfg->text_embed_dim % 8 == 0,
                ORVB_ESHAPE, "orvb_model_create: bad layer/ff/time/text dims");
   ORVB_REQUIRE(cfg->patch_size == 2, ORVB_ESHAPE, "orvb_model_create: patch_size must be 2");
-  ORVB_REQUIRE(!cfg->multiview, ORVB_EINVAL, "orvb_model_create: multiview models are not built yet (SURVEY §8 a11)");
   int rc = check_arch();
   if (rc != ORVB_OK) return rc;
   orvb_model* m = new orvb_model();
@@ -536,6 +590,15 @@ extern "C" int orvb_model_bind_weights(orvb_model* m, const orvb_weights* w) {
     ORVB_REQUIRE(b.norm1_lin_w && b.norm1_ln_w && b.qkv_w && b.q_norm_w && b.k_norm_w && b.out_w && b.norm2_lin_w &&
                      b.norm2_ln_w && b.ff1_w && b.ff2_w,
                  ORVB_EINVAL, "orvb_model_bind_weights: block %d has a NULL weight pointer", l);
+  }
+  if (m->cfg.multiview) {
+    ORVB_REQUIRE(w->mv_blocks_host != nullptr, ORVB_EINVAL, "orvb_model_bind_weights: multiview model without mv_blocks");
+    m->mv_blocks.assign(w->mv_blocks_host, w->mv_blocks_host + m->cfg.layers);
+    for (int l = 0; l < m->cfg.layers; ++l) {
+      const orvb_block_weights& b = m->mv_blocks[l];
+      ORVB_REQUIRE(b.norm1_lin_w && b.norm1_ln_w && b.qkv_w && b.q_norm_w && b.k_norm_w && b.out_w && b.proj_out_w,
+                   ORVB_EINVAL, "orvb_model_bind_weights: mv block %d has a NULL weight pointer", l);
+    }
   }
   m->w.blocks_host = nullptr;
   m->w.mv_blocks_host = nullptr;

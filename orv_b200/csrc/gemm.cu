@@ -21,6 +21,7 @@ struct GemmDev {
   int ldo;
   const bf16* bias;
   int src_rows, dst_rows, dst_offset;
+  int mv_tokens, mv_frames, mv_views;
   const bf16* resid;
   int ldr, resid_mod, resid_views, resid_view_stride;
   const float* gate;
@@ -76,7 +77,13 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float (&v)[64], 
     }
   }
   int out_row = row;
-  if (p.src_rows > 0) {
+  if (p.mv_tokens > 0) {
+    // '(b f) (v s) -> (b v) (text | f s)': row = ((b*F + f)*V + v)*s + i  ->  (b*V + v)*dst_rows + dst_offset + f*s + i
+    const int blk = row / p.mv_tokens, i = row - blk * p.mv_tokens;
+    const int v = blk % p.mv_views, bf = blk / p.mv_views;
+    const int f = bf % p.mv_frames, b = bf / p.mv_frames;
+    out_row = (b * p.mv_views + v) * p.dst_rows + p.dst_offset + f * p.mv_tokens + i;
+  } else if (p.src_rows > 0) {
     int q = row / p.src_rows;
     out_row = q * p.dst_rows + p.dst_offset + (row - q * p.src_rows);
   }
@@ -137,7 +144,7 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float (&v)[64], 
   if (EPI == ORVB_EPI_GATE_RESID) {
     if (p.gate != nullptr) {
       int s;
-      int g = row_group(p.rm, row, &s);
+      int g = row_group(p.rm, out_row, &s);  // modulation group of the DESTINATION row
       int is_text = (p.rm.seq_len > 0) ? (s < p.rm.text_len) : 0;
       const float* gp = p.gate + static_cast<size_t>(g) * p.gate_ld + (is_text ? p.gate_text_off : p.gate_video_off) + n0;
 #pragma unroll
@@ -444,6 +451,7 @@ int gemm_prepare(const orvb_gemm_args* a, int bn_override, CUtensorMap* ta, CUte
   d.out = static_cast<bf16*>(a->out); d.ldo = a->ldo;
   d.bias = static_cast<const bf16*>(a->bias);
   d.src_rows = a->src_rows; d.dst_rows = a->dst_rows; d.dst_offset = a->dst_offset;
+  d.mv_tokens = a->mv_tokens; d.mv_frames = a->mv_frames; d.mv_views = a->mv_views;
   d.resid = static_cast<const bf16*>(a->resid); d.ldr = a->ldr;
   d.resid_mod = a->resid_mod; d.resid_views = a->resid_views; d.resid_view_stride = a->resid_view_stride;
   d.gate = a->gate; d.gate_ld = a->gate_ld; d.gate_text_off = a->gate_text_off; d.gate_video_off = a->gate_video_off;

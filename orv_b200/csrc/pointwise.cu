@@ -432,6 +432,47 @@ int unpatchify_launch(const void* y, void* out, int B, int F, int C, int H, int 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Multiview gather (reference MVBlock.forward, cogvideox_control.py:328-331):
+//   video  '(b v) (f s) d -> (b f) (v s) d'   and   text  '(b v) n d -> b (v n) d' repeated over f,
+// concatenated text-first, i.e. dst[(b f)][v*n_text + n | V*n_text + v*s + i] = src[(b v)][n | n_text + f*s + i].
+// ---------------------------------------------------------------------------------------------------
+__global__ void mv_gather_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int clips, int V, int F,
+                                 int St, int s, int chunks) {
+  const int S = St + F * s;         // source sequence length per (b, v)
+  const int Smv = V * (St + s);     // destination sequence length per (b, f)
+  const long total = static_cast<long>(clips) * F * Smv * chunks;
+  const long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % chunks);
+  long r = idx / chunks;
+  const int d = static_cast<int>(r % Smv);
+  r /= Smv;
+  const int f = static_cast<int>(r % F);
+  const int b = static_cast<int>(r / F);
+  long srow;
+  if (d < V * St) {
+    const int v = d / St, n = d - v * St;
+    srow = static_cast<long>(b * V + v) * S + n;
+  } else {
+    const int e = d - V * St;
+    const int v = e / s, i = e - v * s;
+    srow = static_cast<long>(b * V + v) * S + St + f * s + i;
+  }
+  dst[(static_cast<long>(b * F + f) * Smv + d) * chunks + c] = src[srow * chunks + c];
+}
+
+int mv_gather_launch(const void* src, void* dst, int clips, int views, int frames, int text_len, int tokens,
+                     int width, cudaStream_t stream) {
+  ORVB_REQUIRE(src && dst && width % 8 == 0, ORVB_EINVAL, "mv_gather: bad arguments");
+  const int chunks = width / 8;
+  const long total = static_cast<long>(clips) * frames * views * (text_len + tokens) * chunks;
+  mv_gather_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      static_cast<const uint4*>(src), static_cast<uint4*>(dst), clips, views, frames, text_len, tokens, chunks);
+  ORVB_CHECK_CUDA(cudaGetLastError());
+  return ORVB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Sampler step: CFG combine + v-prediction -> x0 + DDIM / DPM-Solver++(2M, SDE) update + bf16 cast, one pass.
 // Reference: cogvideox_control.py:1433-1459 and diffusers CogVideoX{DDIM,DPM}Scheduler.step.
 // The reference keeps `latents` (and the DPM noise) in bf16 and multiplies them by 0-dim float64 coefficients,

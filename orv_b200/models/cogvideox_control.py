@@ -472,17 +472,35 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
             return None
         return pk.arena.data_ptr() + pk.offsets[key][0] * 2
 
-    def _pos_table(self, frames: int, height: int, width: int) -> Optional[torch.Tensor]:
-        """Video rows of CogVideoXPatchEmbed's joint positional buffer for this latent geometry (bf16, HBM)."""
+    def _pos_table(self, frames: int, height: int, width: int, views: int = 1):
+        """Video rows of CogVideoXPatchEmbed's joint positional buffer for this latent geometry (bf16, HBM).
+        Returns (table used for the hidden states, plain table used for control latents).  With views > 1 the first
+        one is [views, tokens, D] and already contains the view embedding of reference :659-688 / :797-800."""
         c = self.config
         if c.use_rotary_positional_embeddings and not c.use_learned_positional_embeddings:
-            return None
-        key = (frames, height, width)
+            if views > 1:
+                raise NotImplementedError("multiview + rotary embeddings: the reference builds a wrong RoPE table "
+                                          "for this combination (SURVEY App. C.5) and no config uses it")
+            return None, None
+        key = (frames, height, width, views)
         if key not in self._pos_cache:
             D = c.num_attention_heads * c.attention_head_dim
-            pos = sincos_pos_embed_3d(D, width // c.patch_size, height // c.patch_size, frames,
-                                      c.spatial_interpolation_scale, c.temporal_interpolation_scale)
-            self._pos_cache[key] = pos.to(device=self.device, dtype=torch.bfloat16).contiguous()
+            p = c.patch_size
+            pos = sincos_pos_embed_3d(D, width // p, height // p, frames, c.spatial_interpolation_scale,
+                                      c.temporal_interpolation_scale)
+            plain = pos.to(device=self.device, dtype=torch.bfloat16).contiguous()
+            if views > 1:
+                hw = (c.sample_height // p) * (c.sample_width // p)
+                if hw != (height // p) * (width // p):
+                    raise RuntimeError(f"The size of tensor a ({views * (height // p) * (width // p)}) must match the size "
+                                       f"of tensor b ({views * hw}) at non-singleton dimension 1")  # as the reference
+                pv = sincos_pos_embed_3d(D, c.sample_width // p, c.sample_height // p, c.max_n_view,
+                                         c.spatial_interpolation_scale, 1.0)[: views * hw].view(views, 1, hw, D)
+                full = pos.view(1, frames, hw, D) + pv  # [views, frames, hw, D]
+                table = full.reshape(views, frames * hw, D).to(device=self.device, dtype=torch.bfloat16).contiguous()
+            else:
+                table = plain
+            self._pos_cache[key] = (table, plain)
         return self._pos_cache[key]
 
     def _ensure_handle(self):
@@ -505,8 +523,9 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
             for name in L._WEIGHT_FIELDS:
                 if name != "pos_embed":
                     setattr(w, name, self._ptr(name))
-            pos = self._pos_table(*pos_key)
+            pos, pos_plain = self._pos_table(*pos_key)
             w.pos_embed = pos.data_ptr() if pos is not None else None
+            w.pos_embed_plain = pos_plain.data_ptr() if pos_plain is not None else None
             n = self.config.num_layers
             blocks = (L.BlockWeights * n)()
             for i in range(n):
@@ -557,15 +576,25 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
                                "and call .eval() (training/backward is out of scope, SURVEY §2 row 8)")
         if not hidden_states.is_cuda:
             raise RuntimeError("orv_b200 forward needs CUDA tensors on a B200; there is no CPU fallback")
-        if num_views > 1 or c.multiview:
-            raise NotImplementedError("multiview (MVBlock, SURVEY §8 a11) is not built yet")
+        if image_rotary_emb_view is not None:
+            raise NotImplementedError("image_rotary_emb_view is never passed on the ORV path (cogvideox_control.py:1421-1431)")
+        V = int(num_views)
+        if c.multiview and V <= 1:
+            import warnings
+            warnings.warn("You're tring multiview mode but no multiview inputs!")
+        if V > 1 and not c.multiview:
+            raise RuntimeError("num_views > 1 needs a model built with multiview=True")
         out_dtype = hidden_states.dtype
         dev = hidden_states.device
+        Bc = hidden_states.shape[0]
+        if V > 1:  # 'b (v f) c h w -> (b v) f c h w' (a view: (v f) is contiguous) and text repeated per view (:756-759)
+            hidden_states = hidden_states.reshape(Bc * V, hidden_states.shape[1] // V, *hidden_states.shape[2:])
+            encoder_hidden_states = encoder_hidden_states.repeat_interleave(V, dim=0)
         B, Fr, Cin, H, W = hidden_states.shape
         if Cin != c.in_channels:
             raise RuntimeError(f"expected {c.in_channels} input channels, got {hidden_states.shape=}")
         St = encoder_hidden_states.shape[1]
-        pos_key = (Fr, H, W)
+        pos_key = (Fr, H, W, V)
         if (not c.use_rotary_positional_embeddings) and St != c.max_text_seq_length:
             raise RuntimeError(f"The size of tensor a ({St + (Fr // (c.patch_size_t or 1)) * (H // 2) * (W // 2)}) must "
                                f"match the size of the positional table (text length {c.max_text_seq_length})")
@@ -578,6 +607,8 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
         ts = timestep.to(device=dev, dtype=torch.float32).reshape(-1)
         if ts.numel() == 1 and B > 1:
             ts = ts.expand(B)
+        elif V > 1 and ts.numel() == Bc:
+            ts = ts.repeat_interleave(V)  # multiviews share the same noise level (:778-779)
         ts = ts.contiguous()
         if ts.numel() != B:
             raise RuntimeError(f"timestep has {ts.numel()} entries for batch {B}")
@@ -592,6 +623,9 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
                 pad = actions.new_zeros((actions.shape[0], 4 - res_frames, actions.shape[2]))
                 actions = torch.cat([pad, actions], dim=1)
             act_in, is_action_mask, apply = self.action_embed.prepare(actions.to(dev))
+            if V > 1:  # multiviews share the same actions (:815-816)
+                act_in = act_in.repeat_interleave(V, dim=0)
+                apply = apply.repeat_interleave(V, dim=0)
             if act_in.shape[0] != B:
                 raise RuntimeError(f"The size of tensor a ({B}) must match the size of tensor b ({act_in.shape[0]}) at "
                                    "non-singleton dimension 0")  # same failure the reference hits with CFG (P5)
@@ -607,6 +641,11 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
             if n_ctrl and n_ctrl != self.num_control_keys:
                 raise AssertionError(f"Mismatched number of controls: len(controls_hidden_states)={n_ctrl} but "
                                      f"self.num_control_keys={self.num_control_keys}.")
+            if V > 1:
+                if depths is not None:
+                    depths = depths.reshape(Bc * V, depths.shape[1] // V, *depths.shape[2:])
+                if labels is not None:
+                    labels = labels.reshape(Bc * V, labels.shape[1] // V, *labels.shape[2:])
             if depths is not None:
                 depths = depths.to(device=dev, dtype=torch.bfloat16).contiguous()
                 if depths.shape != hs.shape:
@@ -626,9 +665,9 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
                 raise RuntimeError("this model has an ofs embedding; pass `ofs`")
             ofs_val = float(ofs.reshape(-1)[0].item()) if torch.is_tensor(ofs) else float(ofs)
 
-        shape = L.Shape(batch=B, views=1, frames=Fr, height=H, width=W, text_len=St, action_frames=action_frames)
+        shape = L.Shape(batch=B, views=V, frames=Fr, height=H, width=W, text_len=St, action_frames=action_frames)
         lib = L.load()
-        wkey = (B, Fr, H, W, St, action_frames, dev.index)
+        wkey = (B, V, Fr, H, W, St, action_frames, dev.index)
         ws = self._workspaces.get(wkey)
         if ws is None:
             nbytes = lib.orvb_workspace_bytes(self._handle, C.byref(shape))
@@ -700,6 +739,8 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
             self.last_launch_count = lib.orvb_last_launch_count(self._handle)
         if not _static_out:
             out = out.clone()
+        if V > 1:  # '(b v) f c h w -> b (v f) c h w' (:942)
+            out = out.view(Bc, V * Fr, *out.shape[2:])
 
         output = out if out_dtype == torch.bfloat16 else out.to(out_dtype)
         actions_recon = None

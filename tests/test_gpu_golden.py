@@ -26,7 +26,7 @@ def _rel(a, b):
 
 
 @pytest.mark.parametrize("name", ["fwd_actions", "fwd_noactions_b2", "fwd_controls_b2", "fwd_rope_pt2_ofs",
-                                  "fwd_othergeom"])
+                                  "fwd_othergeom", "fwd_multiview_v3"])
 def test_forward_vs_reference_golden(name):
     """bf16 kernels + bf16-rounded weights/inputs vs the reference's fp32 run: mean relative error < 1.5e-2
     (2 layers; torch-bf16 itself sits at ~5e-3 here)."""
@@ -41,7 +41,9 @@ def test_forward_vs_reference_golden(name):
     with torch.no_grad():
         out = m(inp["hidden_states"].cuda().bfloat16(), inp["text"].cuda().bfloat16(), cg, t.cuda(),
                 ofs=ofs.cuda() if ofs is not None else None,
-                image_rotary_emb=(rope[0].cuda(), rope[1].cuda()) if rope else None, return_dict=False)[0]
+                image_rotary_emb=(rope[0].cuda(), rope[1].cuda()) if rope else None, return_dict=False,
+                num_views=V)[0]
+    assert out.shape == blob["output"].shape
     assert _rel(out, blob["output"]) < 1.5e-2
 
 
