@@ -352,6 +352,189 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------------
+// CTA-pair kernel: one 256 x BN output tile per cluster of two CTAs (tcgen05.mma cta_group::2, M = 256).
+//
+// The 1-CTA kernel above streams 16 KB of A + BN*128 B of B from L2 per 128 x BN x 64 step; on B200 that L2 -> SM
+// stream, not the tensor pipe, is what bounds it (ncu: ~12 TB/s of TMA traffic at 52 % tensor-pipe activity).  With
+// a pair, each CTA fetches only its own 128 rows of A and its own BN/2 rows of B: 2/3 of the bytes per FLOP at
+// BN = 256.  BN is a run-time value (any multiple of 16 up to 256), so the host can pick the width that fills the
+// last wave of the 74 clusters best.
+//
+// Roles per CTA: warp 0 TMA producer (both CTAs; byte counts are credited to the LEADER's full barrier), warp 1
+// MMA issuer (leader only), warp 2 TMEM allocator, warps 4-7 epilogue over this CTA's 128 accumulator rows.
+// ---------------------------------------------------------------------------------------------------
+constexpr int G2_STAGES = 6;
+constexpr int G2_A_BYTES = BM * BK * 2;           // 16 KB: this CTA's 128 rows of A
+constexpr int G2_B_BYTES = 128 * BK * 2;          // up to 16 KB: this CTA's BN/2 rows of B
+constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
+constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 1024 + 256;
+constexpr int G2_ACC_COLS = 256;                  // TMEM columns per accumulator buffer (2 buffers = 512)
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                  const GemmDev p, const int bn) {
+  constexpr int STAGES = G2_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  // Both CTAs of the pair must use identical offsets (the MMA applies the leader's descriptors to the peer's shared
+  // memory), which holds because the dynamic shared window starts at the same shared::cta address in every CTA.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * G2_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;  // num_m_tiles counts 256-row pairs here
+  const int num_k = (p.K + BK - 1) / BK;
+  const int half_bn = bn >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);   // leader's producer arrive.expect_tx (both CTAs' bytes)
+      mbar_init(&empty_bar[i], 1);  // multicast tcgen05.commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);   // multicast tcgen05.commit
+      mbar_init(&tempty_bar[i], 8);  // 4 epilogue warps x 2 CTAs (leader's copy is the one waited on)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(tmem_slot, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barriers of BOTH CTAs initialised before any remote arrive / TMA credit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer (both CTAs) ================================
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t stage_tx = 2u * static_cast<uint32_t>(G2_A_BYTES + half_bn * BK * 2);
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m_blk = tile % p.num_m_tiles;
+      const int n_blk = tile / p.num_m_tiles;
+      const int a_row = m_blk * 256 + static_cast<int>(rank) * BM;
+      const int b_row = n_blk * bn + static_cast<int>(rank) * half_bn;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * G2_STAGE_BYTES;
+        uint8_t* sb = sa + G2_A_BYTES;
+        const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+        if (elect_one()) {
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], stage_tx);
+          tma_load_2d_pair(sa, &tma_a, leader_full, kb * BK, a_row);
+          tma_load_2d_pair(sb, &tma_b, leader_full, kb * BK, b_row);
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && rank == 0) {
+    // ================================ MMA issuer (leader CTA) ================================
+    const uint32_t idesc = umma_idesc_bf16(256, bn, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * G2_ACC_COLS);
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * G2_STAGE_BYTES);
+        const uint64_t a_desc = umma_desc_sw128(sa);
+        const uint64_t b_desc = umma_desc_sw128(sa + G2_A_BYTES);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_f16_ss_pair(d_tmem, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc,
+                             static_cast<uint32_t>((kb | k) != 0));
+          }
+          tc_commit_pair(&empty_bar[stage], 3);                     // frees this stage in both CTAs
+          if (kb == num_k - 1) tc_commit_pair(&tfull_bar[acc], 3);  // accumulator complete in both CTAs
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue (both CTAs) ====================================
+    const int ew = warp - 4;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m_blk = tile % p.num_m_tiles;
+      const int n_blk = tile / p.num_m_tiles;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * 256 + static_cast<int>(rank) * BM + ew * 32 + lane;
+      const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * G2_ACC_COLS) + (static_cast<uint32_t>(ew * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < bn; c += 64) {
+        const int n0 = n_blk * bn + c;
+        if (n0 >= p.N) break;  // warp-uniform
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c), r0);
+        tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c + 32), r1);  // may run past bn: still inside the buffer
+        tmem_ld_wait();
+        if (row < p.M) {
+          float v[64];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] = __uint_as_float(r0[j]);
+            v[32 + j] = __uint_as_float(r1[j]);
+          }
+          int ncols = bn - c;
+          if (ncols > 64) ncols = 64;
+          if (p.N - n0 < ncols) ncols = p.N - n0;
+          epilogue_unit<EPI>(p, v, row, n0, ncols);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  // ---- teardown: nobody may exit (or free TMEM) while the peer can still touch this CTA's memory ----
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
 template <int BN, int EPI>
@@ -368,6 +551,34 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmD
   kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
   ORVB_CHECK_CUDA(cudaGetLastError());
   return ORVB_OK;
+}
+
+template <int EPI>
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int bn, cudaStream_t stream) {
+  static bool attr_set = false;
+  auto kern = gemm2_bf16_kernel<EPI>;
+  if (!attr_set) {
+    ORVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int clusters = sm_count() / 2;
+  const int grid = 2 * (tiles < clusters ? tiles : clusters);
+  kern<<<grid, GEMM_THREADS, G2_SMEM_BYTES, stream>>>(ta, tb, p, bn);
+  ORVB_CHECK_CUDA(cudaGetLastError());
+  return ORVB_OK;
+}
+
+static int launch_gemm2_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int bn,
+                            cudaStream_t stream) {
+  switch (epi) {
+    case ORVB_EPI_BIAS: return launch_gemm2<ORVB_EPI_BIAS>(ta, tb, p, bn, stream);
+    case ORVB_EPI_GELU: return launch_gemm2<ORVB_EPI_GELU>(ta, tb, p, bn, stream);
+    case ORVB_EPI_GATE_RESID: return launch_gemm2<ORVB_EPI_GATE_RESID>(ta, tb, p, bn, stream);
+    case ORVB_EPI_QKV: return launch_gemm2<ORVB_EPI_QKV>(ta, tb, p, bn, stream);
+  }
+  set_error("orvb_gemm_bf16: unknown epilogue %d", epi);
+  return ORVB_EINVAL;
 }
 
 template <int BN>
@@ -408,8 +619,33 @@ int gemm_pick_bn(int m, int n) {
   return best_bn;
 }
 
+// Tile width for the CTA-pair kernel: 256-row tiles over `clusters` pairs.  A wave of 256 x bn tiles costs about
+// (G2_WAVE_FIXED + bn) column units (operand streaming of the fixed 256 rows of A + per-tile pipeline turnaround);
+// widths are multiples of 16 (64 when the epilogue normalises whole 64-wide heads).
+constexpr int G2_WAVE_FIXED = 96;
+int gemm_pick_bn_pair(int m, int n, int epi) {
+  const int clusters = sm_count() / 2;
+  const int mt = (m + 255) / 256;
+  const int step = (epi == ORVB_EPI_QKV) ? 64 : 16;
+  int best_bn = 256;
+  double best = 1e30;
+  for (int bn = 256; bn >= 64; bn -= step) {
+    const int nt = (n + bn - 1) / bn;
+    const long tiles = static_cast<long>(mt) * nt;
+    const long waves = (tiles + clusters - 1) / clusters;
+    const double cost = static_cast<double>(waves) * (G2_WAVE_FIXED + bn);
+    if (cost < best - 1e-9) {
+      best = cost;
+      best_bn = bn;
+    }
+  }
+  return best_bn;
+}
+
+// bn > 0: 1-CTA kernel with that N tile; bn < 0: CTA-pair kernel with N tile -bn.
 int gemm_launch_prepared(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int bn, int epi,
                          cudaStream_t stream) {
+  if (bn < 0) return launch_gemm2_epi(epi, ta, tb, p, -bn, stream);
   switch (bn) {
     case 256: return launch_gemm_epi<256>(epi, ta, tb, p, stream);
     case 192: return launch_gemm_epi<192>(epi, ta, tb, p, stream);
@@ -441,10 +677,20 @@ int gemm_prepare(const orvb_gemm_args* a, int bn_override, CUtensorMap* ta, CUte
     ORVB_REQUIRE(a->gate == nullptr || (a->gate_ld % 4 == 0 && a->gate_text_off % 4 == 0 && a->gate_video_off % 4 == 0),
                  ORVB_ESHAPE, "orvb_gemm_bf16: gate pitch/offsets must be multiples of 4");
   }
-  int bn = bn_override > 0 ? bn_override : gemm_pick_bn(a->m, a->n);
+  // More than one 128-row tile: CTA pairs (M = 256 MMAs); otherwise the 1-CTA kernel.
+  int bn;
+  if (bn_override != 0) bn = bn_override;
+  else if (a->m > BM) bn = -gemm_pick_bn_pair(a->m, a->n, a->epilogue);
+  else bn = gemm_pick_bn(a->m, a->n);
+  const bool pair = bn < 0;
+  if (pair) {
+    const int w = -bn;
+    ORVB_REQUIRE(w >= 32 && w <= 256 && w % 16 == 0, ORVB_EINVAL, "gemm: pair tile width %d must be a multiple of 16 in [32, 256]", w);
+    ORVB_REQUIRE(a->epilogue != ORVB_EPI_QKV || w % 64 == 0, ORVB_EINVAL, "gemm: the QKV epilogue needs a tile width that is a multiple of 64 (got %d)", w);
+  }
   int rc = make_tmap_2d_bf16(ta, a->a, a->m, a->k, a->lda, BM, BK);
   if (rc != ORVB_OK) return rc;
-  rc = make_tmap_2d_bf16(tb, a->w, a->n, a->k, a->ldw, bn, BK);
+  rc = make_tmap_2d_bf16(tb, a->w, a->n, a->k, a->ldw, pair ? (-bn) / 2 : bn, BK);
   if (rc != ORVB_OK) return rc;
   GemmDev d;
   d.M = a->m; d.N = a->n; d.K = a->k;
@@ -461,8 +707,8 @@ int gemm_prepare(const orvb_gemm_args* a, int bn_override, CUtensorMap* ta, CUte
   d.kw = static_cast<const bf16*>(a->k_norm_w); d.kb = static_cast<const bf16*>(a->k_norm_b);
   d.qk_eps = a->qk_eps;
   d.rope_cos = a->rope_cos; d.rope_sin = a->rope_sin;
-  d.num_m_tiles = (a->m + BM - 1) / BM;
-  d.num_n_tiles = (a->n + bn - 1) / bn;
+  d.num_m_tiles = pair ? (a->m + 2 * BM - 1) / (2 * BM) : (a->m + BM - 1) / BM;
+  d.num_n_tiles = pair ? (a->n - bn - 1) / (-bn) : (a->n + bn - 1) / bn;
   *p = d;
   *bn_out = bn;
   return ORVB_OK;
@@ -491,7 +737,8 @@ extern "C" int orvb_gemm_bf16(const orvb_gemm_args* args, void* stream) {
   return gemm_launch_prepared(ta, tb, p, bn, args->epilogue, static_cast<cudaStream_t>(stream));
 }
 
-// Test hook: same as orvb_gemm_bf16 with a forced N tile (64 / 128 / 256).
+// Test hook: same as orvb_gemm_bf16 with a forced tile: bn in {64,128,192,256} = 1-CTA kernel, -bn (multiple of 16,
+// 32..256) = CTA-pair kernel.
 extern "C" int orvb_gemm_bf16_bn(const orvb_gemm_args* args, int bn, void* stream) {
   using namespace orvb;
   int rc = check_arch();
