@@ -111,27 +111,6 @@ __device__ __forceinline__ float row_max64(const uint32_t (&r0)[32], const uint3
   return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
 
-// ---- packed fp32 pairs (FFMA2 / FADD2 operate on 64-bit register pairs) ----
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk2(float a, float b) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-}
-__device__ __forceinline__ f32x2 fma2p(f32x2 a, f32x2 b, f32x2 c) {
-  f32x2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ f32x2 add2p(f32x2 a, f32x2 b) {
-  f32x2 d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-
 // exp2 of a pair on the FMA / ALU pipes instead of the MUFU (the unit that bounds this kernel): round-to-nearest
 // split x = i + f with the 1.5 * 2^23 trick, cubic minimax polynomial for 2^f on [-0.5, 0.5] (max relative error
 // 7.5e-5, 50x below one bf16 ulp), exponent inserted with one integer multiply-add.  x <= ~8 always holds (lazy

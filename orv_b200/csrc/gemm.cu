@@ -32,6 +32,7 @@ struct GemmDev {
   float qk_eps;
   const float *rope_cos, *rope_sin;
   int num_m_tiles, num_n_tiles;
+  int tma_store;  // pair kernel: stage full 64-column units in shared memory and write them with TMA
 };
 
 constexpr int BM = 128;
@@ -62,7 +63,8 @@ __device__ __forceinline__ int row_group(const orvb_rowmap& rm, int row, int* s_
 
 // Epilogue over one 64-column unit held by one thread (one output row).
 template <int EPI>
-__device__ __forceinline__ void epilogue_unit(const GemmDev& p, float (&v)[64], int row, int n0, int ncols) {
+__device__ __forceinline__ void epilogue_unit(const GemmDev& p, float (&v)[64], int row, int n0, int ncols,
+                                              uint8_t* stage_row = nullptr, int sw = 0) {
   // ---- bias --------------------------------------------------------------------------------------
   if (p.bias != nullptr) {
 #pragma unroll
@@ -90,7 +92,7 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float (&v)[64], 
 
   if (EPI == ORVB_EPI_GELU) {
 #pragma unroll
-    for (int j = 0; j < 64; ++j) v[j] = gelu_tanh(v[j]);
+    for (int j = 0; j < 64; j += 2) gelu_tanh2(v[j], v[j + 1]);
   }
 
   if (EPI == ORVB_EPI_QKV) {
@@ -179,6 +181,20 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float (&v)[64], 
   }
 
   // ---- store ---------------------------------------------------------------------------------------
+  if (stage_row != nullptr) {
+    // this thread's 128-byte row of a [32 rows x 64 cols] 128B-swizzled staging tile; the warp's elected lane then
+    // writes the whole tile with one TMA store (full 128-byte lines instead of 32 scattered 16-byte pieces per STG)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint4 o;
+      o.x = pack_bf16(v[j * 8 + 0], v[j * 8 + 1]);
+      o.y = pack_bf16(v[j * 8 + 2], v[j * 8 + 3]);
+      o.z = pack_bf16(v[j * 8 + 4], v[j * 8 + 5]);
+      o.w = pack_bf16(v[j * 8 + 6], v[j * 8 + 7]);
+      *reinterpret_cast<uint4*>(stage_row + ((j ^ sw) << 4)) = o;
+    }
+    return;
+  }
   bf16* op = p.out + static_cast<size_t>(out_row) * p.ldo + n0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -367,19 +383,21 @@ constexpr int G2_STAGES = 6;
 constexpr int G2_A_BYTES = BM * BK * 2;           // 16 KB: this CTA's 128 rows of A
 constexpr int G2_B_BYTES = 128 * BK * 2;          // up to 16 KB: this CTA's BN/2 rows of B
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
-constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 1024 + 256;
+constexpr int G2_OUT_STAGE_BYTES = 4 * 2 * 32 * 128;  // per epilogue warp: two [32 x 64] bf16 output tiles
+constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + G2_OUT_STAGE_BYTES + 1024 + 256;
 constexpr int G2_ACC_COLS = 256;                  // TMEM columns per accumulator buffer (2 buffers = 512)
 
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                  const GemmDev p, const int bn) {
+                  const __grid_constant__ CUtensorMap tma_o, const GemmDev p, const int bn) {
   constexpr int STAGES = G2_STAGES;
   extern __shared__ uint8_t smem_raw[];
   // Both CTAs of the pair must use identical offsets (the MMA applies the leader's descriptors to the peer's shared
   // memory), which holds because the dynamic shared window starts at the same shared::cta address in every CTA.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * G2_STAGE_BYTES);
+  uint8_t* out_stage = smem + STAGES * G2_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + G2_OUT_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -397,6 +415,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    if (p.tma_store) tma_prefetch_desc(&tma_o);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -487,21 +506,33 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     const int ew = warp - 4;
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t stores = 0;  // TMA stores issued by this warp (staging buffer = stores & 1)
+    uint8_t* my_stage = out_stage + ew * (2 * 32 * 128);
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m_blk = tile % p.num_m_tiles;
       const int n_blk = tile / p.num_m_tiles;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m_blk * 256 + static_cast<int>(rank) * BM + ew * 32 + lane;
+      const int row0 = m_blk * 256 + static_cast<int>(rank) * BM + ew * 32;
+      const int row = row0 + lane;
       const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * G2_ACC_COLS) + (static_cast<uint32_t>(ew * 32) << 16);
 #pragma unroll 1
       for (int c = 0; c < bn; c += 64) {
         const int n0 = n_blk * bn + c;
-        if (n0 >= p.N) break;  // warp-uniform
+        if (n0 >= p.N || row0 >= p.M) break;  // warp-uniform
         uint32_t r0[32], r1[32];
         tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c), r0);
         tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c + 32), r1);  // may run past bn: still inside the buffer
         tmem_ld_wait();
+        // Units that lie completely inside this tile go through shared memory + TMA (columns past N and rows past M are
+        // clipped by the tensor map); the narrower last unit of a tile whose width is not a multiple of 64 must not
+        // touch its neighbour's columns and is stored directly.
+        const bool staged = p.tma_store && (bn - c >= 64);
+        uint8_t* sbuf = my_stage + (stores & 1u) * (32 * 128);
+        if (staged && stores >= 2) {
+          if (lane == 0) bulk_wait_group_read<1>();  // the store that last used this buffer has read it
+          __syncwarp();
+        }
         if (row < p.M) {
           float v[64];
 #pragma unroll
@@ -512,7 +543,16 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
           int ncols = bn - c;
           if (ncols > 64) ncols = 64;
           if (p.N - n0 < ncols) ncols = p.N - n0;
-          epilogue_unit<EPI>(p, v, row, n0, ncols);
+          epilogue_unit<EPI>(p, v, row, n0, ncols, staged ? sbuf + lane * 128 : nullptr, lane & 7);
+        }
+        if (staged) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tma_o, sbuf, n0, row0);
+            bulk_commit_group();
+          }
+          ++stores;
         }
       }
       tc_fence_before();
@@ -526,6 +566,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   }
 
   // ---- teardown: nobody may exit (or free TMEM) while the peer can still touch this CTA's memory ----
+  if (warp >= 4 && lane == 0) bulk_wait_group<0>();  // staged output tiles fully written
   tc_fence_before();
   cluster_sync_all();
   if (warp == 2) {
@@ -554,7 +595,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmD
 }
 
 template <int EPI>
-static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int bn, cudaStream_t stream) {
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmDev& p, int bn,
+                        cudaStream_t stream) {
   static bool attr_set = false;
   auto kern = gemm2_bf16_kernel<EPI>;
   if (!attr_set) {
@@ -564,18 +606,18 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int clusters = sm_count() / 2;
   const int grid = 2 * (tiles < clusters ? tiles : clusters);
-  kern<<<grid, GEMM_THREADS, G2_SMEM_BYTES, stream>>>(ta, tb, p, bn);
+  kern<<<grid, GEMM_THREADS, G2_SMEM_BYTES, stream>>>(ta, tb, to, p, bn);
   ORVB_CHECK_CUDA(cudaGetLastError());
   return ORVB_OK;
 }
 
-static int launch_gemm2_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int bn,
-                            cudaStream_t stream) {
+static int launch_gemm2_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmDev& p,
+                            int bn, cudaStream_t stream) {
   switch (epi) {
-    case ORVB_EPI_BIAS: return launch_gemm2<ORVB_EPI_BIAS>(ta, tb, p, bn, stream);
-    case ORVB_EPI_GELU: return launch_gemm2<ORVB_EPI_GELU>(ta, tb, p, bn, stream);
-    case ORVB_EPI_GATE_RESID: return launch_gemm2<ORVB_EPI_GATE_RESID>(ta, tb, p, bn, stream);
-    case ORVB_EPI_QKV: return launch_gemm2<ORVB_EPI_QKV>(ta, tb, p, bn, stream);
+    case ORVB_EPI_BIAS: return launch_gemm2<ORVB_EPI_BIAS>(ta, tb, to, p, bn, stream);
+    case ORVB_EPI_GELU: return launch_gemm2<ORVB_EPI_GELU>(ta, tb, to, p, bn, stream);
+    case ORVB_EPI_GATE_RESID: return launch_gemm2<ORVB_EPI_GATE_RESID>(ta, tb, to, p, bn, stream);
+    case ORVB_EPI_QKV: return launch_gemm2<ORVB_EPI_QKV>(ta, tb, to, p, bn, stream);
   }
   set_error("orvb_gemm_bf16: unknown epilogue %d", epi);
   return ORVB_EINVAL;
@@ -643,9 +685,9 @@ int gemm_pick_bn_pair(int m, int n, int epi) {
 }
 
 // bn > 0: 1-CTA kernel with that N tile; bn < 0: CTA-pair kernel with N tile -bn.
-int gemm_launch_prepared(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p, int bn, int epi,
-                         cudaStream_t stream) {
-  if (bn < 0) return launch_gemm2_epi(epi, ta, tb, p, -bn, stream);
+int gemm_launch_prepared(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmDev& p, int bn,
+                         int epi, cudaStream_t stream) {
+  if (bn < 0) return launch_gemm2_epi(epi, ta, tb, to, p, -bn, stream);
   switch (bn) {
     case 256: return launch_gemm_epi<256>(epi, ta, tb, p, stream);
     case 192: return launch_gemm_epi<192>(epi, ta, tb, p, stream);
@@ -656,7 +698,8 @@ int gemm_launch_prepared(const CUtensorMap& ta, const CUtensorMap& tb, const Gem
   return ORVB_EINVAL;
 }
 
-int gemm_prepare(const orvb_gemm_args* a, int bn_override, CUtensorMap* ta, CUtensorMap* tb, GemmDev* p, int* bn_out) {
+int gemm_prepare(const orvb_gemm_args* a, int bn_override, CUtensorMap* ta, CUtensorMap* tb, CUtensorMap* to, GemmDev* p,
+                 int* bn_out) {
   ORVB_REQUIRE(a != nullptr && a->a && a->w && a->out, ORVB_EINVAL, "orvb_gemm_bf16: null pointer");
   ORVB_REQUIRE(a->m > 0 && a->n > 0 && a->k > 0, ORVB_ESHAPE, "orvb_gemm_bf16: empty problem m=%d n=%d k=%d", a->m,
                a->n, a->k);
@@ -692,7 +735,16 @@ int gemm_prepare(const orvb_gemm_args* a, int bn_override, CUtensorMap* ta, CUte
   if (rc != ORVB_OK) return rc;
   rc = make_tmap_2d_bf16(tb, a->w, a->n, a->k, a->ldw, pair ? (-bn) / 2 : bn, BK);
   if (rc != ORVB_OK) return rc;
+  // Output through TMA (pair kernel, rows written in place): [32 rows x 64 cols] boxes of the [M, N] output
+  const bool tma_store = pair && a->src_rows == 0 && a->mv_tokens == 0;
+  if (tma_store) {
+    rc = make_tmap_2d_bf16(to, a->out, a->m, a->n, a->ldo, 32, 64);
+    if (rc != ORVB_OK) return rc;
+  } else {
+    *to = *ta;  // unused placeholder
+  }
   GemmDev d;
+  d.tma_store = tma_store ? 1 : 0;
   d.M = a->m; d.N = a->n; d.K = a->k;
   d.out = static_cast<bf16*>(a->out); d.ldo = a->ldo;
   d.bias = static_cast<const bf16*>(a->bias);
@@ -715,12 +767,12 @@ int gemm_prepare(const orvb_gemm_args* a, int bn_override, CUtensorMap* ta, CUte
 }
 
 int gemm_run(const orvb_gemm_args* a, cudaStream_t stream) {
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, to;
   GemmDev p;
   int bn;
-  int rc = gemm_prepare(a, 0, &ta, &tb, &p, &bn);
+  int rc = gemm_prepare(a, 0, &ta, &tb, &to, &p, &bn);
   if (rc != ORVB_OK) return rc;
-  return gemm_launch_prepared(ta, tb, p, bn, a->epilogue, stream);
+  return gemm_launch_prepared(ta, tb, to, p, bn, a->epilogue, stream);
 }
 
 }  // namespace orvb
@@ -729,12 +781,12 @@ extern "C" int orvb_gemm_bf16(const orvb_gemm_args* args, void* stream) {
   using namespace orvb;
   int rc = check_arch();
   if (rc != ORVB_OK) return rc;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, to;
   GemmDev p;
   int bn;
-  rc = gemm_prepare(args, 0, &ta, &tb, &p, &bn);
+  rc = gemm_prepare(args, 0, &ta, &tb, &to, &p, &bn);
   if (rc != ORVB_OK) return rc;
-  return gemm_launch_prepared(ta, tb, p, bn, args->epilogue, static_cast<cudaStream_t>(stream));
+  return gemm_launch_prepared(ta, tb, to, p, bn, args->epilogue, static_cast<cudaStream_t>(stream));
 }
 
 // Test hook: same as orvb_gemm_bf16 with a forced tile: bn in {64,128,192,256} = 1-CTA kernel, -bn (multiple of 16,
@@ -743,10 +795,10 @@ extern "C" int orvb_gemm_bf16_bn(const orvb_gemm_args* args, int bn, void* strea
   using namespace orvb;
   int rc = check_arch();
   if (rc != ORVB_OK) return rc;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, to;
   GemmDev p;
   int bn_used;
-  rc = gemm_prepare(args, bn, &ta, &tb, &p, &bn_used);
+  rc = gemm_prepare(args, bn, &ta, &tb, &to, &p, &bn_used);
   if (rc != ORVB_OK) return rc;
-  return gemm_launch_prepared(ta, tb, p, bn_used, args->epilogue, static_cast<cudaStream_t>(stream));
+  return gemm_launch_prepared(ta, tb, to, p, bn_used, args->epilogue, static_cast<cudaStream_t>(stream));
 }

@@ -102,6 +102,24 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, ui
       : "memory");
 }
 
+// 2-D tiled store shared -> global (bulk async-group completion); out-of-bounds rows / columns of the box are skipped.
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// waits until at most N of this thread's bulk groups still READ their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_group() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, fences, MMA, commit, load
 // ---------------------------------------------------------------------------------------------
@@ -295,6 +313,51 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+
+// ---- packed fp32 pairs (FFMA2 / FADD2 operate on 64-bit register pairs) ----
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2p(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2p(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+__device__ __forceinline__ f32x2 mul2p(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float tanh_approx(float x) {  // MUFU.TANH, max relative error 2^-11
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// GELU(tanh) of a pair for the GEMM epilogue: 0.5 x (1 + tanh(x (k0 + k0 k1 x^2))) in packed fp32 with one MUFU per
+// value (the exp + divide form below costs two MUFU and ~3x the FP instructions; inside a power-capped GEMM the
+// epilogue's instruction count is not free).  |error| <= 2^-11 * |x| / 2, below the bf16 rounding of the output
+// everywhere but the far negative tail, where the value itself is ~0.
+__device__ __forceinline__ void gelu_tanh2(float& a, float& b) {
+  const float k0 = 0.7978845608028654f, k0k1 = 0.7978845608028654f * 0.044715f;
+  const f32x2 x = pk2(a, b);
+  const f32x2 inner = fma2p(mul2p(x, x), pk2(k0k1, k0k1), pk2(k0, k0));
+  float u0, u1;
+  upk2(mul2p(x, inner), u0, u1);
+  const f32x2 h = mul2p(x, pk2(0.5f, 0.5f));
+  upk2(fma2p(h, pk2(tanh_approx(u0), tanh_approx(u1)), h), a, b);
+}
 
 // tanh-approximated GELU, as torch.nn.functional.gelu(x, approximate="tanh").
 __device__ __forceinline__ float gelu_tanh(float x) {
