@@ -192,6 +192,87 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const LnDev p) {
   }
 }
 
+// Hot variant of the kernel above for the block norms (60 launches per forward): y = xhat * A_g + B_g with the folded
+// A/B tables.  Eight consecutive rows per CTA touch at most two (group, text|video) table rows (every segment of the
+// sequence is far longer than 8 rows), so those are staged once in shared memory instead of being prefetched into
+// every warp's registers; x stays packed (bf16) in registers.  ~60 registers per thread: all 3226 rows of a 2B
+// forward are resident in one wave (the register-heavy generic kernel ran 1 CTA per SM, i.e. three waves).
+template <int MAXC>
+__global__ void __launch_bounds__(256, 4) ln_ab_kernel(const LnDev p) {
+  extern __shared__ uint4 s_ab[];  // [2 slots][A: dim/8 chunks | B: dim/8 chunks]
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nchunks = p.dim >> 3;
+  const int row0 = blockIdx.x * 8;
+  const int row_last = min(row0 + 7, p.rows - 1);
+  int t0, t1;
+  const int g0 = row_group_pw(p.rm, row0, &t0);
+  const int g1 = row_group_pw(p.rm, row_last, &t1);
+  const bf16* ap0 = p.ab + static_cast<size_t>(g0) * p.ab_ld + (t0 ? 0 : 2 * p.dim);
+  const bf16* ap1 = p.ab + static_cast<size_t>(g1) * p.ab_ld + (t1 ? 0 : 2 * p.dim);
+  const int row = row0 + warp;
+  const bool live = row < p.rows;
+  // this warp's row first (longest latency), then the cooperative table copy
+  uint4 xr[MAXC];
+  if (live) {
+    const bf16* xrow = p.x + static_cast<size_t>(row) * p.dim;
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nchunks) xr[i] = *reinterpret_cast<const uint4*>(xrow + c * 8);
+    }
+  }
+  const int two = 2 * nchunks;  // A then B, contiguous in the table row
+  for (int i = threadIdx.x; i < two; i += 256) s_ab[i] = *reinterpret_cast<const uint4*>(ap0 + i * 8);
+  if (ap1 != ap0)
+    for (int i = threadIdx.x; i < two; i += 256) s_ab[two + i] = *reinterpret_cast<const uint4*>(ap1 + i * 8);
+  __syncthreads();
+  if (!live) return;
+  int tt;
+  const int g = row_group_pw(p.rm, row, &tt);
+  const uint4* tab = s_ab + ((g == g0 && tt == t0) ? 0 : two);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i)
+    if (lane + 32 * i < nchunks) {
+      float f[8];
+      unpack8(xr[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += f[j];
+    }
+  const float mean = warp_sum(s) / static_cast<float>(p.dim);
+  float qv = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i)
+    if (lane + 32 * i < nchunks) {
+      float f[8];
+      unpack8(xr[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = f[j] - mean;
+        qv += d * d;
+      }
+    }
+  const float rstd = rsqrtf(warp_sum(qv) / static_cast<float>(p.dim) + p.eps);
+  bf16* yr = p.y + static_cast<size_t>(row) * p.dim;
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nchunks) {
+      float f[8], a8[8], b8[8], o[8];
+      unpack8(xr[i], f);
+      unpack8(tab[c], a8);
+      unpack8(tab[nchunks + c], b8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (f[j] - mean) * rstd * a8[j] + b8[j];
+      uint4 u;
+      u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]);
+      u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
+      *reinterpret_cast<uint4*>(yr + c * 8) = u;
+    }
+  }
+}
+
 // A/B table for the LayerNorm+modulate kernel, built once per forward from the fp32 AdaLN tables:
 //   text  variant: A = w (1 + mod[g][text_off + D ..]),  B = b (1 + ...) + mod[g][text_off ..]
 //   video variant: A = w (1 + mod[g][video_off + D ..]), B = b (1 + ...) + mod[g][video_off ..]
@@ -242,6 +323,16 @@ int ln_modulate_launch(const orvb_ln_args* a, cudaStream_t stream) {
   const int rows_per_block = 8;
   dim3 grid((a->rows + rows_per_block - 1) / rows_per_block);
   const int nchunks = a->dim / 8;
+  // A then B must be adjacent in a table row (ab_combine writes them so) for the staged copy of the hot kernel
+  if (d.ab != nullptr && d.pre_w == nullptr && !d.in_video_only && d.rm.seq_len > 0 && d.rm.text_len >= 8 &&
+      (d.rm.tokens_per_group <= 0 || d.rm.tokens_per_group >= 8) && d.rm.seq_len - d.rm.text_len >= 8) {
+    const int smem = 2 * 2 * nchunks * 16;
+    if (nchunks <= 32 * 8) ln_ab_kernel<8><<<grid, 256, smem, stream>>>(d);
+    else if (nchunks <= 32 * 12) ln_ab_kernel<12><<<grid, 256, smem, stream>>>(d);
+    else ln_ab_kernel<16><<<grid, 256, smem, stream>>>(d);
+    ORVB_CHECK_CUDA(cudaGetLastError());
+    return ORVB_OK;
+  }
   if (nchunks <= 32 * 8) ln_modulate_kernel<8><<<grid, 256, 0, stream>>>(d);
   else if (nchunks <= 32 * 12) ln_modulate_kernel<12><<<grid, 256, 0, stream>>>(d);
   else ln_modulate_kernel<16><<<grid, 256, 0, stream>>>(d);
@@ -251,11 +342,13 @@ int ln_modulate_launch(const orvb_ln_args* a, cudaStream_t stream) {
 
 // ---------------------------------------------------------------------------------------------------
 // Skinny linear: y[r, n] = act(x[r, :] . W[n, :] + b[n]) for <= 8 rows per pass.  HBM-bound on W (the AdaLN
-// linears hold 354 M parameters in the 2B model: ~0.7 GB read per forward), so each warp streams 4 weight rows
-// with 16-byte loads and reuses the fp32 activations (L1-resident) across them.
+// linears hold 354 M parameters in the 2B model: ~0.7 GB read per forward), so the kernel is written for few
+// instructions per weight byte: four lanes share one weight row (each streams every fourth 16-byte chunk, so a warp
+// reads 64 contiguous bytes of 8 rows per load), products are packed FFMA2 over k pairs against fp32 activations
+// held in shared memory, and the only cross-lane traffic is a two-step shuffle over the four lanes of a row.
 // ---------------------------------------------------------------------------------------------------
 constexpr int SK_ROWS = 8;
-constexpr int SK_COLS = 8;
+constexpr int SK_COLS = 8;   // weight rows (output columns) per warp
 constexpr int SK_WARPS = 8;
 
 template <bool BATCHED>
@@ -271,54 +364,44 @@ __global__ void __launch_bounds__(256) skinny_linear_kernel(const float* __restr
   for (int i = threadIdx.x * 4; i < nr * k; i += blockDim.x * 4)
     *reinterpret_cast<float4*>(sx + i) = *reinterpret_cast<const float4*>(x + static_cast<size_t>(r0) * k + i);
   __syncthreads();
-  const int n0 = (blockIdx.x * SK_WARPS + warp) * SK_COLS;
-  if (n0 >= n) return;
-  float acc[SK_ROWS][SK_COLS];
+  const int col = (blockIdx.x * SK_WARPS + warp) * SK_COLS + (lane >> 2);
+  const int q = lane & 3;
+  const bool live = col < n;
+  const bf16* wrow = job.w + static_cast<size_t>(live ? col : 0) * k;
+  f32x2 acc[SK_ROWS];
 #pragma unroll
-  for (int r = 0; r < SK_ROWS; ++r)
-#pragma unroll
-    for (int c = 0; c < SK_COLS; ++c) acc[r][c] = 0.f;
+  for (int r = 0; r < SK_ROWS; ++r) acc[r] = pk2(0.f, 0.f);
 
-  for (int k0 = lane * 8; k0 < k; k0 += 256) {
-    uint4 wq[SK_COLS];
-#pragma unroll
-    for (int c = 0; c < SK_COLS; ++c) {  // all weight loads of this step in flight before any math
-      if (n0 + c < n) wq[c] = *reinterpret_cast<const uint4*>(job.w + static_cast<size_t>(n0 + c) * k + k0);
-      else wq[c] = make_uint4(0u, 0u, 0u, 0u);
-    }
+#pragma unroll 4
+  for (int k0 = q * 8; k0 < k; k0 += 32) {
+    const uint4 wq = *reinterpret_cast<const uint4*>(wrow + k0);
+    const f32x2 w01 = pk2(bf16_lo(wq.x), bf16_hi(wq.x)), w23 = pk2(bf16_lo(wq.y), bf16_hi(wq.y));
+    const f32x2 w45 = pk2(bf16_lo(wq.z), bf16_hi(wq.z)), w67 = pk2(bf16_lo(wq.w), bf16_hi(wq.w));
 #pragma unroll
     for (int r = 0; r < SK_ROWS; ++r) {
       if (r < nr) {
-        const float4 a0 = *reinterpret_cast<const float4*>(sx + r * k + k0);
-        const float4 a1 = *reinterpret_cast<const float4*>(sx + r * k + k0 + 4);
-        const float xv[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-        for (int c = 0; c < SK_COLS; ++c) {
-          float w[8];
-          unpack8(wq[c], w);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[r][c] = fmaf(xv[j], w[j], acc[r][c]);
-        }
+        const ulonglong2 xa = *reinterpret_cast<const ulonglong2*>(sx + r * k + k0);
+        const ulonglong2 xb = *reinterpret_cast<const ulonglong2*>(sx + r * k + k0 + 4);
+        acc[r] = fma2p(xa.x, w01, acc[r]);
+        acc[r] = fma2p(xa.y, w23, acc[r]);
+        acc[r] = fma2p(xb.x, w45, acc[r]);
+        acc[r] = fma2p(xb.y, w67, acc[r]);
       }
     }
   }
 #pragma unroll
-  for (int r = 0; r < SK_ROWS; ++r)
-#pragma unroll
-    for (int c = 0; c < SK_COLS; ++c) acc[r][c] = warp_sum(acc[r][c]);
-  if (lane == 0) {
-#pragma unroll
-    for (int r = 0; r < SK_ROWS; ++r) {
-      if (r < nr) {
-#pragma unroll
-        for (int c = 0; c < SK_COLS; ++c) {
-          if (n0 + c < n) {
-            float v = acc[r][c] + (job.b != nullptr ? __bfloat162float(job.b[n0 + c]) : 0.f);
-            if (act == 1) v = silu(v);
-            else if (act == 2) v = gelu_tanh(v);
-            job.y[static_cast<size_t>(r0 + r) * n + n0 + c] = v;
-          }
-        }
+  for (int r = 0; r < SK_ROWS; ++r) {
+    if (r < nr) {
+      float lo, hi;
+      upk2(acc[r], lo, hi);
+      float v = lo + hi;
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      if (q == 0 && live) {
+        v += (job.b != nullptr ? __bfloat162float(job.b[col]) : 0.f);
+        if (act == 1) v = silu(v);
+        else if (act == 2) v = gelu_tanh(v);
+        job.y[static_cast<size_t>(r0 + r) * n + col] = v;
       }
     }
   }

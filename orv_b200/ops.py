@@ -90,7 +90,10 @@ def attention(qkv: torch.Tensor, batch: int, seq_len: int, heads: int, scale: fl
 
 def ln_modulate(x: torch.Tensor, ln_w, ln_b, eps: float, mod: Optional[torch.Tensor] = None, text_off: int = 0,
                 video_off: int = 0, scale_first: bool = False, rm: Optional[L.RowMap] = None,
-                in_video_only: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                in_video_only: bool = False, out: Optional[torch.Tensor] = None,
+                ab: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """LayerNorm + AdaLN modulate.  `ab` (bf16 [groups, 4*dim] = text A | text B | video A | video B per group) is the
+    folded form the forward uses: y = xhat * A + B with A = w (1 + scale), B = b (1 + scale) + shift."""
     _req(x, torch.bfloat16, "x")
     rows_in, dim = x.shape
     rmap = rm if rm is not None else rowmap()
@@ -110,6 +113,9 @@ def ln_modulate(x: torch.Tensor, ln_w, ln_b, eps: float, mod: Optional[torch.Ten
     a.text_off, a.video_off, a.scale_first = text_off, video_off, int(scale_first)
     a.rowmap = rmap
     a.in_video_only = int(in_video_only)
+    if ab is not None:
+        _req(ab, torch.bfloat16, "ab")
+        a.ab, a.ab_ld = ab.data_ptr(), ab.stride(-2)
     L.check(L.load().orvb_ln_modulate(C.byref(a), L.current_stream()), "orvb_ln_modulate")
     return out
 

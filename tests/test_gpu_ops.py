@@ -178,6 +178,28 @@ def test_attention(ops, B, S, H):
     assert (out.float() - ref).abs().max().item() < 2e-2
 
 
+@pytest.mark.parametrize("D,S,St,tpf,G", [(1920, 3226, 226, 600, 6), (3072, 2026, 226, 600, 4), (128, 75, 11, 16, 5),
+                                         (1920, 100, 20, 0, 1)])
+def test_ln_modulate_folded_tables(ops, D, S, St, tpf, G):
+    """The block-norm path of the forward: y = xhat * A_g + B_g with per-(group, text|video) bf16 tables staged in shared
+    memory; 8-row CTAs straddle the text/video, frame-group and batch boundaries."""
+    torch.manual_seed(16)
+    B = 2
+    x = (torch.randn(B * S, D, device=DEV) * 2 + 0.5).bfloat16()
+    ab = torch.randn(B * G, 4 * D, device=DEV).bfloat16()
+    rm = ops.rowmap(S, St, tpf, G)
+    y = ops.ln_modulate(x, None, None, 1e-5, rm=rm, ab=ab)
+    s = torch.arange(B * S, device=DEV) % S
+    bidx = torch.arange(B * S, device=DEV) // S
+    is_text = s < St
+    grp = torch.where(is_text | (tpf <= 0), torch.zeros_like(s), 1 + (s - St) // max(tpf, 1)) + bidx * G
+    tab = ab.float()[grp]
+    A = torch.where(is_text[:, None], tab[:, :D], tab[:, 2 * D:3 * D])
+    Bt = torch.where(is_text[:, None], tab[:, D:2 * D], tab[:, 3 * D:])
+    ref = torch.nn.functional.layer_norm(x.float(), (D,), eps=1e-5) * A + Bt
+    assert _relmax(y, ref) < BF16_TOL
+
+
 @pytest.mark.parametrize("D", [128, 1920, 3072])
 def test_ln_modulate(ops, D):
     torch.manual_seed(6)
