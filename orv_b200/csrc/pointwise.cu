@@ -361,20 +361,25 @@ __global__ void __launch_bounds__(256) skinny_linear_kernel(const float* __restr
   const int warp = threadIdx.x >> 5;
   const int r0 = blockIdx.y * SK_ROWS;
   const int nr = min(SK_ROWS, rows - r0);
-  for (int i = threadIdx.x * 4; i < nr * k; i += blockDim.x * 4)
-    *reinterpret_cast<float4*>(sx + i) = *reinterpret_cast<const float4*>(x + static_cast<size_t>(r0) * k + i);
-  __syncthreads();
   const int col = (blockIdx.x * SK_WARPS + warp) * SK_COLS + (lane >> 2);
   const int q = lane & 3;
   const bool live = col < n;
   const bf16* wrow = job.w + static_cast<size_t>(live ? col : 0) * k;
+  // The AdaLN linears (time_embed_dim 512): the lane's whole 256-byte share of its weight row goes in flight at once
+  // and before the activation staging, so a warp pays a single HBM round trip.
+  uint4 wq[16];
+  if (k == 512) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) wq[i] = *reinterpret_cast<const uint4*>(wrow + q * 8 + 32 * i);
+  }
+  for (int i = threadIdx.x * 4; i < nr * k; i += blockDim.x * 4)
+    *reinterpret_cast<float4*>(sx + i) = *reinterpret_cast<const float4*>(x + static_cast<size_t>(r0) * k + i);
+  __syncthreads();
   f32x2 acc[SK_ROWS];
 #pragma unroll
   for (int r = 0; r < SK_ROWS; ++r) acc[r] = pk2(0.f, 0.f);
 
-#pragma unroll 4
-  for (int k0 = q * 8; k0 < k; k0 += 32) {
-    const uint4 wq = *reinterpret_cast<const uint4*>(wrow + k0);
+  auto step = [&](const uint4& wq, int k0) {
     const f32x2 w01 = pk2(bf16_lo(wq.x), bf16_hi(wq.x)), w23 = pk2(bf16_lo(wq.y), bf16_hi(wq.y));
     const f32x2 w45 = pk2(bf16_lo(wq.z), bf16_hi(wq.z)), w67 = pk2(bf16_lo(wq.w), bf16_hi(wq.w));
 #pragma unroll
@@ -388,6 +393,13 @@ __global__ void __launch_bounds__(256) skinny_linear_kernel(const float* __restr
         acc[r] = fma2p(xb.y, w67, acc[r]);
       }
     }
+  };
+  if (k == 512) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) step(wq[i], q * 8 + 32 * i);
+  } else {
+#pragma unroll 4
+    for (int k0 = q * 8; k0 < k; k0 += 32) step(*reinterpret_cast<const uint4*>(wrow + k0), k0);
   }
 #pragma unroll
   for (int r = 0; r < SK_ROWS; ++r) {
