@@ -275,8 +275,20 @@ def run_ours(args):
         kernels[n] = ent
     fwd_ms = sum(ms) / nprof
     dom = max(flops.keys(), key=lambda n: kernels[n]["ms_per_forward"])
+    # dram bytes per launch of the dominant kernel, from the committed ncu capture of the same build (profiles/)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        key = {"attention": "attention_kernel", "gemm_qkv": "gemm2_bf16_kernel<3>", "gemm_ff1": "gemm2_bf16_kernel<1>",
+               "gemm_ff2": "gemm2_bf16_kernel<2>", "gemm_out": "gemm2_bf16_kernel<2>"}[dom]
+        for kname, ent in tj.items():
+            if key in kname and ent:
+                traffic = ent[0]["dram_bytes"]
+                break
     roofline = {"bound": "tensor", "kernel": dom, "achieved": kernels[dom]["tflops"], "peak": pk["bf16"],
-                "unit": "TFLOP/s", "frac": round(kernels[dom]["tflops"] / pk["bf16"], 4), "traffic": None,
+                "unit": "TFLOP/s", "frac": round(kernels[dom]["tflops"] / pk["bf16"], 4), "traffic": traffic,
+                "algorithmic_flop_per_launch": flops[dom],
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['source']})",
                 "forward_ms_sum_of_kernels": round(fwd_ms, 3),
                 "forward_tensor_frac": round(FWD_TFLOP / (fwd_ms * 1e-3) / pk["bf16"], 4)}

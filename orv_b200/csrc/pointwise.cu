@@ -343,77 +343,89 @@ int ln_modulate_launch(const orvb_ln_args* a, cudaStream_t stream) {
 // ---------------------------------------------------------------------------------------------------
 // Skinny linear: y[r, n] = act(x[r, :] . W[n, :] + b[n]) for <= 8 rows per pass.  HBM-bound on W (the AdaLN
 // linears hold 354 M parameters in the 2B model: ~0.7 GB read per forward), so the kernel is written for few
-// instructions per weight byte: four lanes share one weight row (each streams every fourth 16-byte chunk, so a warp
-// reads 64 contiguous bytes of 8 rows per load), products are packed FFMA2 over k pairs against fp32 activations
-// held in shared memory, and the only cross-lane traffic is a two-step shuffle over the four lanes of a row.
+// instructions AND few shared-memory reads per weight byte: four lanes share a weight row (a warp reads 64 contiguous
+// bytes of 8 rows per load), each lane quad works on SK_QCOLS weight rows at once so that one 32-byte read of the
+// fp32 activations from shared memory feeds SK_QCOLS x 4 packed FFMA2 (ncu on the 1-row-per-quad version: 31 % issue
+// activity, top stall short_scoreboard — the broadcast LDS.128 of x cost 4 LSU passes each and bounded the kernel at
+// 2.2 TB/s), and the only cross-lane traffic is a two-step shuffle over the four lanes of a row.
 // ---------------------------------------------------------------------------------------------------
 constexpr int SK_ROWS = 8;
-constexpr int SK_COLS = 8;   // weight rows (output columns) per warp
 constexpr int SK_WARPS = 8;
 
-template <bool BATCHED>
+// SK_QCOLS = weight rows per lane quad: 4 for the big batched launch, 1 for the small MLPs (few columns: spread them
+// over more CTAs instead).
+template <bool BATCHED, int SK_QCOLS>
 __global__ void __launch_bounds__(256) skinny_linear_kernel(const float* __restrict__ x, SkinnyJob single,
                                                             const SkinnyJob* __restrict__ jobs, int rows, int n,
                                                             int k, int act) {
-  extern __shared__ float sx[];  // [nr][k] activations of this row chunk, shared by the 64 columns of the block
+  extern __shared__ float sx[];  // [nr][k] activations of this row chunk, shared by all columns of the block
   const SkinnyJob job = BATCHED ? jobs[blockIdx.z] : single;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int r0 = blockIdx.y * SK_ROWS;
   const int nr = min(SK_ROWS, rows - r0);
-  const int col = (blockIdx.x * SK_WARPS + warp) * SK_COLS + (lane >> 2);
-  const int q = lane & 3;
-  const bool live = col < n;
-  const bf16* wrow = job.w + static_cast<size_t>(live ? col : 0) * k;
-  // The AdaLN linears (time_embed_dim 512): the lane's whole 256-byte share of its weight row goes in flight at once
-  // and before the activation staging, so a warp pays a single HBM round trip.
-  uint4 wq[16];
-  if (k == 512) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) wq[i] = *reinterpret_cast<const uint4*>(wrow + q * 8 + 32 * i);
-  }
   for (int i = threadIdx.x * 4; i < nr * k; i += blockDim.x * 4)
     *reinterpret_cast<float4*>(sx + i) = *reinterpret_cast<const float4*>(x + static_cast<size_t>(r0) * k + i);
   __syncthreads();
-  f32x2 acc[SK_ROWS];
+  constexpr int SK_COLS = 8 * SK_QCOLS;  // weight rows (output columns) per warp
+  // quad g of the warp owns columns col0 + g + 8 * c, c < SK_QCOLS: a warp-wide load still touches 8 adjacent rows
+  const int col0 = (blockIdx.x * SK_WARPS + warp) * SK_COLS + (lane >> 2);
+  const int q = lane & 3;
+  const bf16* wrow[SK_QCOLS];
 #pragma unroll
-  for (int r = 0; r < SK_ROWS; ++r) acc[r] = pk2(0.f, 0.f);
+  for (int c = 0; c < SK_QCOLS; ++c) {
+    const int col = col0 + 8 * c;
+    wrow[c] = job.w + static_cast<size_t>(col < n ? col : 0) * k;
+  }
+  f32x2 acc[SK_QCOLS][SK_ROWS];
+#pragma unroll
+  for (int c = 0; c < SK_QCOLS; ++c)
+#pragma unroll
+    for (int r = 0; r < SK_ROWS; ++r) acc[c][r] = pk2(0.f, 0.f);
 
-  auto step = [&](const uint4& wq, int k0) {
-    const f32x2 w01 = pk2(bf16_lo(wq.x), bf16_hi(wq.x)), w23 = pk2(bf16_lo(wq.y), bf16_hi(wq.y));
-    const f32x2 w45 = pk2(bf16_lo(wq.z), bf16_hi(wq.z)), w67 = pk2(bf16_lo(wq.w), bf16_hi(wq.w));
+#pragma unroll 2
+  for (int k0 = q * 8; k0 < k; k0 += 32) {
+    f32x2 w[SK_QCOLS][4];
+#pragma unroll
+    for (int c = 0; c < SK_QCOLS; ++c) {
+      const uint4 wq = *reinterpret_cast<const uint4*>(wrow[c] + k0);
+      w[c][0] = pk2(bf16_lo(wq.x), bf16_hi(wq.x));
+      w[c][1] = pk2(bf16_lo(wq.y), bf16_hi(wq.y));
+      w[c][2] = pk2(bf16_lo(wq.z), bf16_hi(wq.z));
+      w[c][3] = pk2(bf16_lo(wq.w), bf16_hi(wq.w));
+    }
 #pragma unroll
     for (int r = 0; r < SK_ROWS; ++r) {
       if (r < nr) {
         const ulonglong2 xa = *reinterpret_cast<const ulonglong2*>(sx + r * k + k0);
         const ulonglong2 xb = *reinterpret_cast<const ulonglong2*>(sx + r * k + k0 + 4);
-        acc[r] = fma2p(xa.x, w01, acc[r]);
-        acc[r] = fma2p(xa.y, w23, acc[r]);
-        acc[r] = fma2p(xb.x, w45, acc[r]);
-        acc[r] = fma2p(xb.y, w67, acc[r]);
+#pragma unroll
+        for (int c = 0; c < SK_QCOLS; ++c) {
+          acc[c][r] = fma2p(xa.x, w[c][0], acc[c][r]);
+          acc[c][r] = fma2p(xa.y, w[c][1], acc[c][r]);
+          acc[c][r] = fma2p(xb.x, w[c][2], acc[c][r]);
+          acc[c][r] = fma2p(xb.y, w[c][3], acc[c][r]);
+        }
       }
     }
-  };
-  if (k == 512) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) step(wq[i], q * 8 + 32 * i);
-  } else {
-#pragma unroll 4
-    for (int k0 = q * 8; k0 < k; k0 += 32) step(*reinterpret_cast<const uint4*>(wrow + k0), k0);
   }
 #pragma unroll
-  for (int r = 0; r < SK_ROWS; ++r) {
-    if (r < nr) {
-      float lo, hi;
-      upk2(acc[r], lo, hi);
-      float v = lo + hi;
-      v += __shfl_xor_sync(0xffffffffu, v, 1);
-      v += __shfl_xor_sync(0xffffffffu, v, 2);
-      if (q == 0 && live) {
-        v += (job.b != nullptr ? __bfloat162float(job.b[col]) : 0.f);
-        if (act == 1) v = silu(v);
-        else if (act == 2) v = gelu_tanh(v);
-        job.y[static_cast<size_t>(r0 + r) * n + col] = v;
+  for (int c = 0; c < SK_QCOLS; ++c) {
+    const int col = col0 + 8 * c;
+#pragma unroll
+    for (int r = 0; r < SK_ROWS; ++r) {
+      if (r < nr) {
+        float lo, hi;
+        upk2(acc[c][r], lo, hi);
+        float v = lo + hi;
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (q == 0 && col < n) {
+          v += (job.b != nullptr ? __bfloat162float(job.b[col]) : 0.f);
+          if (act == 1) v = silu(v);
+          else if (act == 2) v = gelu_tanh(v);
+          job.y[static_cast<size_t>(r0 + r) * n + col] = v;
+        }
       }
     }
   }
@@ -423,18 +435,27 @@ int skinny_linear_launch(const float* x, const SkinnyJob& job, const SkinnyJob* 
                          int n, int k, int act, cudaStream_t stream) {
   ORVB_REQUIRE(x != nullptr && rows > 0 && n > 0 && k > 0, ORVB_EINVAL, "orvb_skinny_linear: bad arguments");
   ORVB_REQUIRE(k % 8 == 0 && k <= 12288, ORVB_ESHAPE, "orvb_skinny_linear: k must be a multiple of 8 and <= 12288 (got %d)", k);
-  const int cols_per_block = SK_WARPS * SK_COLS;
+  const int njobs = jobs_dev ? num_jobs : 1;
+  const bool wide = static_cast<long>(n) * njobs >= 16384;
+  const int cols_per_block = SK_WARPS * 8 * (wide ? 4 : 1);
   const int smem = SK_ROWS * k * static_cast<int>(sizeof(float));
-  dim3 grid((n + cols_per_block - 1) / cols_per_block, (rows + SK_ROWS - 1) / SK_ROWS, jobs_dev ? num_jobs : 1);
+  dim3 grid((n + cols_per_block - 1) / cols_per_block, (rows + SK_ROWS - 1) / SK_ROWS, njobs);
   static bool attr_set = false;
   if (!attr_set) {
-    ORVB_CHECK_CUDA(cudaFuncSetAttribute(skinny_linear_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    ORVB_CHECK_CUDA(cudaFuncSetAttribute(skinny_linear_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    ORVB_CHECK_CUDA(cudaFuncSetAttribute(skinny_linear_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    ORVB_CHECK_CUDA(cudaFuncSetAttribute(skinny_linear_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    ORVB_CHECK_CUDA(cudaFuncSetAttribute(skinny_linear_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    ORVB_CHECK_CUDA(cudaFuncSetAttribute(skinny_linear_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   ORVB_REQUIRE(smem <= 200 * 1024, ORVB_ESHAPE, "orvb_skinny_linear: k too large for the shared-memory staging");
-  if (jobs_dev != nullptr) skinny_linear_kernel<true><<<grid, 256, smem, stream>>>(x, job, jobs_dev, rows, n, k, act);
-  else skinny_linear_kernel<false><<<grid, 256, smem, stream>>>(x, job, nullptr, rows, n, k, act);
+  if (jobs_dev != nullptr) {
+    if (wide) skinny_linear_kernel<true, 4><<<grid, 256, smem, stream>>>(x, job, jobs_dev, rows, n, k, act);
+    else skinny_linear_kernel<true, 1><<<grid, 256, smem, stream>>>(x, job, jobs_dev, rows, n, k, act);
+  } else {
+    if (wide) skinny_linear_kernel<false, 4><<<grid, 256, smem, stream>>>(x, job, nullptr, rows, n, k, act);
+    else skinny_linear_kernel<false, 1><<<grid, 256, smem, stream>>>(x, job, nullptr, rows, n, k, act);
+  }
   ORVB_CHECK_CUDA(cudaGetLastError());
   return ORVB_OK;
 }
