@@ -155,3 +155,72 @@ def test_full_size_config2_forward_vs_fp32_oracle():
     print(f"full-size rel err: ours {e_ours:.3e}  torch-bf16 {e_torch:.3e}")
     assert e_ours < 1.25 * e_torch + 1e-3
     assert e_ours < 2e-2
+
+
+def _full_geometry_case(cfg_over, B, Fr, H, W, *, controls=False, rope=False, ofs=None, views=1, n_actions=16):
+    """Runs the CUDA forward and the fp32 oracle (on the GPU, fp32 matmuls) at a BASELINE.json geometry with a reduced
+    layer count; returns (rel err ours, rel err torch-bf16) against the fp32 oracle."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = O.default_config(**cfg_over)
+    sd = O.synthetic_state_dict(cfg, seed=0, std=0.02)
+    inp = O.synthetic_inputs(cfg, B, Fr * views, H, W, seed=1, with_controls=controls, n_actions=n_actions)
+    t = torch.full((B,), 499)
+    rp = O.pipeline_rope(cfg, H * 8, W * 8, Fr) if rope else None
+    ofs_t = torch.tensor([ofs]) if ofs is not None else None
+    kw32, kwb = {}, {}
+    for k in ("actions", "depths", "labels"):
+        if k in inp and (controls or k == "actions"):
+            kw32[k] = inp[k].bfloat16().float().cuda()
+            kwb[k] = inp[k].cuda().bfloat16()
+    with torch.no_grad(), torch.device("cuda"):
+        sdr = {k: v.bfloat16().float().cuda() for k, v in sd.items()}
+        rope_c = (rp[0].cuda(), rp[1].cuda()) if rp else None
+        ref = O.forward(sdr, cfg, inp["hidden_states"].bfloat16().float().cuda(), inp["text"].bfloat16().float().cuda(),
+                        t.cuda(), ofs=ofs_t.cuda() if ofs_t is not None else None, rope=rope_c, num_views=views, **kw32)
+        del sdr
+        sdb = {k: v.cuda().bfloat16() for k, v in sd.items()}
+        tb = O.forward(sdb, cfg, inp["hidden_states"].cuda().bfloat16(), inp["text"].cuda().bfloat16(), t.cuda(),
+                       ofs=ofs_t.cuda() if ofs_t is not None else None, rope=rope_c, num_views=views, **kwb)
+        del sdb
+    m = _model(cfg, sd)
+    with torch.no_grad():
+        out = m(inp["hidden_states"].cuda().bfloat16(), inp["text"].cuda().bfloat16(), kwb, t.cuda(),
+                ofs=ofs_t.cuda() if ofs_t is not None else None, image_rotary_emb=rope_c, return_dict=False,
+                num_views=views)[0]
+    torch.cuda.synchronize()
+    assert out.shape == ref.shape and torch.isfinite(out.float()).all()
+    return _rel(out, ref), _rel(tb, ref)
+
+
+def test_full_size_config3_controls():
+    """BASELINE config 3: 2B dims + depth/label condition latents, S = 3226, 2 layers."""
+    e, eb = _full_geometry_case(dict(num_attention_heads=30, attention_head_dim=64, in_channels=32, out_channels=16,
+                                     num_layers=2, sample_width=60, sample_height=40, sample_frames=17,
+                                     modulate_encoder_hidden_states=True, text_embed_dim=4096, max_text_seq_length=226,
+                                     visual_guidance=True, num_control_blocks=2), 1, 5, 40, 60, controls=True)
+    print(f"config 3 geometry: ours {e:.3e} torch-bf16 {eb:.3e}")
+    assert e < 1.25 * eb + 1e-3 and e < 2e-2
+
+
+def test_full_size_config4_5b_cfg_pair():
+    """BASELINE config 4: CogVideoX1.5-5B dims (D=3072, 48 heads, FF 12288, p_t=2, RoPE, ofs), batch 2 (CFG pair),
+    6 latent frames -> S = 226 + 1800, 2 layers."""
+    e, eb = _full_geometry_case(dict(num_attention_heads=48, attention_head_dim=64, in_channels=32, out_channels=16,
+                                     num_layers=2, sample_width=60, sample_height=40, sample_frames=21,
+                                     modulate_encoder_hidden_states=True, text_embed_dim=4096, max_text_seq_length=226,
+                                     patch_size_t=2, use_rotary_positional_embeddings=True, ofs_embed_dim=512,
+                                     patch_bias=False), 2, 6, 40, 60, rope=True, ofs=2.0, n_actions=20)
+    print(f"config 4 geometry: ours {e:.3e} torch-bf16 {eb:.3e}")
+    assert e < 1.25 * eb + 1e-3 and e < 2e-2
+
+
+def test_full_size_config5_multiview():
+    """BASELINE config 5: 2B multiview, 3 views x 5 latent frames of 32x48 latents (S_v = 1920 per view) + conditions,
+    2 temporal + 2 multiview blocks."""
+    e, eb = _full_geometry_case(dict(num_attention_heads=30, attention_head_dim=64, in_channels=32, out_channels=16,
+                                     num_layers=2, sample_width=48, sample_height=32, sample_frames=17,
+                                     modulate_encoder_hidden_states=True, text_embed_dim=4096, max_text_seq_length=226,
+                                     visual_guidance=True, num_control_blocks=2, multiview=True, max_n_view=3),
+                                1, 5, 32, 48, controls=True, views=3)
+    print(f"config 5 geometry: ours {e:.3e} torch-bf16 {eb:.3e}")
+    assert e < 1.25 * eb + 1e-3 and e < 2e-2

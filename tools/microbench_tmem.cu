@@ -26,6 +26,11 @@ __global__ void __launch_bounds__(512, 1) k_tmem(int iters, int nwarps, int mode
 #pragma unroll
         for (int i = 0; i < 32; ++i) x ^= r0[i] ^ r1[i];
         acc += __uint_as_float(x);
+      } else if (mode == 2) {   // 64 ex2 per thread as 32 x ex2.approx.f16x2 (compiles to 2 MUFU.EX2.F16 + PRMT each)
+        uint32_t x = __float_as_uint(acc) | 0x3c003c00u;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { uint32_t y; asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x + i)); x ^= y; }
+        acc += __uint_as_float(x);
       } else if (mode == 1) {   // 64 ex2 per thread
         float x = acc;
 #pragma unroll
@@ -107,13 +112,14 @@ int main() {
   long long* out; float* sink;
   cudaMalloc(&out, 1024 * 8); cudaMalloc(&sink, 4);
   const int iters = 2000;
-  for (int mode = 0; mode < 2; ++mode)
+  for (int mode = 0; mode < 3; ++mode)
     for (int nw : {1, 4, 8, 16}) {
       k_tmem<<<148, 512>>>(iters, nw, mode, out, sink);
       cudaError_t e = cudaDeviceSynchronize();
       long long h; cudaMemcpy(&h, out, 8, cudaMemcpyDeviceToHost);
       const double per_it = double(h) / iters;
       if (mode == 0) printf("tcgen05.ld 2 x (32 lanes x 32 cols): %2d warps: %.1f clk/iter/warp -> %.1f B/clk/SM  (%s)\n", nw, per_it, nw * 8192.0 / per_it, cudaGetErrorString(e));
+      else if (mode == 2) printf("ex2.f16x2 x32 (=64 values)/thread: %2d warps: %.1f clk/iter -> %.2f ex2/clk/SM  (%s)\n", nw, per_it, nw * 64 * 32.0 / per_it, cudaGetErrorString(e));
       else printf("ex2 x64/thread: %2d warps: %.1f clk/iter -> %.2f ex2/clk/SM  (%s)\n", nw, per_it, nw * 64 * 32.0 / per_it, cudaGetErrorString(e));
     }
   run_ldn<8, 8>(out, sink);
