@@ -211,6 +211,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttDev p) {
 
   if ((smem_u32(smem) & 1023u) != 0) __trap();
 
+  pdl_launch_dependents();
   if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&tma_qkv);
     mbar_init(q_full, 1);
@@ -235,6 +236,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttDev p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // the QKV GEMM's output is visible from here on (prologue above overlapped its tail)
 
   if (warp == 16) {
     // ======================================= TMA producer =======================================
@@ -353,8 +355,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttDev p) {
       const int valid = p.seq_len - (j * ATT_BK + stream * 64);  // my columns >= valid are padding
       uint8_t* p_row = p_row0 + (j & 1) * 2 * A4_TILE;
       uint32_t r0[32], r1[32];
-      tmem_ld_32x32b_x32(my_s, r0);
-      tmem_ld_32x32b_x32(my_s + 32u, r1);
+      tmem_ld_32x32b_x16(my_s, r0);
+      tmem_ld_32x32b_x16(my_s + 16u, r0 + 16);
+      tmem_ld_32x32b_x16(my_s + 32u, r1);
+      tmem_ld_32x32b_x16(my_s + 48u, r1 + 16);
       tmem_ld_wait();
       tc_fence_before();  // our reads of S_t are ordered before the QK^T that overwrites it
       mbar_arrive(my_s_free);
@@ -470,8 +474,7 @@ static int launch_attention_v4(const CUtensorMap& tm, const AttDev& p, dim3 grid
     ORVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A4_SMEM_BYTES));
     attr_set = true;
   }
-  kern<<<grid, DUAL ? 608 : 576, A4_SMEM_BYTES, stream>>>(tm, p);
-  ORVB_CHECK_CUDA(cudaGetLastError());
+  ORVB_CHECK_CUDA(launch_kernel(kern, grid, dim3(DUAL ? 608 : 576), A4_SMEM_BYTES, stream, true, tm, p));
   return ORVB_OK;
 }
 

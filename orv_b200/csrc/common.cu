@@ -1,6 +1,7 @@
 #include "common.cuh"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace orvb {
@@ -93,6 +94,15 @@ int check_arch() {
   ORVB_REQUIRE(g_cc_major == 10, ORVB_EARCH,
                "liborv_b200 needs a compute-capability 10.x device (B200, sm_100a); found major=%d", g_cc_major);
   return ORVB_OK;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ORVB_PDL");
+    v = (e != nullptr) ? atoi(e) : 1;
+  }
+  return v != 0;
 }
 
 int sm_count() {

@@ -412,6 +412,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   const int num_k = (p.K + BK - 1) / BK;
   const int half_bn = bn >> 1;
 
+  pdl_launch_dependents();  // the next kernel's CTAs may be scheduled (and run their prologue) as SMs free up
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
@@ -436,6 +437,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   cluster_sync_all();  // barriers of BOTH CTAs initialised before any remote arrive / TMA credit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
 
   if (warp == 0) {
     // ================================ TMA producer (both CTAs) ================================
@@ -606,8 +608,7 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int clusters = sm_count() / 2;
   const int grid = 2 * (tiles < clusters ? tiles : clusters);
-  kern<<<grid, GEMM_THREADS, G2_SMEM_BYTES, stream>>>(ta, tb, to, p, bn);
-  ORVB_CHECK_CUDA(cudaGetLastError());
+  ORVB_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(GEMM_THREADS), G2_SMEM_BYTES, stream, true, ta, tb, to, p, bn));
   return ORVB_OK;
 }
 

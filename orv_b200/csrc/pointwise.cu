@@ -212,6 +212,8 @@ __global__ void __launch_bounds__(256, 4) ln_ab_kernel(const LnDev p) {
   const bf16* ap1 = p.ab + static_cast<size_t>(g1) * p.ab_ld + (t1 ? 0 : 2 * p.dim);
   const int row = row0 + warp;
   const bool live = row < p.rows;
+  pdl_launch_dependents();
+  pdl_wait();  // x comes from the previous kernel
   // this warp's row first (longest latency), then the cooperative table copy
   uint4 xr[MAXC];
   if (live) {
@@ -327,10 +329,9 @@ int ln_modulate_launch(const orvb_ln_args* a, cudaStream_t stream) {
   if (d.ab != nullptr && d.pre_w == nullptr && !d.in_video_only && d.rm.seq_len > 0 && d.rm.text_len >= 8 &&
       (d.rm.tokens_per_group <= 0 || d.rm.tokens_per_group >= 8) && d.rm.seq_len - d.rm.text_len >= 8) {
     const int smem = 2 * 2 * nchunks * 16;
-    if (nchunks <= 32 * 8) ln_ab_kernel<8><<<grid, 256, smem, stream>>>(d);
-    else if (nchunks <= 32 * 12) ln_ab_kernel<12><<<grid, 256, smem, stream>>>(d);
-    else ln_ab_kernel<16><<<grid, 256, smem, stream>>>(d);
-    ORVB_CHECK_CUDA(cudaGetLastError());
+    if (nchunks <= 32 * 8) ORVB_CHECK_CUDA(launch_kernel(ln_ab_kernel<8>, grid, dim3(256), smem, stream, true, d));
+    else if (nchunks <= 32 * 12) ORVB_CHECK_CUDA(launch_kernel(ln_ab_kernel<12>, grid, dim3(256), smem, stream, true, d));
+    else ORVB_CHECK_CUDA(launch_kernel(ln_ab_kernel<16>, grid, dim3(256), smem, stream, true, d));
     return ORVB_OK;
   }
   if (nchunks <= 32 * 8) ln_modulate_kernel<8><<<grid, 256, 0, stream>>>(d);
