@@ -387,8 +387,17 @@ constexpr int G2_OUT_STAGE_BYTES = 4 * 2 * 32 * 128;  // per epilogue warp: two 
 constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + G2_OUT_STAGE_BYTES + 1024 + 256;
 constexpr int G2_ACC_COLS = 256;                  // TMEM columns per accumulator buffer (2 buffers = 512)
 
+// Epilogue warps per CTA.  The light epilogues (bias, gated residual) run eight: warps e and e + 4 share a TMEM lane
+// quarter and take alternate 64-column units, which halves the epilogue of the LAST tile of a cluster — the only one
+// that is not hidden behind a mainloop (the attn-out and FF2 GEMMs have just two tiles per cluster).  The register-
+// heavy ones (GELU, QKV LayerNorm) stay at four.
+__host__ __device__ constexpr int g2_epi_warps(int epi) {
+  return (epi == ORVB_EPI_BIAS || epi == ORVB_EPI_GATE_RESID) ? 8 : 4;
+}
+__host__ __device__ constexpr int g2_threads(int epi) { return (4 + g2_epi_warps(epi)) * 32; }
+
 template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2_threads(EPI), 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                   const __grid_constant__ CUtensorMap tma_o, const GemmDev p, const int bn) {
   constexpr int STAGES = G2_STAGES;
@@ -425,7 +434,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);   // multicast tcgen05.commit
-      mbar_init(&tempty_bar[i], 8);  // 4 epilogue warps x 2 CTAs (leader's copy is the one waited on)
+      mbar_init(&tempty_bar[i], 2 * g2_epi_warps(EPI));  // epilogue warps x 2 CTAs (leader's copy is waited on)
     }
     fence_barrier_init();
   }
@@ -505,11 +514,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     }
   } else if (warp >= 4) {
     // ================================ epilogue (both CTAs) ====================================
-    const int ew = warp - 4;
+    constexpr int EW = g2_epi_warps(EPI);
+    constexpr int NBUF = 8 / EW;             // staging tiles per warp: 32 KB split over the epilogue warps
+    const int ew = (warp - 4) & 3;           // == warp % 4: TMEM lane quarter this warp may access
+    const int unit_par = (warp - 4) >> 2;    // with 8 warps: which of the alternating 64-column units are mine
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t stores = 0;  // TMA stores issued by this warp (staging buffer = stores & 1)
-    uint8_t* my_stage = out_stage + ew * (2 * 32 * 128);
+    uint32_t stores = 0;  // TMA stores issued by this warp (staging buffer = stores % NBUF)
+    uint8_t* my_stage = out_stage + (warp - 4) * (NBUF * 32 * 128);
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m_blk = tile % p.num_m_tiles;
       const int n_blk = tile / p.num_m_tiles;
@@ -522,6 +534,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       for (int c = 0; c < bn; c += 64) {
         const int n0 = n_blk * bn + c;
         if (n0 >= p.N || row0 >= p.M) break;  // warp-uniform
+        if (EW == 8 && ((c >> 6) & 1) != unit_par) continue;
         uint32_t r0[32], r1[32];
         tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c), r0);
         tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c + 32), r1);  // may run past bn: still inside the buffer
@@ -530,9 +543,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         // clipped by the tensor map); the narrower last unit of a tile whose width is not a multiple of 64 must not
         // touch its neighbour's columns and is stored directly.
         const bool staged = p.tma_store && (bn - c >= 64);
-        uint8_t* sbuf = my_stage + (stores & 1u) * (32 * 128);
-        if (staged && stores >= 2) {
-          if (lane == 0) bulk_wait_group_read<1>();  // the store that last used this buffer has read it
+        uint8_t* sbuf = my_stage + (stores % NBUF) * (32 * 128);
+        if (staged && stores >= NBUF) {
+          if (lane == 0) bulk_wait_group_read<NBUF - 1>();  // the store that last used this buffer has read it
           __syncwarp();
         }
         if (row < p.M) {
@@ -608,7 +621,7 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int clusters = sm_count() / 2;
   const int grid = 2 * (tiles < clusters ? tiles : clusters);
-  ORVB_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(GEMM_THREADS), G2_SMEM_BYTES, stream, true, ta, tb, to, p, bn));
+  ORVB_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(g2_threads(EPI)), G2_SMEM_BYTES, stream, true, ta, tb, to, p, bn));
   return ORVB_OK;
 }
 
