@@ -384,28 +384,45 @@ __global__ void __launch_bounds__(256) skinny_linear_kernel(const float* __restr
 #pragma unroll
     for (int r = 0; r < SK_ROWS; ++r) acc[c][r] = pk2(0.f, 0.f);
 
-#pragma unroll 2
-  for (int k0 = q * 8; k0 < k; k0 += 32) {
-    f32x2 w[SK_QCOLS][4];
+  // Weight loads are issued U steps ahead of their use (explicitly: the row-count branches below keep the compiler
+  // from hoisting them).  The small launches (one weight row per quad, a handful of CTAs) are pure load-latency
+  // chains and take U = 8; the batched launch has 4 rows per quad in flight already (U = 1, loop unrolled twice: more
+  look-ahead costs registers, i.e. the second resident CTA, and measured slower).
+  constexpr int U = (SK_QCOLS == 1) ? 8 : 1;
+#pragma unroll(U == 1 ? 2 : 1)
+  for (int kb = q * 8; kb < k; kb += 32 * U) {
+    uint4 wq[U][SK_QCOLS];
 #pragma unroll
-    for (int c = 0; c < SK_QCOLS; ++c) {
-      const uint4 wq = *reinterpret_cast<const uint4*>(wrow[c] + k0);
-      w[c][0] = pk2(bf16_lo(wq.x), bf16_hi(wq.x));
-      w[c][1] = pk2(bf16_lo(wq.y), bf16_hi(wq.y));
-      w[c][2] = pk2(bf16_lo(wq.z), bf16_hi(wq.z));
-      w[c][3] = pk2(bf16_lo(wq.w), bf16_hi(wq.w));
-    }
+    for (int u = 0; u < U; ++u)
+      if (kb + 32 * u < k) {
 #pragma unroll
-    for (int r = 0; r < SK_ROWS; ++r) {
-      if (r < nr) {
-        const ulonglong2 xa = *reinterpret_cast<const ulonglong2*>(sx + r * k + k0);
-        const ulonglong2 xb = *reinterpret_cast<const ulonglong2*>(sx + r * k + k0 + 4);
+        for (int c = 0; c < SK_QCOLS; ++c) wq[u][c] = *reinterpret_cast<const uint4*>(wrow[c] + kb + 32 * u);
+      }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int k0 = kb + 32 * u;
+      if (k0 < k) {
+        f32x2 w[SK_QCOLS][4];
 #pragma unroll
         for (int c = 0; c < SK_QCOLS; ++c) {
-          acc[c][r] = fma2p(xa.x, w[c][0], acc[c][r]);
-          acc[c][r] = fma2p(xa.y, w[c][1], acc[c][r]);
-          acc[c][r] = fma2p(xb.x, w[c][2], acc[c][r]);
-          acc[c][r] = fma2p(xb.y, w[c][3], acc[c][r]);
+          w[c][0] = pk2(bf16_lo(wq[u][c].x), bf16_hi(wq[u][c].x));
+          w[c][1] = pk2(bf16_lo(wq[u][c].y), bf16_hi(wq[u][c].y));
+          w[c][2] = pk2(bf16_lo(wq[u][c].z), bf16_hi(wq[u][c].z));
+          w[c][3] = pk2(bf16_lo(wq[u][c].w), bf16_hi(wq[u][c].w));
+        }
+#pragma unroll
+        for (int r = 0; r < SK_ROWS; ++r) {
+          if (r < nr) {
+            const ulonglong2 xa = *reinterpret_cast<const ulonglong2*>(sx + r * k + k0);
+            const ulonglong2 xb = *reinterpret_cast<const ulonglong2*>(sx + r * k + k0 + 4);
+#pragma unroll
+            for (int c = 0; c < SK_QCOLS; ++c) {
+              acc[c][r] = fma2p(xa.x, w[c][0], acc[c][r]);
+              acc[c][r] = fma2p(xa.y, w[c][1], acc[c][r]);
+              acc[c][r] = fma2p(xb.x, w[c][2], acc[c][r]);
+              acc[c][r] = fma2p(xb.y, w[c][3], acc[c][r]);
+            }
+          }
         }
       }
     }

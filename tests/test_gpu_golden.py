@@ -224,3 +224,33 @@ def test_full_size_config5_multiview():
                                 1, 5, 32, 48, controls=True, views=3)
     print(f"config 5 geometry: ours {e:.3e} torch-bf16 {eb:.3e}")
     assert e < 1.25 * eb + 1e-3 and e < 2e-2
+
+
+def test_full_size_config1_ddim_two_steps_pipeline():
+    """BASELINE config 1 (plumbing): the full CogVideoX-2B geometry, 1 clip 17x320x480, 2 DDIM-trailing steps through
+    the public pipeline on the GPU against the CPU oracle's pipeline run in bf16 with the same CPU generator (identical
+    RNG stream, so the only difference is bf16 forward noise)."""
+    from orv_b200 import CogVideoXDDIMScheduler, CogVideoXImageToVideoPipelineTraj
+    from orv_b200.models.pipeline_control import default_vae_config
+    cfg = O.default_config(num_attention_heads=30, attention_head_dim=64, in_channels=32, out_channels=16, num_layers=30,
+                           sample_width=60, sample_height=40, sample_frames=17, modulate_encoder_hidden_states=True,
+                           text_embed_dim=4096, max_text_seq_length=226)
+    sd = O.synthetic_state_dict(cfg, seed=0, std=0.02)
+    m = _model(cfg, sd)
+    pipe = CogVideoXImageToVideoPipelineTraj(None, None, default_vae_config(), m,
+                                             CogVideoXDDIMScheduler(timestep_spacing="trailing"))
+    inp = O.synthetic_inputs(cfg, 1, 5, 40, 60, seed=1)
+    moments = torch.randn(1, 32, 1, 40, 60, generator=torch.Generator().manual_seed(7)).bfloat16()
+    out = pipe(image=moments, prompt="", prompt_embeds=inp["text"].cuda().bfloat16(), height=320, width=480,
+               num_frames=17, num_inference_steps=2, guidance_scale=1.0, generator=torch.Generator().manual_seed(42),
+               controls_or_guidances={"actions": inp["actions"]}, output_type="latent", return_dict=False)[0]
+    sdb = {k: v.bfloat16() for k, v in sd.items()}
+    del sd
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    with torch.no_grad():
+        ref = O.pipeline_call(sdb, cfg, "ddim", moments, inp["text"].bfloat16(), 17, 320, 480, 2, 1.0,
+                              torch.Generator().manual_seed(42), actions=inp["actions"].bfloat16())
+    assert out.shape == ref.shape == (1, 5, 16, 40, 60) and out.dtype == torch.bfloat16
+    e = _rel(out, ref)
+    print(f"config 1 (2 DDIM steps, 30 layers): rel diff vs CPU bf16 oracle pipeline {e:.3e}")
+    assert e < 3e-2
