@@ -261,9 +261,29 @@ typedef struct orvb_forward_args {
   void* workspace; size_t workspace_bytes;
   /* optional taps for parity tests (bf16 [batch*seq, dim] joint hidden state after block `tap_layer`) */
   void* tap_hidden; int32_t tap_layer;
+  /* 1: the AdaLN tables of this step were installed into `workspace` by orvb_modulation_select; the time / action
+   * embeddings and the table build (timesteps, ofs, actions, action_mask) are skipped. */
+  int32_t skip_modulation;
 } orvb_forward_args;
 
 int orvb_forward(orvb_model* m, const orvb_forward_args* a, void* stream);
+
+/* Modulation schedule.  Every AdaLN shift / scale / gate of the model depends on (timestep, ofs, actions) only —
+ * never on the latents — yet the reference recomputes them inside each of the 50 forwards of a clip
+ * (cogvideox_control.py:117-130, :166-170 through :762-779), re-reading 0.7 GB of AdaLN weights per step.  With the
+ * timesteps of the sampler known up front the tables of ALL steps are built once per clip:
+ *   orvb_modulation_schedule: timesteps fp32 [steps * batch] (step-major), actions bf16 [steps * batch, ...] and
+ *                             action_mask u8 [steps * batch] laid out the same way (NULL as in orvb_forward);
+ *                             `tables` = caller buffer of orvb_modulation_bytes() bytes, 256-byte aligned
+ *   orvb_modulation_select:   copies step `step`'s tables into the forward workspace (two strided device copies);
+ *                             the following orvb_forward on that workspace is called with skip_modulation = 1.
+ * Same kernels, same arithmetic as the per-step path: results are bit-identical. */
+size_t orvb_modulation_bytes(const orvb_model* m, const orvb_shape* shape, int32_t steps);
+int orvb_modulation_schedule(orvb_model* m, const orvb_shape* shape, int32_t steps, const float* timesteps, float ofs,
+                             const void* actions, const uint8_t* action_mask, void* tables, size_t tables_bytes,
+                             void* stream);
+int orvb_modulation_select(const orvb_model* m, const orvb_shape* shape, int32_t steps, int32_t step,
+                           const void* tables, void* workspace, void* stream);
 
 /* Number of kernel launches orvb_forward enqueued in its most recent call on this model (for bench.py's
  * `gpu_launches`). */

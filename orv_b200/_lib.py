@@ -104,6 +104,7 @@ class ForwardArgs(C.Structure):
         ("rope_cos", c_void_p), ("rope_sin", c_void_p),
         ("out", c_void_p), ("workspace", c_void_p), ("workspace_bytes", C.c_size_t),
         ("tap_hidden", c_void_p), ("tap_layer", c_int),
+        ("skip_modulation", c_int),
     ]
 
 
@@ -124,6 +125,7 @@ EXPORTED_SYMBOLS = [
     "orvb_patchify", "orvb_unpatchify",
     "orvb_model_create", "orvb_model_destroy", "orvb_model_bind_weights", "orvb_workspace_bytes",
     "orvb_forward", "orvb_last_launch_count", "orvb_model_set_profile", "orvb_model_get_profile",
+    "orvb_modulation_bytes", "orvb_modulation_schedule", "orvb_modulation_select",
     "orvb_sampler_step",
 ]
 

@@ -28,10 +28,12 @@ struct orvb_model {
   std::vector<orvb_block_weights> blocks;
   std::vector<orvb_block_weights> mv_blocks;
   bool bound = false;
-  orvb::SkinnyJob* jobs_dev = nullptr;  // [sites] AdaLN job table (device metadata owned by the library)
-  orvb::AbSite* ab_sites_dev = nullptr; // [sites] LayerNorm A/B-table build descriptors
-  float* jobs_y_base = nullptr;         // modulation-table base the job table currently points at
-  size_t jobs_site_stride = 0;
+  // Device metadata owned by the library, one set per user of build_modulation (0: the forward's own workspace,
+  // 1: a modulation schedule buffer) so that alternating between the two never rewrites a table a queued kernel reads.
+  orvb::SkinnyJob* jobs_dev_[2] = {nullptr, nullptr};  // [sites] AdaLN job table
+  orvb::AbSite* ab_sites_dev_[2] = {nullptr, nullptr}; // [sites] LayerNorm A/B-table build descriptors
+  float* jobs_y_base_[2] = {nullptr, nullptr};         // modulation-table base the job table currently points at
+  size_t jobs_site_stride_[2] = {0, 0};
   int launches = 0;
   // optional per-kernel-class timing (orvb_model_set_profile): CUDA events around every launch
   bool profile = false;
@@ -83,6 +85,29 @@ struct Workspace {
   size_t bytes;
 };
 
+// Scratch + tables of the modulation prologue (sections 1-2 of the forward) for g.B samples.  Also carved on its own
+// for a whole schedule of timesteps (orvb_modulation_schedule: g.B = steps x batch virtual samples).
+template <typename Take>
+static void carve_modulation(const orvb_config& c, const Geometry& g, Take&& take, Workspace* ws) {
+  const size_t D = g.D;
+  ws->tsin = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * D * 4));
+  ws->t1 = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * g.T * 4));
+  ws->temb = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * g.T * 4));
+  const int od = c.has_ofs ? c.ofs_embed_dim : 8;
+  ws->osin = reinterpret_cast<float*>(take(static_cast<size_t>(od) * 4));
+  ws->o1 = reinterpret_cast<float*>(take(static_cast<size_t>(g.T) * 4));
+  ws->oemb = reinterpret_cast<float*>(take(static_cast<size_t>(g.T) * 4));
+  const int pt = c.patch_size_t > 0 ? c.patch_size_t : 1;
+  const int act_k = c.action_state_dim * c.action_compress * pt;
+  const int fa = g.Fa > 0 ? g.Fa : 1;
+  ws->act_in = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * fa * align_up(act_k, 8) * 4));
+  ws->act_h = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * fa * c.action_hidden * 4));
+  ws->act_emb = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * fa * g.T * 4));
+  ws->emb = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * g.G * g.T * 4));
+  ws->mod = reinterpret_cast<float*>(take(static_cast<size_t>(g.sites) * g.B * g.G * 6 * D * 4));
+  ws->ab = reinterpret_cast<bf16*>(take(static_cast<size_t>(g.sites) * g.B * g.G * 4 * D * 2));
+}
+
 static void carve(const orvb_config& c, const Geometry& g, uint8_t* base, Workspace* ws) {
   size_t off = 0;
   auto take = [&](size_t n) {
@@ -108,22 +133,7 @@ static void carve(const orvb_config& c, const Geometry& g, uint8_t* base, Worksp
     ws->att_mv = reinterpret_cast<bf16*>(take(mv * (g.B / g.V) * g.Fp * g.V * tok * D * 2));
     ws->tmp_mv = reinterpret_cast<bf16*>(take(mv * (g.B / g.V) * g.Fp * g.V * tok * D * 2));
   }
-  ws->tsin = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * D * 4));
-  ws->t1 = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * g.T * 4));
-  ws->temb = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * g.T * 4));
-  const int od = c.has_ofs ? c.ofs_embed_dim : 8;
-  ws->osin = reinterpret_cast<float*>(take(static_cast<size_t>(od) * 4));
-  ws->o1 = reinterpret_cast<float*>(take(static_cast<size_t>(g.T) * 4));
-  ws->oemb = reinterpret_cast<float*>(take(static_cast<size_t>(g.T) * 4));
-  const int pt = c.patch_size_t > 0 ? c.patch_size_t : 1;
-  const int act_k = c.action_state_dim * c.action_compress * pt;
-  const int fa = g.Fa > 0 ? g.Fa : 1;
-  ws->act_in = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * fa * align_up(act_k, 8) * 4));
-  ws->act_h = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * fa * c.action_hidden * 4));
-  ws->act_emb = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * fa * g.T * 4));
-  ws->emb = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * g.G * g.T * 4));
-  ws->mod = reinterpret_cast<float*>(take(static_cast<size_t>(g.sites) * g.B * g.G * 6 * D * 4));
-  ws->ab = reinterpret_cast<bf16*>(take(static_cast<size_t>(g.sites) * g.B * g.G * 4 * D * 2));
+  carve_modulation(c, g, take, ws);
   ws->bytes = off;
 }
 
@@ -236,31 +246,28 @@ static orvb_gemm_args gemm_base(const void* a, const void* w, const void* bias, 
   return g;
 }
 
-static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t st) {
+struct ModIn {
+  const float* timesteps;
+  float ofs;
+  const void* actions;
+  const uint8_t* action_mask;
+};
+
+// Sections 1-2 of the forward: time / ofs / action embeddings -> per-group conditioning rows -> every AdaLN table of
+// the model (fp32 `mod`) and their folded LayerNorm form (bf16 `ab`), for g.B samples.  They depend on the timestep,
+// ofs and the actions only, never on the latents.
+static int build_modulation(orvb_model* m, const Geometry& g, const ModIn& in, const Workspace& ws, int slot,
+                            cudaStream_t st) {
+  SkinnyJob*& jobs_dev = m->jobs_dev_[slot];
+  AbSite*& ab_sites_dev = m->ab_sites_dev_[slot];
+  float*& jobs_y_base = m->jobs_y_base_[slot];
+  size_t& jobs_site_stride = m->jobs_site_stride_[slot];
   const orvb_config& c = m->cfg;
   const orvb_weights& w = m->w;
-  Geometry g;
-  int rc = make_geometry(c, a->shape, &g);
-  if (rc != ORVB_OK) return rc;
-  ORVB_REQUIRE(a->hidden_states && a->text && a->timesteps && a->out && a->workspace, ORVB_EINVAL,
-               "orvb_forward: null input/output/workspace pointer");
-  Workspace ws;
-  carve(c, g, static_cast<uint8_t*>(a->workspace), &ws);
-  ORVB_REQUIRE(a->workspace_bytes >= ws.bytes, ORVB_ENOMEM, "orvb_forward: workspace too small (%zu < %zu)",
-               a->workspace_bytes, ws.bytes);
-  ORVB_REQUIRE(reinterpret_cast<uintptr_t>(a->workspace) % 256 == 0, ORVB_ESHAPE,
-               "orvb_forward: workspace must be 256-byte aligned");
-  ORVB_REQUIRE(!c.use_rope || (a->rope_cos && a->rope_sin), ORVB_EINVAL,
-               "orvb_forward: this model uses rotary embeddings but rope_cos/rope_sin are NULL");
-  ORVB_REQUIRE((g.Fa > 0) == (a->actions != nullptr), ORVB_EINVAL,
-               "orvb_forward: shape.action_frames and the actions pointer disagree");
   const int D = g.D, T = g.T;
   const int pt = c.patch_size_t > 0 ? c.patch_size_t : 1;
-  m->launches = 0;
-  m->ev_used = 0;
-  m->ev_cls.clear();
+  const ModIn* a = &in;
   ORVB_CLS(ORVB_PC_PROLOGUE);
-
   // ---- 1. time / ofs / action embeddings -> per-group conditioning rows -----------------------------
   {
     const int n = g.B * (D / 2);
@@ -313,7 +320,7 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
 
   // ---- 2. all AdaLN tables of the forward in one batched launch (they depend only on emb) ----------
   const size_t site_stride = static_cast<size_t>(g.B) * g.G * 6 * D;
-  if (m->jobs_y_base != ws.mod || m->jobs_site_stride != site_stride) {
+  if (jobs_y_base != ws.mod || jobs_site_stride != site_stride) {
     const int n_jobs = 2 * c.layers + (c.multiview ? c.layers : 0);
     std::vector<SkinnyJob> jobs(n_jobs);
     for (int l = 0; l < c.layers; ++l) {
@@ -324,7 +331,7 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
                                   ws.mod + (2 * l + 1) * site_stride};
     }
     // synchronous small copy: happens once per (model, workspace) pair, outside any graph capture
-    ORVB_CHECK_CUDA(cudaMemcpy(m->jobs_dev, jobs.data(), jobs.size() * sizeof(SkinnyJob), cudaMemcpyHostToDevice));
+    ORVB_CHECK_CUDA(cudaMemcpy(jobs_dev, jobs.data(), jobs.size() * sizeof(SkinnyJob), cudaMemcpyHostToDevice));
     const size_t ab_stride = static_cast<size_t>(g.B) * g.G * 4 * D;
     std::vector<AbSite> sites(g.sites);
     for (int l = 0; l < c.layers; ++l) {
@@ -348,13 +355,13 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
         sites[site] = AbSite{static_cast<const bf16*>(mw.norm1_ln_w), static_cast<const bf16*>(mw.norm1_ln_b),
                              ws.mod + site * site_stride, 6 * D, 3 * D, 0, ws.ab + site * ab_stride};
       }
-      ORVB_CHECK_CUDA(cudaMemcpy(m->jobs_dev, jobs.data(), jobs.size() * sizeof(SkinnyJob), cudaMemcpyHostToDevice));
+      ORVB_CHECK_CUDA(cudaMemcpy(jobs_dev, jobs.data(), jobs.size() * sizeof(SkinnyJob), cudaMemcpyHostToDevice));
     }
-    ORVB_CHECK_CUDA(cudaMemcpy(m->ab_sites_dev, sites.data(), sites.size() * sizeof(AbSite), cudaMemcpyHostToDevice));
-    m->jobs_y_base = ws.mod;
-    m->jobs_site_stride = site_stride;
+    ORVB_CHECK_CUDA(cudaMemcpy(ab_sites_dev, sites.data(), sites.size() * sizeof(AbSite), cudaMemcpyHostToDevice));
+    jobs_y_base = ws.mod;
+    jobs_site_stride = site_stride;
   }
-  ORVB_TRY(skinny_linear_launch(ws.emb, SkinnyJob{nullptr, nullptr, nullptr}, m->jobs_dev,
+  ORVB_TRY(skinny_linear_launch(ws.emb, SkinnyJob{nullptr, nullptr, nullptr}, jobs_dev,
                                 2 * c.layers + (c.multiview ? c.layers : 0), g.B * g.G, 6 * D, T, 0, st));
   float* mod_out = ws.mod + static_cast<size_t>(2 * c.layers) * site_stride;  // norm_out table, row pitch 2D
   {
@@ -363,7 +370,43 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
                                   nullptr, 1, g.B * g.G, 2 * D, T, 0, st));
   }
   // fold LayerNorm affine + (shift, scale) of every site into bf16 A/B tables for the LN kernels
-  ORVB_TRY(ab_combine_launch(m->ab_sites_dev, g.sites, g.B * g.G, D, st));
+  ORVB_TRY(ab_combine_launch(ab_sites_dev, g.sites, g.B * g.G, D, st));
+  return ORVB_OK;
+}
+
+static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t st) {
+  const orvb_config& c = m->cfg;
+  const orvb_weights& w = m->w;
+  Geometry g;
+  int rc = make_geometry(c, a->shape, &g);
+  if (rc != ORVB_OK) return rc;
+  ORVB_REQUIRE(a->hidden_states && a->text && a->timesteps && a->out && a->workspace, ORVB_EINVAL,
+               "orvb_forward: null input/output/workspace pointer");
+  Workspace ws;
+  carve(c, g, static_cast<uint8_t*>(a->workspace), &ws);
+  ORVB_REQUIRE(a->workspace_bytes >= ws.bytes, ORVB_ENOMEM, "orvb_forward: workspace too small (%zu < %zu)",
+               a->workspace_bytes, ws.bytes);
+  ORVB_REQUIRE(reinterpret_cast<uintptr_t>(a->workspace) % 256 == 0, ORVB_ESHAPE,
+               "orvb_forward: workspace must be 256-byte aligned");
+  ORVB_REQUIRE(!c.use_rope || (a->rope_cos && a->rope_sin), ORVB_EINVAL,
+               "orvb_forward: this model uses rotary embeddings but rope_cos/rope_sin are NULL");
+  ORVB_REQUIRE((g.Fa > 0) == (a->actions != nullptr), ORVB_EINVAL,
+               "orvb_forward: shape.action_frames and the actions pointer disagree");
+  const int D = g.D, T = g.T;
+  const int pt = c.patch_size_t > 0 ? c.patch_size_t : 1;
+  m->launches = 0;
+  m->ev_used = 0;
+  m->ev_cls.clear();
+  ORVB_CLS(ORVB_PC_PROLOGUE);
+
+  // ---- 1-2. modulation tables (skipped when the caller installed this step's slice of a schedule) ----
+  if (!a->skip_modulation) {
+    ModIn in;
+    in.timesteps = a->timesteps; in.ofs = a->ofs; in.actions = a->actions; in.action_mask = a->action_mask;
+    int mrc = build_modulation(m, g, in, ws, 0, st);
+    if (mrc != ORVB_OK) return mrc;
+  }
+  const size_t site_stride = static_cast<size_t>(g.B) * g.G * 6 * D;
   const size_t ab_stride = static_cast<size_t>(g.B) * g.G * 4 * D;
 
   orvb_rowmap rm;
@@ -552,18 +595,14 @@ extern "C" int orvb_model_create(const orvb_config* cfg, orvb_model** out) {
   if (rc != ORVB_OK) return rc;
   orvb_model* m = new orvb_model();
   m->cfg = *cfg;
-  cudaError_t e = cudaMalloc(&m->jobs_dev, sizeof(SkinnyJob) * 3 * cfg->layers);
-  if (e != cudaSuccess) {
-    delete m;
-    set_error("orvb_model_create: cudaMalloc(job table) failed: %s", cudaGetErrorString(e));
-    return ORVB_ECUDA;
-  }
-  e = cudaMalloc(&m->ab_sites_dev, sizeof(AbSite) * (3 * cfg->layers + 1));
-  if (e != cudaSuccess) {
-    cudaFree(m->jobs_dev);
-    delete m;
-    set_error("orvb_model_create: cudaMalloc(site table) failed: %s", cudaGetErrorString(e));
-    return ORVB_ECUDA;
+  for (int i = 0; i < 2; ++i) {
+    cudaError_t e = cudaMalloc(&m->jobs_dev_[i], sizeof(SkinnyJob) * 3 * cfg->layers);
+    if (e == cudaSuccess) e = cudaMalloc(&m->ab_sites_dev_[i], sizeof(AbSite) * (3 * cfg->layers + 1));
+    if (e != cudaSuccess) {
+      set_error("orvb_model_create: cudaMalloc(job / site table) failed: %s", cudaGetErrorString(e));
+      orvb_model_destroy(m);
+      return ORVB_ECUDA;
+    }
   }
   *out = m;
   return ORVB_OK;
@@ -571,8 +610,10 @@ extern "C" int orvb_model_create(const orvb_config* cfg, orvb_model** out) {
 
 extern "C" void orvb_model_destroy(orvb_model* m) {
   if (m == nullptr) return;
-  if (m->jobs_dev) cudaFree(m->jobs_dev);
-  if (m->ab_sites_dev) cudaFree(m->ab_sites_dev);
+  for (int i = 0; i < 2; ++i) {
+    if (m->jobs_dev_[i]) cudaFree(m->jobs_dev_[i]);
+    if (m->ab_sites_dev_[i]) cudaFree(m->ab_sites_dev_[i]);
+  }
   for (cudaEvent_t e : m->ev) cudaEventDestroy(e);
   delete m;
 }
@@ -602,7 +643,7 @@ extern "C" int orvb_model_bind_weights(orvb_model* m, const orvb_weights* w) {
   }
   m->w.blocks_host = nullptr;
   m->w.mv_blocks_host = nullptr;
-  m->jobs_y_base = nullptr;
+  m->jobs_y_base_[0] = m->jobs_y_base_[1] = nullptr;
   m->bound = true;
   return ORVB_OK;
 }
@@ -615,6 +656,84 @@ extern "C" size_t orvb_workspace_bytes(const orvb_model* m, const orvb_shape* s)
   Workspace ws;
   carve(m->cfg, g, nullptr, &ws);
   return ws.bytes;
+}
+
+// ---- modulation schedule: the AdaLN tables of many timesteps at once ------------------------------------------
+namespace orvb {
+// Buffer layout: the modulation scratch + tables of carve_modulation() for steps x batch virtual samples (step-major).
+static int schedule_layout(const orvb_model* m, const orvb_shape* s, int steps, uint8_t* base, Geometry* g1, Geometry* gv,
+                           Workspace* ws) {
+  ORVB_REQUIRE(m && s && steps > 0, ORVB_EINVAL, "orvb_modulation_*: bad arguments");
+  int rc = make_geometry(m->cfg, *s, g1);
+  if (rc != ORVB_OK) return rc;
+  *gv = *g1;
+  gv->B = g1->B * steps;
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    uint8_t* p = base ? base + off : nullptr;
+    off += align_up(n);
+    return p;
+  };
+  memset(ws, 0, sizeof(*ws));
+  carve_modulation(m->cfg, *gv, take, ws);
+  ws->bytes = off;
+  return ORVB_OK;
+}
+}  // namespace orvb
+
+extern "C" size_t orvb_modulation_bytes(const orvb_model* m, const orvb_shape* s, int32_t steps) {
+  using namespace orvb;
+  Geometry g1, gv;
+  Workspace ws;
+  if (schedule_layout(m, s, steps, nullptr, &g1, &gv, &ws) != ORVB_OK) return 0;
+  return ws.bytes;
+}
+
+extern "C" int orvb_modulation_schedule(orvb_model* m, const orvb_shape* s, int32_t steps, const float* timesteps,
+                                        float ofs, const void* actions, const uint8_t* action_mask, void* tables,
+                                        size_t tables_bytes, void* stream) {
+  using namespace orvb;
+  ORVB_REQUIRE(m && m->bound, ORVB_EINVAL, "orvb_modulation_schedule: weights are not bound");
+  int rc = check_arch();
+  if (rc != ORVB_OK) return rc;
+  ORVB_REQUIRE(timesteps && tables, ORVB_EINVAL, "orvb_modulation_schedule: null pointer");
+  ORVB_REQUIRE(reinterpret_cast<uintptr_t>(tables) % 256 == 0, ORVB_ESHAPE, "orvb_modulation_schedule: buffer must be 256-byte aligned");
+  Geometry g1, gv;
+  Workspace ws;
+  rc = schedule_layout(m, s, steps, static_cast<uint8_t*>(tables), &g1, &gv, &ws);
+  if (rc != ORVB_OK) return rc;
+  ORVB_REQUIRE(tables_bytes >= ws.bytes, ORVB_ENOMEM, "orvb_modulation_schedule: buffer too small (%zu < %zu)", tables_bytes, ws.bytes);
+  ORVB_REQUIRE((gv.Fa > 0) == (actions != nullptr), ORVB_EINVAL, "orvb_modulation_schedule: shape.action_frames and the actions pointer disagree");
+  m->launches = 0;
+  m->ev_used = 0;
+  m->ev_cls.clear();
+  ModIn in;
+  in.timesteps = timesteps; in.ofs = ofs; in.actions = actions; in.action_mask = action_mask;
+  return build_modulation(m, gv, in, ws, 1, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int orvb_modulation_select(const orvb_model* m, const orvb_shape* s, int32_t steps, int32_t step,
+                                      const void* tables, void* workspace, void* stream) {
+  using namespace orvb;
+  ORVB_REQUIRE(tables && workspace && step >= 0 && step < steps, ORVB_EINVAL, "orvb_modulation_select: bad arguments");
+  Geometry g1, gv;
+  Workspace src, dst;
+  int rc = schedule_layout(m, s, steps, const_cast<uint8_t*>(static_cast<const uint8_t*>(tables)), &g1, &gv, &src);
+  if (rc != ORVB_OK) return rc;
+  carve(m->cfg, g1, static_cast<uint8_t*>(workspace), &dst);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t rows1 = static_cast<size_t>(g1.B) * g1.G, rowsv = static_cast<size_t>(gv.B) * gv.G;
+  const size_t D = g1.D;
+  // every site: rows [step * B*G, (step+1) * B*G) of its [steps*B*G] row block, mod pitch 6D fp32 / ab pitch 4D bf16
+  ORVB_CHECK_CUDA(cudaMemcpy2DAsync(dst.mod, rows1 * 6 * D * 4, src.mod + static_cast<size_t>(step) * rows1 * 6 * D,
+                                    rowsv * 6 * D * 4, rows1 * 6 * D * 4, g1.sites, cudaMemcpyDeviceToDevice, st));
+  ORVB_CHECK_CUDA(cudaMemcpy2DAsync(dst.ab, rows1 * 4 * D * 2, src.ab + static_cast<size_t>(step) * rows1 * 4 * D,
+                                    rowsv * 4 * D * 2, rows1 * 4 * D * 2, g1.sites, cudaMemcpyDeviceToDevice, st));
+  // norm_out's table is packed with row pitch 2D inside its slot
+  const size_t so = static_cast<size_t>(2 * m->cfg.layers);
+  ORVB_CHECK_CUDA(cudaMemcpyAsync(dst.mod + so * rows1 * 6 * D, src.mod + so * rowsv * 6 * D + static_cast<size_t>(step) * rows1 * 2 * D,
+                                  rows1 * 2 * D * 4, cudaMemcpyDeviceToDevice, st));
+  return ORVB_OK;
 }
 
 extern "C" int orvb_forward(orvb_model* m, const orvb_forward_args* a, void* stream) {

@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(256) skinny_linear_kernel(const float* __restr
   // Weight loads are issued U steps ahead of their use (explicitly: the row-count branches below keep the compiler
   // from hoisting them).  The small launches (one weight row per quad, a handful of CTAs) are pure load-latency
   // chains and take U = 8; the batched launch has 4 rows per quad in flight already (U = 1, loop unrolled twice: more
-  look-ahead costs registers, i.e. the second resident CTA, and measured slower).
+  // look-ahead costs registers, i.e. the second resident CTA, and measured slower).
   constexpr int U = (SK_QCOLS == 1) ? 8 : 1;
 #pragma unroll(U == 1 ? 2 : 1)
   for (int kb = q * 8; kb < k; kb += 32 * U) {
