@@ -183,6 +183,13 @@ def load() -> C.CDLL:
         lib.orvb_model_set_profile.restype = c_int
         lib.orvb_model_get_profile.argtypes = [c_void_p, C.POINTER(c_float), C.POINTER(c_int)]
         lib.orvb_model_get_profile.restype = c_int
+        lib.orvb_modulation_bytes.argtypes = [c_void_p, C.POINTER(Shape), c_int]
+        lib.orvb_modulation_bytes.restype = C.c_size_t
+        lib.orvb_modulation_schedule.argtypes = [c_void_p, C.POINTER(Shape), c_int, c_void_p, c_float, c_void_p, c_void_p,
+                                                 c_void_p, C.c_size_t, c_void_p]
+        lib.orvb_modulation_schedule.restype = c_int
+        lib.orvb_modulation_select.argtypes = [c_void_p, C.POINTER(Shape), c_int, c_int, c_void_p, c_void_p, c_void_p]
+        lib.orvb_modulation_select.restype = c_int
     if hasattr(lib, "orvb_sampler_step"):
         lib.orvb_sampler_step.argtypes = [C.POINTER(SamplerStepArgs), c_void_p]
         lib.orvb_sampler_step.restype = c_int

@@ -390,7 +390,7 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
                "orvb_forward: workspace must be 256-byte aligned");
   ORVB_REQUIRE(!c.use_rope || (a->rope_cos && a->rope_sin), ORVB_EINVAL,
                "orvb_forward: this model uses rotary embeddings but rope_cos/rope_sin are NULL");
-  ORVB_REQUIRE((g.Fa > 0) == (a->actions != nullptr), ORVB_EINVAL,
+  ORVB_REQUIRE(a->skip_modulation || (g.Fa > 0) == (a->actions != nullptr), ORVB_EINVAL,
                "orvb_forward: shape.action_frames and the actions pointer disagree");
   const int D = g.D, T = g.T;
   const int pt = c.patch_size_t > 0 ? c.patch_size_t : 1;

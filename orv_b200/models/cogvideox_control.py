@@ -337,6 +337,75 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
         self.__dict__["_bound_pos_key"] = None
         if "_graphs" in self.__dict__:
             self._graphs.clear()  # captured graphs hold the old weight addresses
+        self.__dict__["_mod_sched"] = None  # tables were built from the old weights
+
+    def prepare_modulation_schedule(self, timesteps, hidden_shape, text_len: int,
+                                    controls_or_guidances: Dict[str, torch.Tensor], ofs=None, num_views: int = 1) -> None:
+        """Builds the AdaLN shift / scale / gate tables of EVERY step of a sampler run in one pass.
+
+        They depend on (timestep, ofs, actions) only, never on the latents, but the reference recomputes them inside
+        each forward (cogvideox_control.py:117-130, :166-170): 0.7 GB of AdaLN weights re-read per step.  After this
+        call, `forward(..., _mod_step=i)` installs step i's tables and skips that part; results are bit-identical.
+        The eval-time action-mask draw of the reference (one `torch.rand(B)` per forward, components.py:66-69) is
+        made here, once per step and in step order, so the device RNG stream is consumed exactly as without a schedule.
+        `hidden_shape` = shape of the `hidden_states` the forwards will receive ([B, V*F, C, H, W])."""
+        self._ensure_handle()
+        dev = next(self.parameters()).device
+        c = self.config
+        Bc, VF, _, H, W = hidden_shape
+        V = num_views if (c.multiview and num_views > 1) else 1
+        B, Fr = Bc * V, VF // V
+        self._ensure_native((Fr, H, W, V))
+        ts = torch.as_tensor(timesteps, dtype=torch.float32).reshape(-1)
+        steps = ts.numel()
+        act_rows, masks, is_masks, action_frames = None, None, None, 0
+        actions = controls_or_guidances.get("actions", None)
+        if actions is not None:
+            res_frames = (actions.size(1) + 1) % 4
+            if res_frames > 0:
+                pad = actions.new_zeros((actions.shape[0], 4 - res_frames, actions.shape[2]))
+                actions = torch.cat([pad, actions], dim=1)
+            rows, mk, im = [], [], []
+            for _ in range(steps):  # one RNG draw per step, in order
+                act_in, is_mask, apply = self.action_embed.prepare(actions.to(dev))
+                if V > 1:
+                    act_in, apply = act_in.repeat_interleave(V, dim=0), apply.repeat_interleave(V, dim=0)
+                if act_in.shape[0] != B:
+                    raise RuntimeError(f"The size of tensor a ({B}) must match the size of tensor b ({act_in.shape[0]}) at "
+                                       "non-singleton dimension 0")
+                rows.append(act_in)
+                mk.append(apply)
+                im.append(is_mask)
+            action_frames = rows[0].shape[1]
+            act_rows = torch.stack(rows).to(torch.bfloat16).contiguous()          # [steps, B, F', k]
+            masks = torch.stack(mk).contiguous() if bool(self.action_embed.mask) else None
+            is_masks = im
+        ofs_val = 0.0
+        if self.ofs_embedding is not None:
+            if ofs is None:
+                raise RuntimeError("this model has an ofs embedding; pass `ofs`")
+            ofs_val = float(ofs.reshape(-1)[0].item()) if torch.is_tensor(ofs) else float(ofs)
+        shape = L.Shape(batch=B, views=V, frames=Fr, height=H, width=W, text_len=text_len, action_frames=action_frames)
+        lib = L.load()
+        nbytes = lib.orvb_modulation_bytes(self._handle, C.byref(shape), steps)
+        if nbytes == 0:
+            raise RuntimeError("orvb_modulation_bytes: " + lib.orvb_last_error().decode())
+        buf = self.__dict__.get("_mod_buf")
+        if buf is None or buf.numel() < nbytes + 256 or buf.device != dev:
+            buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+            self.__dict__["_mod_buf"] = buf
+        ptr = (buf.data_ptr() + 255) // 256 * 256
+        ts_dev = ts.repeat_interleave(B).to(dev).contiguous()                      # step-major [steps * B]
+        L.check(lib.orvb_modulation_schedule(self._handle, C.byref(shape), steps, ts_dev.data_ptr(), ofs_val,
+                                             L.ptr(act_rows), L.ptr(masks), ptr, buf.numel() - (ptr - buf.data_ptr()),
+                                             L.current_stream()), "orvb_modulation_schedule")
+        self.__dict__["last_schedule_launches"] = lib.orvb_last_launch_count(self._handle)
+        self.__dict__["_mod_sched"] = SimpleNamespace(
+            steps=steps, ptr=ptr, buf=buf, action_frames=action_frames, is_mask=is_masks,
+            wkey=(B, V, Fr, H, W, text_len, action_frames, dev.index), keep=(ts_dev, act_rows, masks))
+
+    def clear_modulation_schedule(self) -> None:
+        self.__dict__["_mod_sched"] = None
 
     def set_profile(self, enable: bool) -> None:
         """Per-kernel-class CUDA-event timing inside orvb_forward (bench.py); disables graph replay meanwhile."""
@@ -567,6 +636,7 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
         image_rotary_emb_view: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
         _tap: Optional[Tuple[int, torch.Tensor]] = None,
         _static_out: bool = False,
+        _mod_step: Optional[int] = None,
     ):
         c = self.config
         if timestep_cond is not None:
@@ -617,6 +687,15 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
         act_in = mask_u8 = is_action_mask = None
         action_frames = 0
         actions = controls_or_guidances.get("actions", None)
+        sched = self.__dict__.get("_mod_sched") if _mod_step is not None else None
+        if _mod_step is not None:
+            if sched is None or not (0 <= _mod_step < sched.steps):
+                raise RuntimeError("_mod_step given but no matching modulation schedule is installed "
+                                   "(prepare_modulation_schedule)")
+            # the action embedding, its eval-time mask draw and the timestep were consumed when the schedule was built
+            action_frames = sched.action_frames
+            is_action_mask = sched.is_mask[_mod_step] if sched.is_mask is not None else None
+            actions = None
         if actions is not None:
             res_frames = (actions.size(1) + 1) % 4
             if res_frames > 0:
@@ -687,8 +766,15 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
                 mask=torch.empty(B, dtype=torch.uint8, device=dev),
                 out=torch.empty((B, Fr, c.out_channels, H, W), dtype=torch.bfloat16, device=dev))
             self._static[wkey] = sm
+        if sched is not None:
+            if sched.wkey != wkey:
+                raise RuntimeError(f"modulation schedule was built for shape key {sched.wkey}, forward called with {wkey}")
+            L.check(lib.orvb_modulation_select(self._handle, C.byref(shape), sched.steps, _mod_step, sched.ptr, ws_ptr,
+                                               L.current_stream()), "orvb_modulation_select")
         sm.ts.copy_(ts)
         if act_in is not None:
+            if sm.act is None:  # entry first created by a scheduled call (no per-step action input)
+                sm.act = torch.empty_like(act_in)
             sm.act.copy_(act_in)
             if mask_u8 is not None:
                 sm.mask.copy_(mask_u8)
@@ -708,12 +794,13 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
             a.tap_layer, a.tap_hidden = _tap[0], _tap[1].data_ptr()
         else:
             a.tap_layer = -1
+        a.skip_modulation = 1 if sched is not None else 0
 
         def launch():
             L.check(lib.orvb_forward(self._handle, C.byref(a), L.current_stream()), "orvb_forward")
 
         gkey = (wkey, hs.data_ptr(), text.data_ptr(), L.ptr(depths), L.ptr(labels), L.ptr(rope_cos), L.ptr(rope_sin),
-                ofs_val, mask_u8 is not None)
+                ofs_val, mask_u8 is not None, sched is not None)
         if self.use_cuda_graph and _tap is None and not self._profiling:
             ent = self._graphs.get(gkey)
             if ent is None:

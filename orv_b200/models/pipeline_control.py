@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import inspect
 import math
+import os
 from dataclasses import dataclass
 from types import SimpleNamespace
 from typing import Any, Callable, Dict, List, Optional, Tuple, Union
@@ -383,6 +384,15 @@ class CogVideoXImageToVideoPipelineTraj:
                 self._staging[("old_x0", tuple(latents.shape))] = old_x0
         have_old = False
         launches = 0
+        # The AdaLN tables of all steps depend on (timestep, ofs, actions) only: build them once for the whole run
+        # instead of inside every forward (ORVB_MOD_SCHEDULE=0 keeps the per-step path; results are bit-identical).
+        use_sched = (os.environ.get("ORVB_MOD_SCHEDULE", "1") != "0"
+                     and hasattr(self.transformer, "prepare_modulation_schedule"))
+        if use_sched:
+            self.transformer.prepare_modulation_schedule([float(t) for t in ts_list], tuple(model_input.shape),
+                                                         prompt_embeds.shape[1], controls_or_guidances, ofs=ofs_emb,
+                                                         num_views=num_views)
+            launches += getattr(self.transformer, "last_schedule_launches", 0)
         with self.progress_bar(total=num_inference_steps) as progress_bar:
             for i, t in enumerate(ts_list):
                 if self.interrupt:
@@ -394,7 +404,7 @@ class CogVideoXImageToVideoPipelineTraj:
                     hidden_states=model_input, encoder_hidden_states=prompt_embeds, timestep=timestep, ofs=ofs_emb,
                     image_rotary_emb=image_rotary_emb, attention_kwargs=attention_kwargs,
                     controls_or_guidances=controls_or_guidances, return_dict=False, num_views=num_views,
-                    _static_out=fused)[0]
+                    _static_out=fused, _mod_step=i if use_sched else None)[0]
                 launches += self.transformer.last_launch_count + 2
                 if use_dynamic_cfg:
                     self._guidance_scale = 1 + guidance_scale * (
@@ -436,6 +446,8 @@ class CogVideoXImageToVideoPipelineTraj:
                         cb = callback_on_step_end(self, i, timesteps[i], {"latents": latents})
                         latents = cb.pop("latents", latents)
                 progress_bar.update()
+        if use_sched:
+            self.transformer.clear_modulation_schedule()
         self.last_step_launches = launches
 
         B = latents.shape[0]

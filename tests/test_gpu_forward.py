@@ -81,3 +81,38 @@ def test_forward_small_rope_pt2_ofs():
     cfg = small_cfg(patch_size_t=2, use_rotary_positional_embeddings=True, ofs_embed_dim=512, patch_bias=False)
     e, _ = run_case(cfg, 2, 4, 6, 8, rope=True, ofs=2.0, n_actions=12)
     assert e < 1.5e-2, e
+
+
+@pytest.mark.parametrize("mask_on,views", [(False, 1), (True, 1), (False, 3)])
+def test_modulation_schedule_is_bit_identical(mask_on, views):
+    """AdaLN tables built once for a list of timesteps (prepare_modulation_schedule + _mod_step) must reproduce the
+    per-step forwards bit for bit, including the reference's eval-time action-mask draws (same device RNG stream)."""
+    over = dict(visual_guidance=True, multiview=True, max_n_view=3) if views > 1 else {}
+    cfg = small_cfg(**over)
+    sd32 = O.synthetic_state_dict(cfg, seed=0, std=0.05)
+    m = build_model(cfg, sd32)
+    m.action_embed.mask = mask_on
+    B, Fr, H, W = (1, 2, 6, 8) if views > 1 else (4, 3, 6, 8)
+    inp = O.synthetic_inputs(cfg, B, Fr * views, H, W, seed=1, with_controls=views > 1, n_actions=4 if views > 1 else 8)
+    hs, text = inp["hidden_states"].cuda().bfloat16(), inp["text"].cuda().bfloat16()
+    cg = {"actions": inp["actions"].cuda().bfloat16()}
+    if views > 1:
+        cg["depths"], cg["labels"] = inp["depths"].cuda().bfloat16(), inp["labels"].cuda().bfloat16()
+    steps = [999.0, 749.0, 499.0, 249.0, 19.0]
+    with torch.no_grad():
+        torch.manual_seed(11)
+        ref = [m(hs, text, cg, torch.full((B,), t, device="cuda"), return_dict=False, num_views=views) for t in steps]
+        ref = [(o.clone(), k.clone()) for o, k, _ in ref]
+        torch.manual_seed(11)
+        m.prepare_modulation_schedule(steps, tuple(hs.shape), text.shape[1], cg, num_views=views)
+        for rep in range(2):  # second pass replays the captured graph
+            for i, t in enumerate(steps):
+                out, is_mask, _ = m(hs, text, cg, torch.full((B,), t, device="cuda"), return_dict=False, num_views=views,
+                                    _mod_step=i)
+                assert torch.equal(out, ref[i][0]), (rep, i)
+                assert torch.equal(is_mask, ref[i][1])
+        m.clear_modulation_schedule()
+        with pytest.raises(RuntimeError):
+            m(hs, text, cg, torch.full((B,), 499.0, device="cuda"), return_dict=False, num_views=views, _mod_step=0)
+    if mask_on:
+        assert any(bool(k.any()) for _, k in ref) or True  # 10 % draws: may be all-False for a tiny batch
