@@ -392,7 +392,7 @@ constexpr int G2_ACC_COLS = 256;                  // TMEM columns per accumulato
 // that is not hidden behind a mainloop (the attn-out and FF2 GEMMs have just two tiles per cluster).  The register-
 // heavy ones (GELU, QKV LayerNorm) stay at four.
 __host__ __device__ constexpr int g2_epi_warps(int epi) {
-  return (epi == ORVB_EPI_BIAS || epi == ORVB_EPI_GATE_RESID) ? 8 : 4;
+  return (epi == ORVB_EPI_BIAS || epi == ORVB_EPI_GATE_RESID || epi == ORVB_EPI_QKV || epi == ORVB_EPI_GELU) ? 8 : 4;
 }
 __host__ __device__ constexpr int g2_threads(int epi) { return (4 + g2_epi_warps(epi)) * 32; }
 
