@@ -9,8 +9,8 @@ import torch
 
 sys.path.insert(0, ".")
 from bench import init_weights_, peaks  # noqa: E402
-from oracle import flat_oracle as O  # noqa: E402  (input / RoPE-table generators only)
 from orv_b200 import CogVideoXTransformer3DModelTraj  # noqa: E402
+from orv_b200.models.embeddings import get_3d_rotary_pos_embed  # noqa: E402
 
 BASE2B = dict(num_attention_heads=30, attention_head_dim=64, in_channels=32, out_channels=16, num_layers=30,
               modulate_encoder_hidden_states=True, text_embed_dim=4096, max_text_seq_length=226, time_embed_dim=512, patch_size=2)
@@ -29,22 +29,28 @@ dev = torch.device("cuda")
 pk = peaks()
 for cid in [int(a) for a in sys.argv[1:]] or [3, 4, 5]:
     c = CASES[cid]
-    cfg = O.default_config(**c["cfg"])
+    cfg = c["cfg"]
     V = c.get("views", 1)
     with torch.device(dev):
         model = CogVideoXTransformer3DModelTraj(**cfg)
     init_weights_(model, 0)
     model = model.to(torch.bfloat16).eval()
     model.action_embed.mask = False
-    inp = O.synthetic_inputs(cfg, c["B"], c["F"] * V, c["H"], c["W"], seed=1, with_controls=c.get("controls", False),
-                             n_actions=c.get("n_actions", 16))
-    cg = {"actions": inp["actions"].to(dev).bfloat16()}
+    gen = torch.Generator(device=dev).manual_seed(1)
+    lat_shape = (c["B"], c["F"] * V, cfg["in_channels"], c["H"], c["W"])
+    hs = torch.randn(lat_shape, generator=gen, device=dev).bfloat16()
+    text = (torch.randn(c["B"], 226, 4096, generator=gen, device=dev) * 0.2).bfloat16()
+    cg = {"actions": ((torch.rand(c["B"], c.get("n_actions", 16), 7, generator=gen, device=dev) * 2 - 1) * 20).bfloat16()}
     if c.get("controls"):
-        cg["depths"], cg["labels"] = inp["depths"].to(dev).bfloat16(), inp["labels"].to(dev).bfloat16()
-    rope = O.pipeline_rope(cfg, c["H"] * 8, c["W"] * 8, c["F"]) if c.get("rope") else None
-    rope = (rope[0].to(dev), rope[1].to(dev)) if rope else None
+        cg["depths"] = torch.randn(lat_shape, generator=gen, device=dev).bfloat16()
+        cg["labels"] = torch.randn(lat_shape, generator=gen, device=dev).bfloat16()
+    rope = None
+    if c.get("rope"):  # CogVideoX1.5 'slice' grid over (F / p_t, H / 2, W / 2) tokens
+        gh, gw, pt = c["H"] // 2, c["W"] // 2, cfg["patch_size_t"]
+        cos, sin = get_3d_rotary_pos_embed(64, None, (gh, gw), (c["F"] + pt - 1) // pt, grid_type="slice",
+                                           max_size=(cfg["sample_height"] // 2, cfg["sample_width"] // 2))
+        rope = (cos.to(dev).float().contiguous(), sin.to(dev).float().contiguous())
     ofs = torch.tensor([c["ofs"]], device=dev) if "ofs" in c else None
-    hs, text = inp["hidden_states"].to(dev).bfloat16(), inp["text"].to(dev).bfloat16()
     t = torch.full((c["B"],), 499, device=dev)
     call = lambda: model(hs, text, cg, t, ofs=ofs, image_rotary_emb=rope, return_dict=False, num_views=V)[0]  # noqa: E731
     with torch.no_grad():
