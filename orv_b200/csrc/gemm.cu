@@ -1,4 +1,8 @@
-// Persistent, warp-specialised bf16 GEMM for sm_100a:  out = epilogue(A[M,K] · W[N,K]^T)
+// Persistent, warp-specialised bf16 GEMMs for sm_100a:  out = epilogue(A[M,K] · W[N,K]^T)
+//
+// Two kernels share the fused epilogues below: the single-CTA kernel (128 x BN tiles, used for M <= 128 and as the
+// bit-exactness reference) and the CTA-pair kernel further down (256 x BN tiles, tcgen05 cta_group::2 — the one the
+// forward runs).  Roles of the single-CTA kernel:
 //
 //   warp 0      TMA producer   (cp.async.bulk.tensor → 128B-swizzled smem ring)
 //   warp 1      MMA issuer     (one thread, tcgen05.mma cta_group::1, 128 x BN x 16 atoms, fp32 accum in TMEM)
@@ -377,22 +381,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 // last wave of the 74 clusters best.
 //
 // Roles per CTA: warp 0 TMA producer (both CTAs; byte counts are credited to the LEADER's full barrier), warp 1
-// MMA issuer (leader only), warp 2 TMEM allocator, warps 4-7 epilogue over this CTA's 128 accumulator rows.
+// MMA issuer (leader only), warp 2 TMEM allocator, warps 4-11 epilogue over this CTA's 128 accumulator rows (eight
+// warps: e and e + 4 share a TMEM lane quarter and alternate 64-column units; tcgen05.ld -> fused epilogue ->
+// 128B-swizzled staging tile -> one TMA store per warp and unit).
 // ---------------------------------------------------------------------------------------------------
 constexpr int G2_STAGES = 6;
 constexpr int G2_A_BYTES = BM * BK * 2;           // 16 KB: this CTA's 128 rows of A
 constexpr int G2_B_BYTES = 128 * BK * 2;          // up to 16 KB: this CTA's BN/2 rows of B
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
-constexpr int G2_OUT_STAGE_BYTES = 4 * 2 * 32 * 128;  // per epilogue warp: two [32 x 64] bf16 output tiles
+constexpr int G2_OUT_STAGE_BYTES = 8 * 32 * 128;  // 32 KB of [32 x 64] bf16 output staging tiles, split over the epilogue warps
 constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + G2_OUT_STAGE_BYTES + 1024 + 256;
 constexpr int G2_ACC_COLS = 256;                  // TMEM columns per accumulator buffer (2 buffers = 512)
 
-// Epilogue warps per CTA.  The light epilogues (bias, gated residual) run eight: warps e and e + 4 share a TMEM lane
-// quarter and take alternate 64-column units, which halves the epilogue of the LAST tile of a cluster — the only one
-// that is not hidden behind a mainloop (the attn-out and FF2 GEMMs have just two tiles per cluster).  The register-
-// heavy ones (GELU, QKV LayerNorm) stay at four.
+// Epilogue warps per CTA: eight — warps e and e + 4 share a TMEM lane quarter and take alternate 64-column units, which
+// halves the epilogue of the LAST tile of a cluster, the only one that is not hidden behind a mainloop (the attn-out
+// and FF2 GEMMs have just two tiles per cluster).  Measured: attn-out 41 -> 36 us, fused FF1 = plain FF1.  The
+// register-heavy epilogues still fit (QKV LayerNorm 168, GELU 162 registers at 384 threads); a value of 4 keeps the
+// code path for an epilogue that would not.
 __host__ __device__ constexpr int g2_epi_warps(int epi) {
-  return (epi == ORVB_EPI_BIAS || epi == ORVB_EPI_GATE_RESID || epi == ORVB_EPI_QKV || epi == ORVB_EPI_GELU) ? 8 : 4;
+  (void)epi;
+  return 8;
 }
 __host__ __device__ constexpr int g2_threads(int epi) { return (4 + g2_epi_warps(epi)) * 32; }
 
