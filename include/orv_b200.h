@@ -108,6 +108,10 @@ typedef struct orvb_gemm_args {
 
 /* tcgen05 / TMA GEMM.  Requirements: k % 8 == 0, n % 8 == 0, lda/ldw/ldo % 8 == 0, 16-byte aligned bases. */
 int orvb_gemm_bf16(const orvb_gemm_args* args, void* stream);
+/* Tile choice of orvb_gemm_bf16 for an [m, n] output (host arithmetic only): > 0 = single-CTA kernel, 128 x value tiles;
+ * < 0 = CTA-pair kernel (tcgen05 cta_group::2), 256 x (-value) tiles, the width that fills the last wave of the
+ * device's SM pairs best. */
+int orvb_gemm_tile_width(int32_t m, int32_t n, int32_t epilogue);
 
 /* Non-causal multi-head attention over a packed QKV buffer (reference a8: F.scaled_dot_product_attention).
  * qkv: bf16 [batch * seq_len, 3 * heads * 64] with Q | K | V column blocks; out: bf16 [batch * seq_len, heads*64].

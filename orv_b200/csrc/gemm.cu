@@ -824,3 +824,11 @@ extern "C" int orvb_gemm_bf16_bn(const orvb_gemm_args* args, int bn, void* strea
   if (rc != ORVB_OK) return rc;
   return gemm_launch_prepared(ta, tb, to, p, bn_used, args->epilogue, static_cast<cudaStream_t>(stream));
 }
+
+// Which kernel / tile width orvb_gemm_bf16 picks for an [m, n] output on this device: > 0 = single-CTA kernel with that
+// N tile, < 0 = CTA-pair kernel with N tile -value.  Pure host arithmetic (148 SMs assumed when no GPU is present).
+extern "C" int orvb_gemm_tile_width(int32_t m, int32_t n, int32_t epilogue) {
+  using namespace orvb;
+  if (m <= 0 || n <= 0) return 0;
+  return m > BM ? -gemm_pick_bn_pair(m, n, epilogue) : gemm_pick_bn(m, n);
+}

@@ -227,3 +227,23 @@ def test_shard_range_is_the_reference_partition():
         assert got == [(r * per, (r + 1) * per if r != w - 1 else n) for r in range(w)]
         covered = [i for a, b in got for i in range(a, b)]
         assert covered == list(range(n))
+
+
+def test_gemm_tile_choice_for_the_config2_block():
+    """Host-side tile selection (no GPU needed): the four GEMMs of a CogVideoX-2B block at S = 3226 tokens use the
+    CTA-pair kernel with the widths that fill the last wave of the 74 SM pairs (profiles/r01_gemm_notes.md), the QKV
+    epilogue only ever gets whole 64-wide heads, and single-tile problems stay on the single-CTA kernel."""
+    from orv_b200 import _lib as L
+    lib = L.load()
+    S, D, FF = 3226, 1920, 7680
+    assert lib.orvb_gemm_tile_width(S, 3 * D, L.EPI_QKV) == -192
+    assert lib.orvb_gemm_tile_width(S, D, L.EPI_GATE_RESID) == -176
+    assert lib.orvb_gemm_tile_width(S, FF, L.EPI_GELU) == -240
+    for n in (64, 128, 1920, 3072, 5760, 9216, 12288):
+        w = lib.orvb_gemm_tile_width(S, n, L.EPI_QKV)
+        assert w < 0 and (-w) % 64 == 0 and 64 <= -w <= 256
+        w = lib.orvb_gemm_tile_width(S, n, L.EPI_BIAS)
+        assert w < 0 and (-w) % 16 == 0 and 64 <= -w <= 256
+    assert lib.orvb_gemm_tile_width(128, 512, L.EPI_BIAS) > 0
+    assert lib.orvb_gemm_tile_width(6, 512, L.EPI_BIAS) in (64, 128, 192, 256)
+    assert lib.orvb_gemm_tile_width(0, 512, L.EPI_BIAS) == 0
