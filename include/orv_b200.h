@@ -118,6 +118,12 @@ int orvb_gemm_tile_width(int32_t m, int32_t n, int32_t epilogue);
  * softmax scale = scale (1/sqrt(64) in the reference).  head_dim is fixed at 64 (every shipped config). */
 int orvb_attention_bf16(const void* qkv, void* out, int32_t batch, int32_t seq_len, int32_t heads, float scale,
                         void* stream);
+/* Test hooks of the attention kernel.  The running row max is raised lazily (only when a key tile exceeds it by more
+ * than 2^threshold, default 8), which makes the rescale of the TMEM-resident output accumulators rare;
+ * orvb_attention_set_rescale_threshold(0) forces that path on almost every tile (negative = restore the default).
+ * orvb_attention_set_debug installs a device buffer for in-kernel clock stamps (builds with -DORVB_ATT_TIMELINE). */
+void orvb_attention_set_rescale_threshold(float log2_units);
+void orvb_attention_set_debug(void* dev_buf);
 
 /* LayerNorm(eps, affine) followed by AdaLN modulation y = LN(x) * (1 + scale_g) + shift_g where g is the row's
  * group and (shift, scale) come from the fp32 table `mod` (row pitch mod_ld):

@@ -121,7 +121,8 @@ class SamplerStepArgs(C.Structure):
 # Every symbol include/orv_b200.h declares; tests check the .so exports all of them.
 EXPORTED_SYMBOLS = [
     "orvb_version", "orvb_last_error", "orvb_check_device",
-    "orvb_gemm_bf16", "orvb_gemm_tile_width", "orvb_attention_bf16", "orvb_ln_modulate", "orvb_skinny_linear",
+    "orvb_gemm_bf16", "orvb_gemm_tile_width", "orvb_attention_bf16", "orvb_attention_set_rescale_threshold",
+    "orvb_attention_set_debug", "orvb_ln_modulate", "orvb_skinny_linear",
     "orvb_patchify", "orvb_unpatchify",
     "orvb_model_create", "orvb_model_destroy", "orvb_model_bind_weights", "orvb_workspace_bytes",
     "orvb_forward", "orvb_last_launch_count", "orvb_model_set_profile", "orvb_model_get_profile",
@@ -154,6 +155,11 @@ def load() -> C.CDLL:
     if hasattr(lib, "orvb_gemm_bf16_bn"):
         lib.orvb_gemm_bf16_bn.argtypes = [C.POINTER(GemmArgs), c_int, c_void_p]
         lib.orvb_gemm_bf16_bn.restype = c_int
+    if hasattr(lib, "orvb_attention_set_rescale_threshold"):
+        lib.orvb_attention_set_rescale_threshold.argtypes = [c_float]
+        lib.orvb_attention_set_rescale_threshold.restype = None
+        lib.orvb_attention_set_debug.argtypes = [c_void_p]
+        lib.orvb_attention_set_debug.restype = None
     if hasattr(lib, "orvb_attention_bf16"):
         lib.orvb_attention_bf16.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]
         lib.orvb_attention_bf16.restype = c_int

@@ -26,7 +26,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
-]
+] + os.environ.get("ORVB_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _nvcc() -> str:

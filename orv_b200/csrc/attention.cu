@@ -38,13 +38,19 @@ constexpr int ATT_D = 64;
 constexpr int ATT_TMEM_COLS = 512;  // S_t: [t*128, +128)   O_{t,stream}: [256 + t*128 + stream*64, +64)
 constexpr int ATT_XCH_STRIDE = 67;  // floats per row of the end-of-kernel stream exchange (conflict-free)
 constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units
-constexpr int ATT_DEFAULT_VARIANT = 3;
+// 1 = ONE MMA-issuing warp, warp-uniform issue.  The one-issuer-per-query-tile variants (3, 11, 19) are ~4 % faster but
+// NOT safe: when the rare lazy-rescale path rewrites an O accumulator (tcgen05.ld -> scale -> tcgen05.st) while a
+// DIFFERENT thread is issuing tcgen05.mma, a few rows come out wrong (forced rescale: 28/30 launches bad with two
+// issuers, 0/60 with one; same signature with two CTAs per SM — profiles/r01_attention_notes.md).  They stay
+// selectable through ORVB_ATT_VARIANT for experiments only.
+constexpr int ATT_DEFAULT_VARIANT = 1;
 
 struct AttDev {
   bf16* out;
   int seq_len, heads, dim;  // dim = heads * 64
   float scale_log2;         // softmax scale * log2(e)
   int q_row0, q_rows;       // queries = rows [q_row0, q_row0 + q_rows) of every sequence; output is compact
+  float rescale_threshold;  // log2 units by which a tile max must exceed the running max before it is raised
   long long* dbg;           // optional timeline buffer (tools/profile_attention_timeline.py); nullptr in production
 };
 
@@ -179,12 +185,20 @@ __device__ __forceinline__ float softmax_pass(const uint32_t (&r0)[32], const ui
   return (s0 + s1) + (s2 + s3);
 }
 
-// Timeline stamps of CTA (0,0,0): row `who`, slot = 4 * j + k.  Only taken when a debug buffer is installed.
+// Timeline stamps of CTA (0,0,0): row `who`, slot = 4 * j + k, taken when a debug buffer is installed
+// (tools/profile_attention_timeline.py).  Compiled in only with -DORVB_ATT_TIMELINE: the eight predicated stamps per
+// key tile cost issue slots the softmax warps are short of.
+#ifdef ORVB_ATT_TIMELINE
 #define A4_STAMP(who, j, k)                                                                             \
   do {                                                                                                  \
     if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (j) < 32) \
       p.dbg[(who) * 128 + (j) * 4 + (k)] = clock64();                                                   \
   } while (0)
+#else
+#define A4_STAMP(who, j, k) \
+  do {                      \
+  } while (0)
+#endif
 
 template <bool DUAL, bool UNIFORM, int EMU>
 __global__ void __launch_bounds__(DUAL ? 608 : 576, 1)
@@ -366,7 +380,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttDev p) {
       const float mx = (valid >= 64) ? row_max64<false>(r0, r1, valid) : row_max64<true>(r0, r1, valid);
       const float m_tile = mx * scale;
       // ---- lazy rescale: raise the running max only when this tile exceeds it by > 2^8 ----
-      const bool grow = m_tile > m_run + ATT_RESCALE_THRESHOLD;
+      const bool grow = m_tile > m_run + p.rescale_threshold;
       if (__any_sync(0xffffffffu, grow)) {
         const float m_new = grow ? m_tile : m_run;
         const float alpha = grow ? ex2(m_run - m_new) : 1.0f;
@@ -391,15 +405,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttDev p) {
                                       : softmax_pass<true, 0>(r0, r1, p_row, sw, scale, -m_run, valid);
       l_run += sum;
       A4_STAMP(warp, j, 3);
-      if (j + 1 < n_kv) {
-        // S_{t,j+1} has normally been complete for a while (its QK^T was queued when s_free fired): start copying it
-        // now so the TMEM read overlaps the fence / arrive below.
-        mbar_wait(my_s_full, static_cast<uint32_t>((j + 1) & 1));
-        tc_fence_after();
-        tmem_ld_32x32b_x32(my_s, r0);
-        tmem_ld_32x32b_x32(my_s + 32u, r1);
-      }
-      A4_STAMP(warp, j, 0);
       fence_proxy_async_smem();  // make the P stores visible to the tensor-core (async) proxy
       tc_fence_before();         // order our TMEM loads / stores before the MMAs that follow
       mbar_arrive(my_p_full);
@@ -479,6 +484,7 @@ static int launch_attention_v4(const CUtensorMap& tm, const AttDev& p, dim3 grid
 }
 
 static long long* g_att_dbg = nullptr;
+static float g_att_threshold = -1.f;  // < 0: take ORVB_ATT_THRESHOLD or the default on the next launch
 
 int attention_launch(const void* qkv, void* out, int batch, int seq_len, int heads, float scale, int q_row0,
                      int q_rows, cudaStream_t stream) {
@@ -503,6 +509,13 @@ int attention_launch(const void* qkv, void* out, int batch, int seq_len, int hea
   p.q_row0 = q_row0;
   p.q_rows = q_rows;
   p.dbg = g_att_dbg;
+  // Test knob (ORVB_ATT_THRESHOLD or orvb_attention_set_rescale_threshold): 0 raises the running max on (almost) every key tile, i.e. forces the otherwise rare
+  // TMEM read-modify-write of the O accumulators (tests/test_gpu_ops.py::test_attention_forced_rescale).
+  if (g_att_threshold < 0.f) {
+    const char* e = getenv("ORVB_ATT_THRESHOLD");
+    g_att_threshold = e ? static_cast<float>(atof(e)) : ATT_RESCALE_THRESHOLD;
+  }
+  p.rescale_threshold = g_att_threshold;
   dim3 grid((q_rows + 2 * ATT_BQ - 1) / (2 * ATT_BQ), heads, batch);
   // A/B switch for measurements: bit 0 = warp-uniform MMA issue, bit 1 = one MMA warp per query tile, 4 = v3 kernel.
   static int variant = -1;
@@ -537,3 +550,7 @@ extern "C" int orvb_attention_bf16(const void* qkv, void* out, int32_t batch, in
 // Measurement hook: installs (or clears, with NULL) a device buffer of 18 x 128 int64 that CTA (0,0,0) of the next
 // attention launches fills with clock64() stamps (tools/profile_attention_timeline.py).
 extern "C" void orvb_attention_set_debug(void* dev_buf) { orvb::g_att_dbg = static_cast<long long*>(dev_buf); }
+
+// Test hook: log2-unit threshold of the lazy row-max update (default 8; 0 forces the O-accumulator rescale path on
+// almost every key tile; a negative value restores the default / ORVB_ATT_THRESHOLD).
+extern "C" void orvb_attention_set_rescale_threshold(float log2_units) { orvb::g_att_threshold = log2_units; }

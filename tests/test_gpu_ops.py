@@ -156,6 +156,27 @@ def test_attention_rising_max(ops, B, S, H):
     assert (out.float() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("B,S,H", [(1, 3226, 30), (2, 2026, 48)])
+def test_attention_forced_rescale(ops, B, S, H):
+    """Threshold 0 makes the kernel raise the running row max (and rescale the TMEM-resident O accumulators) on almost
+    every key tile instead of almost never; results must still match, launch after launch.  (This is the path that
+    corrupts rows when a second thread issues tcgen05.mma concurrently — the shipped kernel has a single issuer.)"""
+    from orv_b200 import _lib as L
+    lib = L.load()
+    torch.manual_seed(9)
+    qkv = torch.randn(B * S, 3 * H * 64, device=DEV).bfloat16()
+    qkv[:, : H * 64] *= 2.0
+    q, k, v = qkv.float().view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v, scale=0.125).permute(0, 2, 1, 3).reshape(B * S, H * 64)
+    lib.orvb_attention_set_rescale_threshold(0.0)
+    try:
+        for _ in range(12):
+            out = ops.attention(qkv, B, S, H, 0.125)
+            assert (out.float() - ref).abs().max().item() < 2e-2
+    finally:
+        lib.orvb_attention_set_rescale_threshold(-1.0)
+
+
 def test_attention_repeatable(ops):
     """The kernel has no atomics or order-dependent reductions: repeated launches must be bit-identical (race check)."""
     torch.manual_seed(8)

@@ -1,4 +1,5 @@
-"""Prints the clock64 timeline of CTA (0,0,0) of the attention kernel (run under gpurun)."""
+"""Prints the clock64 timeline of CTA (0,0,0) of the attention kernel (run under gpurun).
+Needs a library built with the stamps compiled in:  ORVB_EXTRA_NVCC_FLAGS=-DORVB_ATT_TIMELINE python -m orv_b200.build --force"""
 import ctypes as C
 import sys
 import torch

@@ -4,8 +4,8 @@ import sys
 import torch
 sys.path.insert(0, ".")
 from orv_b200 import ops
-B, S, H = 1, 3226, 30
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+B, S, H = (int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) > 4 else (1, 3226, 30)
 torch.manual_seed(0)
 qkv = torch.randn(B * S, 3 * H * 64, device="cuda").bfloat16()
 qkv[:, : H * 64] *= 2.0
@@ -14,12 +14,12 @@ ref = torch.nn.functional.scaled_dot_product_attention(q, k, v, scale=0.125).per
 bad_runs = 0
 for i in range(n):
     out = ops.attention(qkv, B, S, H, 0.125).float()
-    err = (out - ref).abs().view(S, H, 64).amax(dim=2)          # [S, H]
+    err = (out - ref).abs().view(B * S, H, 64).amax(dim=2)      # [B*S, H]
     bad = (err > 0.05).nonzero()
     if bad.numel():
         bad_runs += 1
-        tiles = sorted({(int(h), int(r) // 128) for r, h in bad.tolist()})
-        rows = sorted({int(r) % 128 for r, h in bad.tolist()})
+        tiles = sorted({(int(h), (int(r) % S) // 128) for r, h in bad.tolist()})
+        rows = sorted({(int(r) % S) % 128 for r, h in bad.tolist()})
         print(f"run {i}: {bad.shape[0]} bad (row, head) pairs; (head, q-tile): {tiles[:12]}; rows-in-tile {rows[0]}..{rows[-1]} ({len(rows)} distinct)",
               flush=True)
 print(f"bad runs: {bad_runs}/{n}", flush=True)
