@@ -211,10 +211,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttDev p) {
   uint64_t* k_empty = bars + 5;   // [2]
   uint64_t* v_empty = bars + 7;   // [2]
   uint64_t* s_full = bars + 9;    // [2] per query tile
-  uint64_t* p_full = bars + 11;   // [2]
-  uint64_t* o_full = bars + 13;   // [2 tiles][2 P buffers]: PV_{t,j} retired (j & 1 selects the barrier)
-  uint64_t* s_free = bars + 17;   // [2] S_t copied to registers by all 8 softmax warps of the tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  // p_full: [2 tiles][2 P buffers].  One barrier per P buffer, not per tile: the single issuing warp serves the two
+  // tiles in turn, and a tile whose next QK^T is already queued may finish key tile j+1 while the issuer is still
+  // blocked on the OTHER tile's P_j.  With one barrier per tile its P_j wait would then be two phases behind, which a
+  // parity wait cannot tell from "not yet" (dead-lock until the watchdog trap); per buffer it is at most one.
+  uint64_t* p_full = bars + 11;   // [4]
+  uint64_t* o_full = bars + 15;   // [2 tiles][2 P buffers]: PV_{t,j} retired (j & 1 selects the barrier)
+  uint64_t* s_free = bars + 19;   // [2] S_t copied to registers by all 8 softmax warps of the tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -235,7 +239,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttDev p) {
       mbar_init(&k_empty[i], DUAL ? 2 : 1);
       mbar_init(&v_empty[i], DUAL ? 2 : 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 256);  // every softmax thread of the tile, after its own proxy fence
+      mbar_init(&p_full[2 * i], 256);  // every softmax thread of the tile, after its own proxy fence
+      mbar_init(&p_full[2 * i + 1], 256);
       mbar_init(&o_full[2 * i], 1);
       mbar_init(&o_full[2 * i + 1], 1);
       mbar_init(&s_free[i], 256);
@@ -316,7 +321,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttDev p) {
         }
 #pragma unroll 1
         for (int t = t_lo; t <= t_hi; ++t) {
-          mbar_wait(&p_full[t], static_cast<uint32_t>(j & 1));  // P_{t,j} in smem, O_t rescaled if needed
+          mbar_wait(&p_full[2 * t + (j & 1)], static_cast<uint32_t>((j >> 1) & 1));  // P_{t,j} in smem, O_t rescaled
           tc_fence_after();
           A4_STAMP(16 + t, j, 2);
           mbar_wait(&v_full[st], static_cast<uint32_t>((j >> 1) & 1));
@@ -352,7 +357,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttDev p) {
     const uint32_t my_s = tmem_base + lane_off + static_cast<uint32_t>(t * 128 + stream * 64);
     const uint32_t my_o = tmem_base + lane_off + static_cast<uint32_t>(256 + t * 128 + stream * 64);
     uint64_t* my_s_full = &s_full[t];
-    uint64_t* my_p_full = &p_full[t];
+    uint64_t* my_p_full = &p_full[2 * t];  // [j & 1]
     uint64_t* my_o_full = &o_full[2 * t];  // [j & 1]; completion k of barrier b belongs to PV_{t, 2k + b}
     uint64_t* my_s_free = &s_free[t];
     float m_run = -INFINITY;  // running (lazy) max in the scaled log2 domain
@@ -407,7 +412,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttDev p) {
       A4_STAMP(warp, j, 3);
       fence_proxy_async_smem();  // make the P stores visible to the tensor-core (async) proxy
       tc_fence_before();         // order our TMEM loads / stores before the MMAs that follow
-      mbar_arrive(my_p_full);
+      mbar_arrive(&my_p_full[j & 1]);
     }
 
     // ---- combine the two streams of this query tile, normalise, store ----
