@@ -342,6 +342,45 @@ typedef struct orvb_sampler_step_args {
 } orvb_sampler_step_args;
 int orvb_sampler_step(const orvb_sampler_step_args* a, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Occupancy voxelization (replaces the reference extension orv/ops/voxelize:
+ * `voxelization_op.dynamic_voxelize_forward` / `hard_voxelize_forward`, voxelization.cpp:104-150, bound at
+ * voxelization.py:89-116) and the label vote of its caller (orv/dataset/prepare_dataset.py:137-198).
+ * Points are fp32 [n, c] with xyz in the first three features; cells are int32 (z, y, x) like the reference's
+ * `coors`; grid_size = round((range_max - range_min) / voxel_size) per axis, computed in float as the reference does.
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* coors[i] = (z, y, x) of point i, or (-1, -1, -1) when it falls outside the range (or is NaN).  The reference's CPU
+ * implementation writes exactly this (voxelization_cpu.cpp:18-42); its CUDA kernel leaves the later components of
+ * an out-of-range point at their zero initialisation (voxelization_kernel.cuh:24-41) — callers test coors[:, 0]. */
+int orvb_dynamic_voxelize(const float* points, int32_t n, int32_t c, const float* voxel_size /*[3]*/,
+                          const float* coors_range /*[6]*/, int32_t* coors /*[n, 3]*/, void* stream);
+
+typedef struct orvb_voxelize_args {
+  const float* points;            /* fp32 [n, c], c >= 3 (c == 4 and a 16-byte aligned base take the 128-bit path) */
+  int32_t n, c;
+  float voxel_size[3];
+  float coors_range[6];           /* x_min, y_min, z_min, x_max, y_max, z_max */
+  int32_t max_points;             /* > 0: points kept per voxel (the first ones in index order)              */
+  int32_t max_voxels;             /* > 0: voxels kept (the first ones in order of first appearance)          */
+  float* voxels;                  /* fp32 [max_voxels, max_points, c], ZERO-FILLED by the caller as the reference's
+                                     new_zeros (voxelization.py:97-98); only occupied slots are written; NULL = skip */
+  int32_t* coors;                 /* int32 [max_voxels, 3] (z, y, x) or NULL                                  */
+  int32_t* num_points_per_voxel;  /* int32 [max_voxels] or NULL                                               */
+  int64_t* voxel_num;             /* device scalar: number of voxels produced (<= max_voxels); required       */
+  /* Optional fused label vote of points_to_voxels (prepare_dataset.py:176-196): float64 [max_voxels, 4] rows
+   * (x, y, z, label) where label + 1 is the most frequent LAST feature among the voxel's max_points slots, empty
+   * slots counting as 0 and 0 yielding to the runner-up; ties go to the smaller label.  Real points must carry a
+   * last feature > 0 (the caller adds 1 to its labels, prepare_dataset.py:160-161). */
+  double* voxel_labels;
+  void* workspace; size_t workspace_bytes;  /* orvb_voxelize_workspace_bytes(n, max_voxels), 256-byte aligned */
+} orvb_voxelize_args;
+
+size_t orvb_voxelize_workspace_bytes(int32_t n, int32_t max_voxels);
+/* Deterministic hard voxelization: the result of the reference's deterministic path (voxelization_cpu.cpp:48-108,
+ * voxelization_kernel.cu:24-129), which is also a valid outcome of its non-deterministic one. */
+int orvb_hard_voxelize(const orvb_voxelize_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

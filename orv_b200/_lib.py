@@ -118,6 +118,17 @@ class SamplerStepArgs(C.Structure):
     ]
 
 
+class VoxelizeArgs(C.Structure):
+    _fields_ = [
+        ("points", c_void_p), ("n", c_int), ("c", c_int),
+        ("voxel_size", c_float * 3), ("coors_range", c_float * 6),
+        ("max_points", c_int), ("max_voxels", c_int),
+        ("voxels", c_void_p), ("coors", c_void_p), ("num_points_per_voxel", c_void_p), ("voxel_num", c_void_p),
+        ("voxel_labels", c_void_p),
+        ("workspace", c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 # Every symbol include/orv_b200.h declares; tests check the .so exports all of them.
 EXPORTED_SYMBOLS = [
     "orvb_version", "orvb_last_error", "orvb_check_device",
@@ -128,6 +139,7 @@ EXPORTED_SYMBOLS = [
     "orvb_forward", "orvb_last_launch_count", "orvb_model_set_profile", "orvb_model_get_profile",
     "orvb_modulation_bytes", "orvb_modulation_schedule", "orvb_modulation_select",
     "orvb_sampler_step",
+    "orvb_dynamic_voxelize", "orvb_voxelize_workspace_bytes", "orvb_hard_voxelize",
 ]
 
 _lib = None
@@ -202,6 +214,14 @@ def load() -> C.CDLL:
     if hasattr(lib, "orvb_sampler_step"):
         lib.orvb_sampler_step.argtypes = [C.POINTER(SamplerStepArgs), c_void_p]
         lib.orvb_sampler_step.restype = c_int
+    if hasattr(lib, "orvb_hard_voxelize"):
+        lib.orvb_dynamic_voxelize.argtypes = [c_void_p, c_int, c_int, C.POINTER(c_float), C.POINTER(c_float), c_void_p,
+                                              c_void_p]
+        lib.orvb_dynamic_voxelize.restype = c_int
+        lib.orvb_voxelize_workspace_bytes.argtypes = [c_int, c_int]
+        lib.orvb_voxelize_workspace_bytes.restype = C.c_size_t
+        lib.orvb_hard_voxelize.argtypes = [C.POINTER(VoxelizeArgs), c_void_p]
+        lib.orvb_hard_voxelize.restype = c_int
     _lib = lib
     return lib
 

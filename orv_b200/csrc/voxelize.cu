@@ -1,0 +1,663 @@
+// Point-cloud voxelization for the occupancy condition: the B200 replacement of the reference's
+// `orv/ops/voxelize` extension (voxelization.py:41-122 -> voxelization_kernel.cu / voxelization_cpu.cpp) and of the
+// label vote its caller runs on the result (orv/dataset/prepare_dataset.py:137-198).
+//
+// Integer / index work, HBM-bound.  The reference's deterministic CUDA path scans, for every point, ALL earlier
+// points for a duplicate voxel (point_to_voxelidx_kernel, voxelization_kernel.cuh:90-132: O(N^2) loads) and then
+// numbers the voxels in a <<<1,1>>> kernel (determin_voxel_num, :134-162).  Here the same result — voxels numbered
+// in order of first appearance, points kept in index order, max_points / max_voxels caps — comes from O(N) passes:
+//
+//   1. voxel_insert_kernel   128-bit point loads -> (z,y,x) cell -> open-addressing hash insert of the 64-bit cell
+//                            key, atomicMin of the point index per occupied slot (= first point of the voxel)
+//   2. first_flag_kernel     flag[i] = "point i is the first of its voxel"; exclusive scan -> voxel numbers in
+//                            first-appearance order, total voxel count
+//   3. sort_key_kernel       key[i] = voxel number (or the drop sentinel for invalid / over-cap voxels)
+//   4. stable LSD radix sort of (voxel number, point index), 8 bits per pass, ceil(log2(cap+1)/8) passes: points of a
+//      voxel end up contiguous and in index order, so "position in voxel" = sorted position - segment start
+//   5. segment_kernel / gather_kernel   segment bounds per voxel, feature copy of the first max_points points
+//   6. label_vote_kernel     (optional) one warp per voxel: most frequent label among the max_points slots of the
+//                            voxel (empty slots count as label 0, which yields to the runner-up), without ever
+//                            materialising the reference's [max_voxels, max_points, C] tensor (160 MB at its
+//                            1e5 x 100 x 4 call site) or copying it to the host.
+//
+// No atomics decide an output value except atomicMin / atomicCAS whose results are order-independent, so the output
+// is bit-identical run to run and identical to the reference's deterministic path.
+#include "common.cuh"
+
+#include <math.h>
+
+namespace orvb {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr unsigned long long kEmptyKey = ~0ull;
+constexpr int kItems = 8;                    // elements per thread in the scan / sort tiles
+constexpr int kTile = kThreads * kItems;     // 2048
+
+struct VoxGeom {
+  float lo[3];
+  float vs[3];
+  int32_t grid[3];
+};
+
+// floor((p - lo) / vs) per axis with IEEE subtraction / division (what the reference's CPU loop and its CUDA kernel
+// both evaluate: voxelization_cpu.cpp:21, voxelization_kernel.cuh:23-41); false when any axis leaves [0, grid).
+// NaN coordinates are invalid (CPU-reference behaviour: the cast of NaN to int is negative on x86).
+__device__ __forceinline__ bool voxel_cell(const VoxGeom& g, float px, float py, float pz, int& cx, int& cy, int& cz) {
+  const float fx = floorf(__fdiv_rn(__fsub_rn(px, g.lo[0]), g.vs[0]));
+  const float fy = floorf(__fdiv_rn(__fsub_rn(py, g.lo[1]), g.vs[1]));
+  const float fz = floorf(__fdiv_rn(__fsub_rn(pz, g.lo[2]), g.vs[2]));
+  const float lim = 2147483648.f;
+  if (!(fx >= 0.f && fx < lim && fy >= 0.f && fy < lim && fz >= 0.f && fz < lim)) return false;
+  cx = static_cast<int>(fx);
+  cy = static_cast<int>(fy);
+  cz = static_cast<int>(fz);
+  return cx < g.grid[0] && cy < g.grid[1] && cz < g.grid[2];
+}
+
+template <bool VEC4>
+__device__ __forceinline__ void load_xyz(const float* __restrict__ points, int64_t i, int c, float& x, float& y,
+                                         float& z) {
+  if (VEC4) {
+    const float4 p = __ldg(reinterpret_cast<const float4*>(points) + i);  // one coalesced 128-bit load per point
+    x = p.x; y = p.y; z = p.z;
+  } else {
+    const float* p = points + i * c;
+    x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2);
+  }
+}
+
+// ---- dynamic voxelization: coors[i] = (z, y, x) or (-1, -1, -1) ---------------------------------------------------
+template <bool VEC4>
+__global__ void __launch_bounds__(kThreads) dynamic_voxelize_kernel(const float* __restrict__ points, int n, int c,
+                                                                    VoxGeom g, int32_t* __restrict__ coors) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
+  if (i >= n) return;
+  float x, y, z;
+  load_xyz<VEC4>(points, i, c, x, y, z);
+  int cx, cy, cz;
+  const bool ok = voxel_cell(g, x, y, z, cx, cy, cz);
+  int32_t* o = coors + i * 3;
+  o[0] = ok ? cz : -1;
+  o[1] = ok ? cy : -1;
+  o[2] = ok ? cx : -1;
+}
+
+// ---- 1. cell + hash insert ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t hash_slot(unsigned long long key, int log2_slots) {
+  return static_cast<uint32_t>((key * 0x9E3779B97F4A7C15ull) >> (64 - log2_slots));
+}
+
+template <bool VEC4>
+__global__ void __launch_bounds__(kThreads) voxel_insert_kernel(const float* __restrict__ points, int n, int c, VoxGeom g,
+                                                                int32_t* __restrict__ cell /*[n,3] z,y,x*/,
+                                                                int32_t* __restrict__ slot_of /*[n]*/,
+                                                                unsigned long long* __restrict__ t_keys,
+                                                                int32_t* __restrict__ t_first, int log2_slots) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
+  if (i >= n) return;
+  float x, y, z;
+  load_xyz<VEC4>(points, i, c, x, y, z);
+  int cx, cy, cz;
+  const bool ok = voxel_cell(g, x, y, z, cx, cy, cz);
+  int32_t* o = cell + i * 3;
+  o[0] = ok ? cz : -1;
+  o[1] = ok ? cy : -1;
+  o[2] = ok ? cx : -1;
+  if (!ok) {
+    slot_of[i] = -1;
+    return;
+  }
+  const unsigned long long key =
+      (static_cast<unsigned long long>(cz) * static_cast<unsigned long long>(g.grid[1]) + cy) *
+          static_cast<unsigned long long>(g.grid[0]) + cx;
+  const uint32_t mask = (1u << log2_slots) - 1u;
+  uint32_t s = hash_slot(key, log2_slots);
+  while (true) {  // the table has >= 2n slots, so an empty one is always reachable
+    const unsigned long long prev = atomicCAS(&t_keys[s], kEmptyKey, key);
+    if (prev == kEmptyKey || prev == key) break;
+    s = (s + 1u) & mask;
+  }
+  atomicMin(&t_first[s], static_cast<int32_t>(i));
+  slot_of[i] = static_cast<int32_t>(s);
+}
+
+// ---- 2. first-of-voxel flags ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) first_flag_kernel(const int32_t* __restrict__ slot_of,
+                                                              const int32_t* __restrict__ t_first, int n,
+                                                              uint32_t* __restrict__ flag) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
+  if (i >= n) return;
+  const int32_t s = slot_of[i];
+  flag[i] = (s >= 0 && t_first[s] == static_cast<int32_t>(i)) ? 1u : 0u;
+}
+
+// ---- block-wide exclusive scan of one value per thread (256 threads) ------------------------------------------------
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t& total) {
+  __shared__ uint32_t warp_sums[kThreads / 32 + 1];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(kFull, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t w = (lane < kThreads / 32) ? warp_sums[lane] : 0u;
+    uint32_t winc = w;
+#pragma unroll
+    for (int o = 1; o < kThreads / 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(kFull, winc, o);
+      if (lane >= o) winc += t;
+    }
+    if (lane < kThreads / 32) warp_sums[lane] = winc - w;
+    if (lane == kThreads / 32 - 1) warp_sums[kThreads / 32] = winc;
+  }
+  __syncthreads();
+  const uint32_t res = warp_sums[warp] + inc - v;
+  total = warp_sums[kThreads / 32];
+  __syncthreads();  // warp_sums may be reused by the caller's next scan
+  return res;
+}
+
+// tile sums: sums[b] = sum of in[b*kTile .. (b+1)*kTile)
+__global__ void __launch_bounds__(kThreads) scan_reduce_kernel(const uint32_t* __restrict__ in, int64_t n,
+                                                               uint32_t* __restrict__ sums) {
+  const int64_t base = static_cast<int64_t>(blockIdx.x) * kTile + static_cast<int64_t>(threadIdx.x) * kItems;
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    if (base + k < n) s += in[base + k];
+  }
+  uint32_t total;
+  block_exclusive_scan(s, total);
+  if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+// exclusive scan of one tile (+ offsets[b]); in == out allowed (each thread reads its items before it writes them)
+__global__ void __launch_bounds__(kThreads) scan_tile_kernel(const uint32_t* in, uint32_t* out, int64_t n,
+                                                             const uint32_t* __restrict__ offsets,
+                                                             uint32_t* __restrict__ total_out) {
+  const int64_t base = static_cast<int64_t>(blockIdx.x) * kTile + static_cast<int64_t>(threadIdx.x) * kItems;
+  uint32_t v[kItems];
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    v[k] = (base + k < n) ? in[base + k] : 0u;
+    s += v[k];
+  }
+  uint32_t total;
+  uint32_t run = block_exclusive_scan(s, total);
+  if (offsets != nullptr) run += offsets[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    if (base + k < n) out[base + k] = run;
+    run += v[k];
+  }
+  if (total_out != nullptr && threadIdx.x == 0 && gridDim.x == 1) *total_out = total;
+}
+
+inline int64_t tiles_of(int64_t n) { return (n + kTile - 1) / kTile; }
+inline size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+// scratch (uint32 entries) needed by scan_u32 for n inputs
+size_t scan_scratch_entries(int64_t n) {
+  size_t e = 0;
+  while (n > kTile) {
+    n = tiles_of(n);
+    e += align256(static_cast<size_t>(n) * 4) / 4;
+  }
+  return e + 64;
+}
+
+// exclusive scan of n uint32 (in == out allowed); *total_out (device) = sum of all inputs
+int scan_u32(const uint32_t* in, uint32_t* out, int64_t n, uint32_t* scratch, uint32_t* total_out, cudaStream_t st) {
+  const int64_t nb = tiles_of(n);
+  if (nb <= 1) {
+    scan_tile_kernel<<<1, kThreads, 0, st>>>(in, out, n, nullptr, total_out);
+    ORVB_CHECK_CUDA(cudaGetLastError());
+    return ORVB_OK;
+  }
+  scan_reduce_kernel<<<static_cast<unsigned>(nb), kThreads, 0, st>>>(in, n, scratch);
+  ORVB_CHECK_CUDA(cudaGetLastError());
+  uint32_t* next = scratch + align256(static_cast<size_t>(nb) * 4) / 4;
+  const int rc = scan_u32(scratch, scratch, nb, next, total_out, st);
+  if (rc != ORVB_OK) return rc;
+  scan_tile_kernel<<<static_cast<unsigned>(nb), kThreads, 0, st>>>(in, out, n, scratch, nullptr);
+  ORVB_CHECK_CUDA(cudaGetLastError());
+  return ORVB_OK;
+}
+
+// ---- 3. voxel numbers -> sort keys ------------------------------------------------------------------------------------
+// t_vid[slot] = voxel number (order of first appearance), written by the voxel's first point.
+__global__ void __launch_bounds__(kThreads) number_slots_kernel(const int32_t* __restrict__ slot_of,
+                                                                const int32_t* __restrict__ t_first,
+                                                                const uint32_t* __restrict__ order, int n,
+                                                                int32_t* __restrict__ t_vid) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
+  if (i >= n) return;
+  const int32_t s = slot_of[i];
+  if (s >= 0 && t_first[s] == static_cast<int32_t>(i)) t_vid[s] = static_cast<int32_t>(order[i]);
+}
+
+// key[i] = voxel number, or `cap` (sorts last) for invalid points and voxels beyond max_voxels
+// (voxelization_cpu.cpp:83: a new voxel is refused once voxel_num >= max_voxels, and so are its later points).
+__global__ void __launch_bounds__(kThreads) sort_key_kernel(const int32_t* __restrict__ slot_of,
+                                                            const int32_t* __restrict__ t_vid, int n, uint32_t cap,
+                                                            uint32_t* __restrict__ key,
+                                                            const uint32_t* __restrict__ total_voxels,
+                                                            long long* __restrict__ voxel_num) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
+  if (i == 0 && voxel_num != nullptr) *voxel_num = static_cast<long long>(min(*total_voxels, cap));
+  if (i >= n) return;
+  const int32_t s = slot_of[i];
+  uint32_t k = cap;
+  if (s >= 0) {
+    const uint32_t v = static_cast<uint32_t>(t_vid[s]);
+    if (v < cap) k = v;
+  }
+  key[i] = k;
+}
+
+// ---- 4. stable LSD radix sort, 8 bits per pass ------------------------------------------------------------------------
+// hist[d * nblocks + b] = number of keys of tile b whose digit is d (digit-major, so one exclusive scan over the
+// whole array yields the global start of (digit d, tile b)).
+__global__ void __launch_bounds__(kThreads) radix_hist_kernel(const uint32_t* __restrict__ keys, int n, int shift,
+                                                              uint32_t* __restrict__ hist, int nblocks) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t base = static_cast<int64_t>(blockIdx.x) * kTile;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    const int64_t idx = base + k * kThreads + threadIdx.x;
+    if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  hist[static_cast<size_t>(threadIdx.x) * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+// Scatter of one tile.  Warp w owns the 256 consecutive elements [tile + 256 w, tile + 256 (w+1)) and walks them 32
+// at a time, so (warp, iteration, lane) order = element order: ranks by __match_any_sync peers below the lane keep
+// the sort stable.  vin == nullptr means "value = element index" (first pass).
+__global__ void __launch_bounds__(kThreads) radix_scatter_kernel(const uint32_t* __restrict__ kin,
+                                                                 const uint32_t* __restrict__ vin,
+                                                                 uint32_t* __restrict__ kout, uint32_t* __restrict__ vout,
+                                                                 int n, int shift, const uint32_t* __restrict__ offs,
+                                                                 int nblocks) {
+  __shared__ uint32_t wh[kThreads / 32][256];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) wh[w][threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t wbase = static_cast<int64_t>(blockIdx.x) * kTile + warp * (32 * kItems);
+  // A: per-warp digit histogram
+  for (int it = 0; it < kItems; ++it) {
+    const int64_t idx = wbase + it * 32 + lane;
+    const bool act = idx < n;
+    const uint32_t d = act ? ((kin[idx] >> shift) & 255u) : (256u + lane);  // inactive lanes match nobody
+    const unsigned peers = __match_any_sync(kFull, d);
+    if (act && lane == __ffs(peers) - 1) wh[warp][d] += __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  // B: thread d turns the per-warp counts of digit d into global start positions
+  {
+    const int d = threadIdx.x;
+    uint32_t run = offs[static_cast<size_t>(d) * nblocks + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) {
+      const uint32_t t = wh[w][d];
+      wh[w][d] = run;
+      run += t;
+    }
+  }
+  __syncthreads();
+  // C: stable scatter
+  for (int it = 0; it < kItems; ++it) {
+    const int64_t idx = wbase + it * 32 + lane;
+    const bool act = idx < n;
+    const uint32_t key = act ? kin[idx] : 0u;
+    const uint32_t d = act ? ((key >> shift) & 255u) : (256u + lane);
+    const unsigned peers = __match_any_sync(kFull, d);
+    const uint32_t start = act ? wh[warp][d] : 0u;
+    __syncwarp();  // every lane has read its start before a leader advances it
+    if (act) {
+      const uint32_t dest = start + __popc(peers & ((1u << lane) - 1u));
+      kout[dest] = key;
+      vout[dest] = (vin != nullptr) ? vin[idx] : static_cast<uint32_t>(idx);
+      if (lane == __ffs(peers) - 1) wh[warp][d] = start + __popc(peers);
+    }
+    __syncwarp();
+  }
+}
+
+// ---- 5. segments + gather ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) segment_kernel(const uint32_t* __restrict__ skey, int n, uint32_t cap,
+                                                           int32_t* __restrict__ seg_start,
+                                                           int32_t* __restrict__ seg_end) {
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
+  if (p >= n) return;
+  const uint32_t v = skey[p];
+  if (v >= cap) return;
+  if (p == 0 || skey[p - 1] != v) seg_start[v] = static_cast<int32_t>(p);
+  if (p == n - 1 || skey[p + 1] != v) seg_end[v] = static_cast<int32_t>(p + 1);
+}
+
+template <bool VEC4>
+__global__ void __launch_bounds__(kThreads) gather_kernel(const float* __restrict__ points, int n, int c,
+                                                          const uint32_t* __restrict__ skey,
+                                                          const uint32_t* __restrict__ sval, uint32_t cap,
+                                                          const int32_t* __restrict__ seg_start,
+                                                          const int32_t* __restrict__ seg_end,
+                                                          const int32_t* __restrict__ cell, int max_points,
+                                                          float* __restrict__ voxels, int32_t* __restrict__ coors,
+                                                          int32_t* __restrict__ num_points) {
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
+  if (p >= n) return;
+  const uint32_t v = skey[p];
+  if (v >= cap) return;
+  const int32_t start = seg_start[v];
+  const int32_t rank = static_cast<int32_t>(p) - start;
+  const uint32_t idx = sval[p];
+  if (rank == 0) {
+    if (coors != nullptr) {
+      coors[3 * static_cast<size_t>(v) + 0] = cell[3 * static_cast<size_t>(idx) + 0];
+      coors[3 * static_cast<size_t>(v) + 1] = cell[3 * static_cast<size_t>(idx) + 1];
+      coors[3 * static_cast<size_t>(v) + 2] = cell[3 * static_cast<size_t>(idx) + 2];
+    }
+    if (num_points != nullptr) num_points[v] = min(seg_end[v] - start, max_points);
+  }
+  if (voxels == nullptr || rank >= max_points) return;
+  const size_t dst = (static_cast<size_t>(v) * max_points + rank) * c;
+  if (VEC4) {
+    *reinterpret_cast<float4*>(voxels + dst) = __ldg(reinterpret_cast<const float4*>(points) + idx);
+  } else {
+    const float* src = points + static_cast<size_t>(idx) * c;
+    for (int k = 0; k < c; ++k) voxels[dst + k] = __ldg(src + k);
+  }
+}
+
+// ---- 6. label vote (points_to_voxels, prepare_dataset.py:176-196) ------------------------------------------------------
+// One warp per voxel.  The label of a point is its LAST feature; the reference counts labels over the max_points
+// slots of the voxel (unfilled slots hold 0), sorts the counts in descending order (stable on the host: ties go to the
+// smaller label) and takes the runner-up when the winner is 0.  out[v] = (x, y, z, label - 1) as float64, the dtype
+// numpy gives the reference's concatenate of int32 coordinates and float32 labels.
+struct Vote {
+  int count;
+  float value;
+};
+__device__ __forceinline__ bool vote_better(const Vote& a, const Vote& b) {  // a strictly ahead of b
+  return a.count > b.count || (a.count == b.count && a.count > 0 && a.value < b.value);
+}
+__device__ __forceinline__ Vote vote_warp_best(Vote v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Vote t;
+    t.count = __shfl_xor_sync(kFull, v.count, o);
+    t.value = __shfl_xor_sync(kFull, v.value, o);
+    if (vote_better(t, v)) v = t;
+  }
+  return v;
+}
+
+constexpr int kVoteStage = 128;  // labels of a voxel staged in shared memory (per warp); the rest re-read from L2
+
+__global__ void __launch_bounds__(kThreads) label_vote_kernel(const float* __restrict__ points, int c,
+                                                              const uint32_t* __restrict__ sval,
+                                                              const int32_t* __restrict__ seg_start,
+                                                              const int32_t* __restrict__ seg_end,
+                                                              const int32_t* __restrict__ cell, int max_points,
+                                                              const long long* __restrict__ voxel_num,
+                                                              double* __restrict__ out) {
+  __shared__ float stage[kThreads / 32][kVoteStage];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long nv = *voxel_num;
+  const long long v = static_cast<long long>(blockIdx.x) * (kThreads / 32) + warp;
+  if (v >= nv) return;
+  const int32_t start = seg_start[v];
+  const int kept = min(seg_end[v] - start, max_points);
+  const int pad = max_points - kept;
+  float* my = stage[warp];
+  for (int e = lane; e < kept && e < kVoteStage; e += 32)
+    my[e] = __ldg(points + static_cast<size_t>(sval[start + e]) * c + (c - 1));
+  __syncwarp();
+  auto label_at = [&](int e) -> float {
+    return e < kVoteStage ? my[e] : __ldg(points + static_cast<size_t>(sval[start + e]) * c + (c - 1));
+  };
+  Vote best_all = {0, 0.f}, best_nz = {0, 0.f};
+  if (lane == 0 && pad > 0) {  // the empty slots: label 0
+    int cnt = pad;
+    for (int f = 0; f < kept; ++f) cnt += (label_at(f) == 0.f) ? 1 : 0;
+    best_all.count = cnt;
+    best_all.value = 0.f;
+  }
+  for (int e = lane; e < kept; e += 32) {
+    const float le = label_at(e);
+    int cnt = (le == 0.f) ? pad : 0;
+    for (int f = 0; f < kept; ++f) cnt += (label_at(f) == le) ? 1 : 0;
+    Vote cand = {cnt, le};
+    if (vote_better(cand, best_all)) best_all = cand;
+    if (le != 0.f && vote_better(cand, best_nz)) best_nz = cand;
+  }
+  best_all = vote_warp_best(best_all);
+  best_nz = vote_warp_best(best_nz);
+  if (lane == 0) {
+    const float top = (best_all.value == 0.f && best_nz.count > 0) ? best_nz.value : best_all.value;
+    const uint32_t idx = sval[start];
+    double* o = out + 4 * v;
+    o[0] = static_cast<double>(cell[3 * static_cast<size_t>(idx) + 2]);
+    o[1] = static_cast<double>(cell[3 * static_cast<size_t>(idx) + 1]);
+    o[2] = static_cast<double>(cell[3 * static_cast<size_t>(idx) + 0]);
+    o[3] = static_cast<double>(top - 1.f);
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------------------
+int make_geom(const float* voxel_size, const float* coors_range, VoxGeom* g) {
+  for (int i = 0; i < 3; ++i) {
+    ORVB_REQUIRE(voxel_size[i] > 0.f, ORVB_EINVAL, "voxelize: voxel_size[%d] = %g must be positive", i, voxel_size[i]);
+    g->lo[i] = coors_range[i];
+    g->vs[i] = voxel_size[i];
+    // grid_size = round((max - min) / voxel) in float, as voxelization_cpu.cpp:120-123 / voxelization_kernel.cu:28-30
+    const float extent = (coors_range[3 + i] - coors_range[i]) / voxel_size[i];
+    const double r = round(static_cast<double>(extent));
+    ORVB_REQUIRE(r >= 0 && r < 2147483648.0, ORVB_ESHAPE, "voxelize: grid extent %g on axis %d is out of range", r, i);
+    g->grid[i] = static_cast<int32_t>(r);
+  }
+  // the 64-bit cell key (z * gy + y) * gx + x must stay below the empty-slot marker
+  ORVB_REQUIRE(static_cast<double>(g->grid[0]) * g->grid[1] * g->grid[2] < 1.8e19, ORVB_ESHAPE,
+               "voxelize: grid %d x %d x %d has more than 2^64 cells", g->grid[0], g->grid[1], g->grid[2]);
+  return ORVB_OK;
+}
+
+struct VoxWorkspace {
+  int log2_slots;
+  size_t slots;
+  uint32_t cap;
+  int passes;
+  int nblocks;
+  size_t off_cell, off_slot, off_keys, off_first, off_vid, off_flag, off_scan, off_total, off_ka, off_va, off_kb, off_vb,
+      off_hist, off_seg_start, off_seg_end, bytes;
+};
+
+VoxWorkspace plan_workspace(int32_t n, int32_t max_voxels) {
+  VoxWorkspace w = {};
+  const size_t nn = static_cast<size_t>(n > 0 ? n : 1);
+  w.log2_slots = 10;
+  while ((static_cast<size_t>(1) << w.log2_slots) < 2 * nn) ++w.log2_slots;
+  w.slots = static_cast<size_t>(1) << w.log2_slots;
+  w.cap = static_cast<uint32_t>(n < max_voxels ? n : max_voxels);
+  int bits = 1;
+  while ((1ull << bits) <= w.cap) ++bits;  // keys take values 0..cap
+  w.passes = (bits + 7) / 8;
+  w.nblocks = static_cast<int>(tiles_of(static_cast<int64_t>(nn)));
+  const size_t hist_entries = static_cast<size_t>(256) * w.nblocks;
+  const size_t scan_entries = scan_scratch_entries(static_cast<int64_t>(hist_entries > nn ? hist_entries : nn));
+  size_t o = 0;
+  auto take = [&](size_t bytes) { const size_t at = o; o += align256(bytes); return at; };
+  w.off_cell = take(nn * 12);
+  w.off_slot = take(nn * 4);
+  w.off_keys = take(w.slots * 8);
+  w.off_first = take(w.slots * 4);
+  w.off_vid = take(w.slots * 4);
+  w.off_flag = take(nn * 4);
+  w.off_scan = take(scan_entries * 4);
+  w.off_total = take(256);
+  w.off_ka = take(nn * 4);
+  w.off_va = take(nn * 4);
+  w.off_kb = take(nn * 4);
+  w.off_vb = take(nn * 4);
+  w.off_hist = take(hist_entries * 4);
+  w.off_seg_start = take((static_cast<size_t>(w.cap) + 1) * 4);
+  w.off_seg_end = take((static_cast<size_t>(w.cap) + 1) * 4);
+  w.bytes = o;
+  return w;
+}
+
+}  // namespace
+}  // namespace orvb
+
+using namespace orvb;
+
+extern "C" int orvb_dynamic_voxelize(const float* points, int32_t n, int32_t c, const float* voxel_size,
+                                     const float* coors_range, int32_t* coors, void* stream) {
+  int rc = check_arch();
+  if (rc != ORVB_OK) return rc;
+  ORVB_REQUIRE(voxel_size != nullptr && coors_range != nullptr, ORVB_EINVAL, "dynamic_voxelize: null geometry");
+  ORVB_REQUIRE(n >= 0 && c >= 3, ORVB_ESHAPE, "dynamic_voxelize: points must be [n, >= 3], got [%d, %d]", n, c);
+  if (n == 0) return ORVB_OK;
+  ORVB_REQUIRE(points != nullptr && coors != nullptr, ORVB_EINVAL, "dynamic_voxelize: null pointer");
+  VoxGeom g;
+  rc = make_geom(voxel_size, coors_range, &g);
+  if (rc != ORVB_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned blocks = static_cast<unsigned>((static_cast<int64_t>(n) + kThreads - 1) / kThreads);
+  const bool vec4 = (c == 4) && (reinterpret_cast<uintptr_t>(points) % 16 == 0);
+  if (vec4)
+    dynamic_voxelize_kernel<true><<<blocks, kThreads, 0, st>>>(points, n, c, g, coors);
+  else
+    dynamic_voxelize_kernel<false><<<blocks, kThreads, 0, st>>>(points, n, c, g, coors);
+  ORVB_CHECK_CUDA(cudaGetLastError());
+  return ORVB_OK;
+}
+
+extern "C" size_t orvb_voxelize_workspace_bytes(int32_t n, int32_t max_voxels) {
+  if (n < 0 || max_voxels <= 0) return 0;
+  return plan_workspace(n, max_voxels).bytes;
+}
+
+extern "C" int orvb_hard_voxelize(const orvb_voxelize_args* a, void* stream) {
+  int rc = check_arch();
+  if (rc != ORVB_OK) return rc;
+  ORVB_REQUIRE(a != nullptr, ORVB_EINVAL, "hard_voxelize: null args");
+  ORVB_REQUIRE(a->n >= 0 && a->n < (1 << 30) && a->c >= 3, ORVB_ESHAPE,
+               "hard_voxelize: points must be [n < 2^30, >= 3], got [%d, %d]", a->n, a->c);
+  ORVB_REQUIRE(a->max_points > 0 && a->max_voxels > 0, ORVB_EINVAL,
+               "hard_voxelize: max_points = %d and max_voxels = %d must be positive (use orvb_dynamic_voxelize for -1)",
+               a->max_points, a->max_voxels);
+  ORVB_REQUIRE(a->voxel_num != nullptr, ORVB_EINVAL, "hard_voxelize: voxel_num is required");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a->n == 0) {
+    ORVB_CHECK_CUDA(cudaMemsetAsync(a->voxel_num, 0, sizeof(int64_t), st));
+    return ORVB_OK;
+  }
+  ORVB_REQUIRE(a->points != nullptr && a->workspace != nullptr, ORVB_EINVAL, "hard_voxelize: null pointer");
+  VoxGeom g;
+  rc = make_geom(a->voxel_size, a->coors_range, &g);
+  if (rc != ORVB_OK) return rc;
+  const VoxWorkspace w = plan_workspace(a->n, a->max_voxels);
+  ORVB_REQUIRE(a->workspace_bytes >= w.bytes, ORVB_ENOMEM, "hard_voxelize: workspace %zu < %zu bytes",
+               a->workspace_bytes, w.bytes);
+  ORVB_REQUIRE(reinterpret_cast<uintptr_t>(a->workspace) % 256 == 0, ORVB_ESHAPE,
+               "hard_voxelize: workspace must be 256-byte aligned");
+  char* base = static_cast<char*>(a->workspace);
+  int32_t* cell = reinterpret_cast<int32_t*>(base + w.off_cell);
+  int32_t* slot_of = reinterpret_cast<int32_t*>(base + w.off_slot);
+  unsigned long long* t_keys = reinterpret_cast<unsigned long long*>(base + w.off_keys);
+  int32_t* t_first = reinterpret_cast<int32_t*>(base + w.off_first);
+  int32_t* t_vid = reinterpret_cast<int32_t*>(base + w.off_vid);
+  uint32_t* flag = reinterpret_cast<uint32_t*>(base + w.off_flag);
+  uint32_t* scan_scratch = reinterpret_cast<uint32_t*>(base + w.off_scan);
+  uint32_t* total = reinterpret_cast<uint32_t*>(base + w.off_total);
+  uint32_t* ka = reinterpret_cast<uint32_t*>(base + w.off_ka);
+  uint32_t* va = reinterpret_cast<uint32_t*>(base + w.off_va);
+  uint32_t* kb = reinterpret_cast<uint32_t*>(base + w.off_kb);
+  uint32_t* vb = reinterpret_cast<uint32_t*>(base + w.off_vb);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(base + w.off_hist);
+  int32_t* seg_start = reinterpret_cast<int32_t*>(base + w.off_seg_start);
+  int32_t* seg_end = reinterpret_cast<int32_t*>(base + w.off_seg_end);
+
+  const int n = a->n;
+  const unsigned blocks = static_cast<unsigned>((static_cast<int64_t>(n) + kThreads - 1) / kThreads);
+  const bool vec4 = (a->c == 4) && (reinterpret_cast<uintptr_t>(a->points) % 16 == 0);
+  const bool vec4_out = vec4 && (a->voxels == nullptr || reinterpret_cast<uintptr_t>(a->voxels) % 16 == 0);
+
+  ORVB_CHECK_CUDA(cudaMemsetAsync(t_keys, 0xff, w.slots * 8, st));
+  ORVB_CHECK_CUDA(cudaMemsetAsync(t_first, 0x7f, w.slots * 4, st));
+  if (vec4)
+    voxel_insert_kernel<true><<<blocks, kThreads, 0, st>>>(a->points, n, a->c, g, cell, slot_of, t_keys, t_first,
+                                                          w.log2_slots);
+  else
+    voxel_insert_kernel<false><<<blocks, kThreads, 0, st>>>(a->points, n, a->c, g, cell, slot_of, t_keys, t_first,
+                                                           w.log2_slots);
+  ORVB_CHECK_CUDA(cudaGetLastError());
+  first_flag_kernel<<<blocks, kThreads, 0, st>>>(slot_of, t_first, n, flag);
+  ORVB_CHECK_CUDA(cudaGetLastError());
+  rc = scan_u32(flag, flag, n, scan_scratch, total, st);
+  if (rc != ORVB_OK) return rc;
+  number_slots_kernel<<<blocks, kThreads, 0, st>>>(slot_of, t_first, flag, n, t_vid);
+  ORVB_CHECK_CUDA(cudaGetLastError());
+  sort_key_kernel<<<blocks, kThreads, 0, st>>>(slot_of, t_vid, n, w.cap, ka, total,
+                                              reinterpret_cast<long long*>(a->voxel_num));
+  ORVB_CHECK_CUDA(cudaGetLastError());
+
+  // stable LSD radix sort of (voxel number, point index)
+  const uint32_t* kin = ka;
+  const uint32_t* vin = nullptr;  // identity
+  uint32_t* kout = kb;
+  uint32_t* vout = vb;
+  for (int pass = 0; pass < w.passes; ++pass) {
+    const int shift = 8 * pass;
+    radix_hist_kernel<<<w.nblocks, kThreads, 0, st>>>(kin, n, shift, hist, w.nblocks);
+    ORVB_CHECK_CUDA(cudaGetLastError());
+    rc = scan_u32(hist, hist, static_cast<int64_t>(256) * w.nblocks, scan_scratch, nullptr, st);
+    if (rc != ORVB_OK) return rc;
+    radix_scatter_kernel<<<w.nblocks, kThreads, 0, st>>>(kin, vin, kout, vout, n, shift, hist, w.nblocks);
+    ORVB_CHECK_CUDA(cudaGetLastError());
+    kin = kout;
+    vin = vout;
+    kout = (kout == kb) ? ka : kb;
+    vout = (vout == vb) ? va : vb;
+  }
+  const uint32_t* skey = kin;
+  const uint32_t* sval = vin;
+
+  segment_kernel<<<blocks, kThreads, 0, st>>>(skey, n, w.cap, seg_start, seg_end);
+  ORVB_CHECK_CUDA(cudaGetLastError());
+  if (a->voxels != nullptr || a->coors != nullptr || a->num_points_per_voxel != nullptr) {
+    if (vec4_out)
+      gather_kernel<true><<<blocks, kThreads, 0, st>>>(a->points, n, a->c, skey, sval, w.cap, seg_start, seg_end, cell,
+                                                      a->max_points, a->voxels, a->coors, a->num_points_per_voxel);
+    else
+      gather_kernel<false><<<blocks, kThreads, 0, st>>>(a->points, n, a->c, skey, sval, w.cap, seg_start, seg_end, cell,
+                                                       a->max_points, a->voxels, a->coors, a->num_points_per_voxel);
+    ORVB_CHECK_CUDA(cudaGetLastError());
+  }
+  if (a->voxel_labels != nullptr) {
+    const unsigned vblocks = (w.cap + kThreads / 32 - 1) / (kThreads / 32);
+    if (vblocks > 0) {
+      label_vote_kernel<<<vblocks, kThreads, 0, st>>>(a->points, a->c, sval, seg_start, seg_end, cell, a->max_points,
+                                                     reinterpret_cast<const long long*>(a->voxel_num),
+                                                     a->voxel_labels);
+      ORVB_CHECK_CUDA(cudaGetLastError());
+    }
+  }
+  return ORVB_OK;
+}
