@@ -9,10 +9,11 @@
 //
 //   1. voxel_insert_kernel   128-bit point loads -> (z,y,x) cell -> open-addressing hash insert of the 64-bit cell
 //                            key, atomicMin of the point index per occupied slot (= first point of the voxel)
-//   2. first_flag_kernel     flag[i] = "point i is the first of its voxel"; exclusive scan -> voxel numbers in
-//                            first-appearance order, total voxel count
-//   3. sort_key_kernel       key[i] = voxel number (or the drop sentinel for invalid / over-cap voxels)
-//   4. stable LSD radix sort of (voxel number, point index), 8 bits per pass, ceil(log2(cap+1)/8) passes: points of a
+//   2. exclusive scan of the flags "point i is the first of its voxel" (evaluated inside the scan kernels) -> voxel
+//      numbers in first-appearance order, total voxel count
+//   3. sort_key_kernel       key[i] = voxel number of i's voxel = order[first point of the voxel] (or the drop
+//                            sentinel for invalid / over-cap voxels)
+//   4. stable LSD radix sort of (voxel number, point index), 9 bits per pass, ceil(log2(cap+1)/9) passes: points of a
 //      voxel end up contiguous and in index order, so "position in voxel" = sorted position - segment start
 //   5. segment_kernel / gather_kernel   segment bounds per voxel, feature copy of the first max_points points
 //   6. label_vote_kernel     (optional) one warp per voxel: most frequent label among the max_points slots of the
@@ -34,6 +35,8 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr unsigned long long kEmptyKey = ~0ull;
 constexpr int kItems = 8;                    // elements per thread in the scan / sort tiles
 constexpr int kTile = kThreads * kItems;     // 2048
+constexpr int kRadixBits = 9;                // 17-bit keys (max_voxels = 1e5, the occupancy caller) sort in two passes
+constexpr int kBins = 1 << kRadixBits;       // 512
 
 struct VoxGeom {
   float lo[3];
@@ -123,15 +126,19 @@ __global__ void __launch_bounds__(kThreads) voxel_insert_kernel(const float* __r
   slot_of[i] = static_cast<int32_t>(s);
 }
 
-// ---- 2. first-of-voxel flags ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) first_flag_kernel(const int32_t* __restrict__ slot_of,
-                                                              const int32_t* __restrict__ t_first, int n,
-                                                              uint32_t* __restrict__ flag) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
-  if (i >= n) return;
-  const int32_t s = slot_of[i];
-  flag[i] = (s >= 0 && t_first[s] == static_cast<int32_t>(i)) ? 1u : 0u;
-}
+// ---- 2. first-of-voxel flags (evaluated inside the scan kernels, never stored) ---------------------------------------
+struct LoadU32 {
+  const uint32_t* in;
+  __device__ __forceinline__ uint32_t operator()(int64_t i) const { return in[i]; }
+};
+struct LoadFirstFlag {  // 1 when point i is the first (lowest-index) point of its voxel
+  const int32_t* slot_of;
+  const int32_t* t_first;
+  __device__ __forceinline__ uint32_t operator()(int64_t i) const {
+    const int32_t s = __ldg(slot_of + i);
+    return (s >= 0 && __ldg(t_first + s) == static_cast<int32_t>(i)) ? 1u : 0u;
+  }
+};
 
 // ---- block-wide exclusive scan of one value per thread (256 threads) ------------------------------------------------
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t& total) {
@@ -165,13 +172,13 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t& t
 }
 
 // tile sums: sums[b] = sum of in[b*kTile .. (b+1)*kTile)
-__global__ void __launch_bounds__(kThreads) scan_reduce_kernel(const uint32_t* __restrict__ in, int64_t n,
-                                                               uint32_t* __restrict__ sums) {
+template <class Load>
+__global__ void __launch_bounds__(kThreads) scan_reduce_kernel(Load in, int64_t n, uint32_t* __restrict__ sums) {
   const int64_t base = static_cast<int64_t>(blockIdx.x) * kTile + static_cast<int64_t>(threadIdx.x) * kItems;
   uint32_t s = 0;
 #pragma unroll
   for (int k = 0; k < kItems; ++k) {
-    if (base + k < n) s += in[base + k];
+    if (base + k < n) s += in(base + k);
   }
   uint32_t total;
   block_exclusive_scan(s, total);
@@ -179,7 +186,8 @@ __global__ void __launch_bounds__(kThreads) scan_reduce_kernel(const uint32_t* _
 }
 
 // exclusive scan of one tile (+ offsets[b]); in == out allowed (each thread reads its items before it writes them)
-__global__ void __launch_bounds__(kThreads) scan_tile_kernel(const uint32_t* in, uint32_t* out, int64_t n,
+template <class Load>
+__global__ void __launch_bounds__(kThreads) scan_tile_kernel(Load in, uint32_t* out, int64_t n,
                                                              const uint32_t* __restrict__ offsets,
                                                              uint32_t* __restrict__ total_out) {
   const int64_t base = static_cast<int64_t>(blockIdx.x) * kTile + static_cast<int64_t>(threadIdx.x) * kItems;
@@ -187,7 +195,7 @@ __global__ void __launch_bounds__(kThreads) scan_tile_kernel(const uint32_t* in,
   uint32_t s = 0;
 #pragma unroll
   for (int k = 0; k < kItems; ++k) {
-    v[k] = (base + k < n) ? in[base + k] : 0u;
+    v[k] = (base + k < n) ? in(base + k) : 0u;
     s += v[k];
   }
   uint32_t total;
@@ -214,40 +222,38 @@ size_t scan_scratch_entries(int64_t n) {
   return e + 64;
 }
 
-// exclusive scan of n uint32 (in == out allowed); *total_out (device) = sum of all inputs
-int scan_u32(const uint32_t* in, uint32_t* out, int64_t n, uint32_t* scratch, uint32_t* total_out, cudaStream_t st) {
+// exclusive scan of n values produced by `in` (a LoadU32 over `out` itself is allowed: each thread reads its items
+// before it writes them); *total_out (device) = sum of all inputs
+template <class Load>
+int scan_any(Load in, uint32_t* out, int64_t n, uint32_t* scratch, uint32_t* total_out, cudaStream_t st) {
   const int64_t nb = tiles_of(n);
   if (nb <= 1) {
-    scan_tile_kernel<<<1, kThreads, 0, st>>>(in, out, n, nullptr, total_out);
+    scan_tile_kernel<Load><<<1, kThreads, 0, st>>>(in, out, n, nullptr, total_out);
     ORVB_CHECK_CUDA(cudaGetLastError());
     return ORVB_OK;
   }
-  scan_reduce_kernel<<<static_cast<unsigned>(nb), kThreads, 0, st>>>(in, n, scratch);
+  scan_reduce_kernel<Load><<<static_cast<unsigned>(nb), kThreads, 0, st>>>(in, n, scratch);
   ORVB_CHECK_CUDA(cudaGetLastError());
   uint32_t* next = scratch + align256(static_cast<size_t>(nb) * 4) / 4;
-  const int rc = scan_u32(scratch, scratch, nb, next, total_out, st);
+  const int rc = scan_any(LoadU32{scratch}, scratch, nb, next, total_out, st);
   if (rc != ORVB_OK) return rc;
-  scan_tile_kernel<<<static_cast<unsigned>(nb), kThreads, 0, st>>>(in, out, n, scratch, nullptr);
+  scan_tile_kernel<Load><<<static_cast<unsigned>(nb), kThreads, 0, st>>>(in, out, n, scratch, nullptr);
   ORVB_CHECK_CUDA(cudaGetLastError());
   return ORVB_OK;
 }
-
-// ---- 3. voxel numbers -> sort keys ------------------------------------------------------------------------------------
-// t_vid[slot] = voxel number (order of first appearance), written by the voxel's first point.
-__global__ void __launch_bounds__(kThreads) number_slots_kernel(const int32_t* __restrict__ slot_of,
-                                                                const int32_t* __restrict__ t_first,
-                                                                const uint32_t* __restrict__ order, int n,
-                                                                int32_t* __restrict__ t_vid) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
-  if (i >= n) return;
-  const int32_t s = slot_of[i];
-  if (s >= 0 && t_first[s] == static_cast<int32_t>(i)) t_vid[s] = static_cast<int32_t>(order[i]);
+inline int scan_u32(const uint32_t* in, uint32_t* out, int64_t n, uint32_t* scratch, uint32_t* total_out,
+                    cudaStream_t st) {
+  return scan_any(LoadU32{in}, out, n, scratch, total_out, st);
 }
 
-// key[i] = voxel number, or `cap` (sorts last) for invalid points and voxels beyond max_voxels
-// (voxelization_cpu.cpp:83: a new voxel is refused once voxel_num >= max_voxels, and so are its later points).
+// ---- 3. voxel numbers -> sort keys ------------------------------------------------------------------------------------
+// order[] = exclusive scan of the first-point flags, so order[f] is the voxel number (order of first appearance) of
+// the voxel whose first point is f.  key[i] = that number, or `cap` (sorts last) for invalid points and voxels beyond
+// max_voxels (voxelization_cpu.cpp:83: a new voxel is refused once voxel_num >= max_voxels, and so are its later
+// points).
 __global__ void __launch_bounds__(kThreads) sort_key_kernel(const int32_t* __restrict__ slot_of,
-                                                            const int32_t* __restrict__ t_vid, int n, uint32_t cap,
+                                                            const int32_t* __restrict__ t_first,
+                                                            const uint32_t* __restrict__ order, int n, uint32_t cap,
                                                             uint32_t* __restrict__ key,
                                                             const uint32_t* __restrict__ total_voxels,
                                                             long long* __restrict__ voxel_num) {
@@ -257,28 +263,28 @@ __global__ void __launch_bounds__(kThreads) sort_key_kernel(const int32_t* __res
   const int32_t s = slot_of[i];
   uint32_t k = cap;
   if (s >= 0) {
-    const uint32_t v = static_cast<uint32_t>(t_vid[s]);
+    const uint32_t v = order[t_first[s]];
     if (v < cap) k = v;
   }
   key[i] = k;
 }
 
-// ---- 4. stable LSD radix sort, 8 bits per pass ------------------------------------------------------------------------
+// ---- 4. stable LSD radix sort, kRadixBits bits per pass ----------------------------------------------------------------
 // hist[d * nblocks + b] = number of keys of tile b whose digit is d (digit-major, so one exclusive scan over the
 // whole array yields the global start of (digit d, tile b)).
 __global__ void __launch_bounds__(kThreads) radix_hist_kernel(const uint32_t* __restrict__ keys, int n, int shift,
                                                               uint32_t* __restrict__ hist, int nblocks) {
-  __shared__ uint32_t h[256];
-  h[threadIdx.x] = 0;
+  __shared__ uint32_t h[kBins];
+  for (int d = threadIdx.x; d < kBins; d += kThreads) h[d] = 0;
   __syncthreads();
   const int64_t base = static_cast<int64_t>(blockIdx.x) * kTile;
 #pragma unroll
   for (int k = 0; k < kItems; ++k) {
     const int64_t idx = base + k * kThreads + threadIdx.x;
-    if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & 255u], 1u);
+    if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & (kBins - 1)], 1u);
   }
   __syncthreads();
-  hist[static_cast<size_t>(threadIdx.x) * nblocks + blockIdx.x] = h[threadIdx.x];
+  for (int d = threadIdx.x; d < kBins; d += kThreads) hist[static_cast<size_t>(d) * nblocks + blockIdx.x] = h[d];
 }
 
 // Scatter of one tile.  Warp w owns the 256 consecutive elements [tile + 256 w, tile + 256 (w+1)) and walks them 32
@@ -289,26 +295,25 @@ __global__ void __launch_bounds__(kThreads) radix_scatter_kernel(const uint32_t*
                                                                  uint32_t* __restrict__ kout, uint32_t* __restrict__ vout,
                                                                  int n, int shift, const uint32_t* __restrict__ offs,
                                                                  int nblocks) {
-  __shared__ uint32_t wh[kThreads / 32][256];
+  __shared__ uint32_t wh[kThreads / 32][kBins];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int w = 0; w < kThreads / 32; ++w) wh[w][threadIdx.x] = 0;
+  for (int w = 0; w < kThreads / 32; ++w)
+    for (int d = threadIdx.x; d < kBins; d += kThreads) wh[w][d] = 0;
   __syncthreads();
   const int64_t wbase = static_cast<int64_t>(blockIdx.x) * kTile + warp * (32 * kItems);
   // A: per-warp digit histogram
   for (int it = 0; it < kItems; ++it) {
     const int64_t idx = wbase + it * 32 + lane;
     const bool act = idx < n;
-    const uint32_t d = act ? ((kin[idx] >> shift) & 255u) : (256u + lane);  // inactive lanes match nobody
+    const uint32_t d = act ? ((kin[idx] >> shift) & (kBins - 1)) : (kBins + lane);  // inactive lanes match nobody
     const unsigned peers = __match_any_sync(kFull, d);
     if (act && lane == __ffs(peers) - 1) wh[warp][d] += __popc(peers);
     __syncwarp();
   }
   __syncthreads();
-  // B: thread d turns the per-warp counts of digit d into global start positions
-  {
-    const int d = threadIdx.x;
+  // B: per digit, turn the per-warp counts into global start positions
+  for (int d = threadIdx.x; d < kBins; d += kThreads) {
     uint32_t run = offs[static_cast<size_t>(d) * nblocks + blockIdx.x];
 #pragma unroll
     for (int w = 0; w < kThreads / 32; ++w) {
@@ -323,7 +328,7 @@ __global__ void __launch_bounds__(kThreads) radix_scatter_kernel(const uint32_t*
     const int64_t idx = wbase + it * 32 + lane;
     const bool act = idx < n;
     const uint32_t key = act ? kin[idx] : 0u;
-    const uint32_t d = act ? ((key >> shift) & 255u) : (256u + lane);
+    const uint32_t d = act ? ((key >> shift) & (kBins - 1)) : (kBins + lane);
     const unsigned peers = __match_any_sync(kFull, d);
     const uint32_t start = act ? wh[warp][d] : 0u;
     __syncwarp();  // every lane has read its start before a leader advances it
@@ -483,7 +488,7 @@ struct VoxWorkspace {
   uint32_t cap;
   int passes;
   int nblocks;
-  size_t off_cell, off_slot, off_keys, off_first, off_vid, off_flag, off_scan, off_total, off_ka, off_va, off_kb, off_vb,
+  size_t off_cell, off_slot, off_keys, off_first, off_flag, off_scan, off_total, off_ka, off_va, off_kb, off_vb,
       off_hist, off_seg_start, off_seg_end, bytes;
 };
 
@@ -496,9 +501,9 @@ VoxWorkspace plan_workspace(int32_t n, int32_t max_voxels) {
   w.cap = static_cast<uint32_t>(n < max_voxels ? n : max_voxels);
   int bits = 1;
   while ((1ull << bits) <= w.cap) ++bits;  // keys take values 0..cap
-  w.passes = (bits + 7) / 8;
+  w.passes = (bits + kRadixBits - 1) / kRadixBits;
   w.nblocks = static_cast<int>(tiles_of(static_cast<int64_t>(nn)));
-  const size_t hist_entries = static_cast<size_t>(256) * w.nblocks;
+  const size_t hist_entries = static_cast<size_t>(kBins) * w.nblocks;
   const size_t scan_entries = scan_scratch_entries(static_cast<int64_t>(hist_entries > nn ? hist_entries : nn));
   size_t o = 0;
   auto take = [&](size_t bytes) { const size_t at = o; o += align256(bytes); return at; };
@@ -506,7 +511,6 @@ VoxWorkspace plan_workspace(int32_t n, int32_t max_voxels) {
   w.off_slot = take(nn * 4);
   w.off_keys = take(w.slots * 8);
   w.off_first = take(w.slots * 4);
-  w.off_vid = take(w.slots * 4);
   w.off_flag = take(nn * 4);
   w.off_scan = take(scan_entries * 4);
   w.off_total = take(256);
@@ -582,7 +586,6 @@ extern "C" int orvb_hard_voxelize(const orvb_voxelize_args* a, void* stream) {
   int32_t* slot_of = reinterpret_cast<int32_t*>(base + w.off_slot);
   unsigned long long* t_keys = reinterpret_cast<unsigned long long*>(base + w.off_keys);
   int32_t* t_first = reinterpret_cast<int32_t*>(base + w.off_first);
-  int32_t* t_vid = reinterpret_cast<int32_t*>(base + w.off_vid);
   uint32_t* flag = reinterpret_cast<uint32_t*>(base + w.off_flag);
   uint32_t* scan_scratch = reinterpret_cast<uint32_t*>(base + w.off_scan);
   uint32_t* total = reinterpret_cast<uint32_t*>(base + w.off_total);
@@ -608,13 +611,11 @@ extern "C" int orvb_hard_voxelize(const orvb_voxelize_args* a, void* stream) {
     voxel_insert_kernel<false><<<blocks, kThreads, 0, st>>>(a->points, n, a->c, g, cell, slot_of, t_keys, t_first,
                                                            w.log2_slots);
   ORVB_CHECK_CUDA(cudaGetLastError());
-  first_flag_kernel<<<blocks, kThreads, 0, st>>>(slot_of, t_first, n, flag);
-  ORVB_CHECK_CUDA(cudaGetLastError());
-  rc = scan_u32(flag, flag, n, scan_scratch, total, st);
+  // order[i] = number of voxels whose first point precedes i (flags evaluated on the fly, never stored)
+  uint32_t* order = flag;
+  rc = scan_any(LoadFirstFlag{slot_of, t_first}, order, n, scan_scratch, total, st);
   if (rc != ORVB_OK) return rc;
-  number_slots_kernel<<<blocks, kThreads, 0, st>>>(slot_of, t_first, flag, n, t_vid);
-  ORVB_CHECK_CUDA(cudaGetLastError());
-  sort_key_kernel<<<blocks, kThreads, 0, st>>>(slot_of, t_vid, n, w.cap, ka, total,
+  sort_key_kernel<<<blocks, kThreads, 0, st>>>(slot_of, t_first, order, n, w.cap, ka, total,
                                               reinterpret_cast<long long*>(a->voxel_num));
   ORVB_CHECK_CUDA(cudaGetLastError());
 
@@ -624,10 +625,10 @@ extern "C" int orvb_hard_voxelize(const orvb_voxelize_args* a, void* stream) {
   uint32_t* kout = kb;
   uint32_t* vout = vb;
   for (int pass = 0; pass < w.passes; ++pass) {
-    const int shift = 8 * pass;
+    const int shift = kRadixBits * pass;
     radix_hist_kernel<<<w.nblocks, kThreads, 0, st>>>(kin, n, shift, hist, w.nblocks);
     ORVB_CHECK_CUDA(cudaGetLastError());
-    rc = scan_u32(hist, hist, static_cast<int64_t>(256) * w.nblocks, scan_scratch, nullptr, st);
+    rc = scan_u32(hist, hist, static_cast<int64_t>(kBins) * w.nblocks, scan_scratch, nullptr, st);
     if (rc != ORVB_OK) return rc;
     radix_scatter_kernel<<<w.nblocks, kThreads, 0, st>>>(kin, vin, kout, vout, n, shift, hist, w.nblocks);
     ORVB_CHECK_CUDA(cudaGetLastError());

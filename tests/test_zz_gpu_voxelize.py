@@ -59,10 +59,11 @@ def test_hard_golden(name):
 @pytest.mark.parametrize("seed,n,c,mp,mv,cell", [
     (21, 1, 4, 3, 3, 0.05),             # a single point
     (22, 2047, 4, 2, 50, 0.05),         # one tile minus one
-    (23, 2049, 3, 5, 100000, 0.01),     # tile + 1, scalar-load path, 3 sort passes
+    (23, 2049, 3, 5, 100000, 0.01),     # tile + 1, scalar-load path, 12-bit keys (cap = n): two 9-bit sort passes
     (24, 300000, 4, 3, 70000, 0.004),   # many tiles, max_voxels bites, 17-bit keys
-    (25, 200000, 5, 100, 255, 0.05),    # one sort pass (cap 255), long segments, max_points bites
-    (26, 100000, 4, 7, 256, 0.05),      # cap 256 -> 9-bit keys, two passes
+    (25, 200000, 5, 100, 255, 0.05),    # one sort pass, long segments, max_points bites
+    (26, 100000, 4, 7, 511, 0.05),      # keys 0..511 (sentinel included): 10 bits, two passes
+    (27, 100000, 4, 7, 510, 0.05),      # keys 0..510: 9 bits, one pass with every bin in use
 ])
 def test_hard_random_vs_oracle(seed, n, c, mp, mv, cell):
     g = torch.Generator().manual_seed(seed)
