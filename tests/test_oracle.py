@@ -126,3 +126,50 @@ def test_timestep_embedding_matches_independent_port(tmp_path):
             ref = O.timestep_sinusoid(torch.tensor(t), dim, flip, shift).numpy()
             assert got.shape == ref.shape
             assert np.abs(got - ref).max() < tol, (dim, flip, shift, t, float(np.abs(got - ref).max()))
+
+
+def test_sincos_tables_match_the_mae_port_in_transformers():
+    """diffusers' sin-cos position tables are the MAE functions (get_2d_sincos_pos_embed_from_grid /
+    get_1d_sincos_pos_embed_from_grid); diffusers is absent, but `transformers` ships its own copy of the MAE code
+    (models/vit_mae/modeling_vit_mae.py).  That copy pins the oracle's restatement of (a) the frequency ladder and the
+    [sin | cos] layout, (b) the w-first meshgrid / first-half-encodes-grid[0] convention of the spatial table, and
+    (c) the temporal | spatial split of the 3-D table (App. A.2)."""
+    import numpy as np
+    from transformers.models.vit_mae.modeling_vit_mae import (get_1d_sincos_pos_embed_from_grid,
+                                                              get_2d_sincos_pos_embed)
+    pos = torch.tensor([0.0, 1.0, 2.5, 17.0, 299.0])
+    for d in (16, 480, 720):
+        want = get_1d_sincos_pos_embed_from_grid(d, pos.numpy().astype(np.float64))
+        assert np.allclose(O.sincos_1d(d, pos).numpy(), want, rtol=0, atol=1e-12)
+    D, g, T = 64, 6, 3
+    table = O.sincos_3d(D, (g, g), T, 1.0, 1.0)  # [T, g*g, D], temporal quarter first
+    spatial = get_2d_sincos_pos_embed(3 * D // 4, g)  # [g*g, 3D/4]
+    temporal = get_1d_sincos_pos_embed_from_grid(D // 4, np.arange(T, dtype=np.float64))
+    for t in range(T):
+        assert np.allclose(table[t, :, D // 4:].numpy(), spatial, rtol=0, atol=1e-6)
+        assert np.allclose(table[t, :, :D // 4].numpy(), np.broadcast_to(temporal[t], (g * g, D // 4)), rtol=0, atol=1e-6)
+
+
+def test_rope_matches_independent_ports():
+    """diffusers' apply_rotary_emb(use_real=True, use_real_unbind_dim=-1) rotates interleaved (even, odd) pairs by the
+    angle pos * theta^(-2i/d).  Two independent implementations of that rotation ship in the image: flash-attn's torch
+    reference `apply_rotary_emb_torch(interleaved=True)` and the complex-multiplication form in transformers' Llama-4
+    (`apply_rotary_emb` with freqs_cis = polar(1, angle)).  Both pin `O.rope_1d` + `O.apply_rope`."""
+    from flash_attn.layers.rotary import apply_rotary_emb_torch
+    from transformers.models.llama4.modeling_llama4 import apply_rotary_emb as llama4_rope
+    g = torch.Generator().manual_seed(0)
+    B, H, S, d = 2, 3, 11, 64
+    x = torch.randn(B, H, S, d, generator=g)
+    pos = torch.arange(S).float() * 1.5
+    cos, sin = O.rope_1d(d, pos)                      # [S, d], each frequency repeated for the pair
+    got = O.apply_rope(x, cos, sin)
+    # the frequency ladder as flash-attn's RotaryEmbedding / Llama define it
+    inv_freq = 1.0 / (10000.0 ** (torch.arange(0, d, 2).float() / d))
+    ang = torch.outer(pos, inv_freq)                  # [S, d/2]
+    assert torch.equal(cos[:, 0::2], ang.cos()) and torch.equal(cos[:, 1::2], ang.cos())
+    assert torch.equal(sin[:, 0::2], ang.sin()) and torch.equal(sin[:, 1::2], ang.sin())
+    want_fa = apply_rotary_emb_torch(x.transpose(1, 2), ang.cos(), ang.sin(), interleaved=True).transpose(1, 2)
+    assert torch.allclose(got, want_fa, rtol=0, atol=1e-6)
+    freqs_cis = torch.polar(torch.ones_like(ang), ang)[None]  # [1, S, d/2]
+    want_l4, _ = llama4_rope(x.transpose(1, 2), x.transpose(1, 2), freqs_cis)
+    assert torch.allclose(got, want_l4.transpose(1, 2), rtol=0, atol=1e-5)
