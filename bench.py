@@ -3,6 +3,9 @@
 
     python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
     python bench.py --impl reference --steps K --warmup W     (the reference algorithm on the host CPU cores)
+    python bench.py --impl torch-eager --steps K --warmup W   (the reference forward in eager torch on cuda:0; the
+                                                               default run calls this in a child process and reports
+                                                               it as `torch_eager_gpu`)
 
 A "step" is one clip: the full 50-iteration denoise loop (transformer forward + CFG/scheduler update per
 iteration) over one synthetic 17-frame 320x480 clip (latents [1,5,16,40,60], text [1,226,4096], 16 actions).
@@ -161,6 +164,70 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# second baseline leg: the reference's DEPLOYMENT path — eager PyTorch on the same GPU (SURVEY §8d "beat this")
+# ----------------------------------------------------------------------------------------------------------------
+def run_torch_eager(args, device: str = "cuda:0", cfg_over: dict | None = None):
+    """Times the restated reference forward (oracle/flat_oracle.py) executed by eager torch in bf16 on `device`:
+    cuBLAS GEMMs + SDPA(flash) + the ~60 elementwise kernels per block the reference launches.  A baseline leg like
+    `cpu_baseline` — never the product — run in its own process by `torch_eager_gpu_leg`."""
+    from oracle import flat_oracle as O
+    dev = torch.device(device)
+    cfg = O.default_config(**dict(config2(), **(cfg_over or {})))
+    g = torch.Generator(device=dev).manual_seed(0)
+    sd = {}
+    for name, shape in O.param_shapes(cfg).items():
+        t = torch.randn(shape, generator=g, device=dev) * 0.02
+        if name.endswith(".weight") and len(shape) == 1:
+            t = 1.0 + t
+        sd[name] = t.to(torch.bfloat16)
+    lat_h, lat_w = cfg["sample_height"], cfg["sample_width"]
+    inp = O.synthetic_inputs(cfg, 1, 5, lat_h, lat_w, seed=1)
+    hs, text, act = (inp[k].to(dev, torch.bfloat16) for k in ("hidden_states", "text", "actions"))
+    t = torch.tensor([999], dtype=torch.int64, device=dev)
+    cuda = dev.type == "cuda"
+    steps, warm = max(args.steps, 1), max(args.warmup, 1)
+    with torch.no_grad():
+        for _ in range(warm):
+            O.forward(sd, cfg, hs, text, t, actions=act)
+        if cuda:
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.forward(sd, cfg, hs, text, t, actions=act)
+        if cuda:
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / steps
+        else:
+            ms = (time.perf_counter() - t0) * 1e3 / steps
+    line = {"impl": "torch-eager", "metric": "denoised_video_frames_per_sec",
+            "value": FRAMES_PER_CLIP / (NUM_INFERENCE_STEPS * ms * 1e-3), "unit": "frames/s", "ms_per_forward": ms,
+            "forwards_timed": steps, "device": str(dev),
+            "sample": "config-2 transformer forward (1 clip, S=3226 tokens, 30 layers), restated reference forward in "
+                      "eager torch bf16 (cuBLAS + SDPA); frames/s = 16 / (50 forwards), sampler arithmetic excluded"}
+    print(json.dumps(line), flush=True)
+    return line
+
+
+def torch_eager_gpu_leg(timeout_s: float = 90.0) -> dict:
+    """Runs `bench.py --impl torch-eager` in a child process (a failure there cannot take the bench line with it)."""
+    try:
+        res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "torch-eager", "--steps", "5",
+                              "--warmup", "2"], capture_output=True, text=True, timeout=timeout_s)
+        lines = [x for x in res.stdout.splitlines() if x.startswith("{")]
+        if res.returncode == 0 and lines:
+            out = json.loads(lines[-1])
+            out.pop("impl", None)
+            out.pop("metric", None)
+            return out
+        return {"unavailable": ((res.stderr or "") + (res.stdout or ""))[-300:].strip() or f"exit code {res.returncode}"}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": repr(e)[:300]}
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------------
 def init_weights_(model, seed: int, std: float = 0.02):
@@ -315,6 +382,8 @@ def run_ours(args):
         sec, sample, cores = cpu_reference_step_seconds(1, 0, budget_s=25.0)
         line["cpu_baseline"] = {"value": FRAMES_PER_CLIP / (sec * NUM_INFERENCE_STEPS), "unit": "frames/s",
                                 "cores": cores, "kind": "port", "sample": sample}
+        # what the reference actually deploys: the same forward in eager torch on this GPU (own process)
+        line["torch_eager_gpu"] = torch_eager_gpu_leg()
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -327,11 +396,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-eager"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch-eager":
+        run_torch_eager(args)
     else:
         run_ours(args)
 

@@ -99,6 +99,25 @@ def joint_pos_embedding(cfg: dict, frames_lat: int, height: int, width: int) -> 
     return joint
 
 
+_TABLES: Dict[tuple, Tensor] = {}
+
+
+def _cached_table(kind: str, cfg: dict, geom: tuple, like: Tensor) -> Tensor:
+    """Position tables are registered buffers in the reference (computed at construction, moved with the module);
+    the oracle builds them on the CPU as before and keeps one copy per (geometry, device, dtype)."""
+    key = (kind, cfg["num_attention_heads"], cfg["attention_head_dim"], cfg["patch_size"], cfg["max_text_seq_length"],
+           cfg["sample_width"], cfg["sample_height"], cfg["max_n_view"], cfg["spatial_interpolation_scale"],
+           cfg["temporal_interpolation_scale"], geom, str(like.device), like.dtype)
+    t = _TABLES.get(key)
+    if t is None:
+        t = joint_pos_embedding(cfg, *geom) if kind == "joint" else view_pos_embedding(cfg, *geom)
+        t = t.to(device=like.device, dtype=like.dtype)
+        if len(_TABLES) > 64:
+            _TABLES.clear()
+        _TABLES[key] = t
+    return t
+
+
 def view_pos_embedding(cfg: dict, n_view: int) -> Tensor:
     """cogvideox_control.py:659-688: 3-D sin-cos whose 'time' axis is the view index -> [n_view * h*w, D]."""
     p = cfg["patch_size"]
@@ -111,7 +130,7 @@ def view_pos_embedding(cfg: dict, n_view: int) -> Tensor:
 def timestep_sinusoid(t: Tensor, dim: int, flip_sin_to_cos: bool, freq_shift: float) -> Tensor:
     """diffusers get_timestep_embedding (App. A.4)."""
     half = dim // 2
-    exponent = -math.log(10000) * torch.arange(half, dtype=torch.float32) / (half - freq_shift)
+    exponent = -math.log(10000) * torch.arange(half, dtype=torch.float32, device=t.device) / (half - freq_shift)
     emb = t[:, None].float() * torch.exp(exponent)[None]
     emb = torch.cat([torch.sin(emb), torch.cos(emb)], dim=-1)
     if flip_sin_to_cos:
@@ -219,7 +238,7 @@ def patch_embed(sd, cfg, text: Tensor, image: Tensor) -> Tensor:
         x = _lin(sd, "patch_embed.proj", x)
     emb = torch.cat([text, x], dim=1).contiguous()
     if (not cfg["use_rotary_positional_embeddings"]) or cfg["use_learned_positional_embeddings"]:
-        pos = joint_pos_embedding(cfg, Fr, H, W).to(emb.dtype)
+        pos = _cached_table("joint", cfg, (Fr, H, W), emb)  # a buffer in the reference: built once, not per forward
         emb = emb + pos[None]
     return emb
 
@@ -348,7 +367,7 @@ def forward(sd: Dict[str, Tensor], cfg: dict, hidden_states: Tensor, encoder_hid
         b = B // V
         s = hid.shape[1] // Fr
         h5 = hid.view(b, V, Fr, s, D).permute(0, 2, 1, 3, 4).reshape(b * Fr, V * s, D)
-        h5 = h5 + view_pos_embedding(cfg, V)[None].to(dt)
+        h5 = h5 + _cached_table("view", cfg, (V,), h5)[None]
         hid = h5.view(b, Fr, V, s, D).permute(0, 2, 1, 3, 4).reshape(B, Fr * s, D)
 
     action_emb = None
