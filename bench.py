@@ -376,6 +376,8 @@ def run_ours(args):
                 "ms_per_step": e2e_secs / args.steps * 1e3},
         "gpu_launches": int(launches_per_clip * args.steps),
         "tensor_frac_of_peak": round(NUM_INFERENCE_STEPS * FWD_TFLOP * world * args.steps / secs / (pk["bf16"] * world), 4),
+        "tensor_frac_of_burst_peak": round(NUM_INFERENCE_STEPS * FWD_TFLOP * world * args.steps / secs
+                                           / (pk["bf16_burst"] * world), 4),
         "roofline": roofline, "kernels": kernels, "clocks": clk,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
