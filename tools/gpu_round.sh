@@ -15,3 +15,9 @@ timeout 600 ncu $SECS --clock-control none -k regex:attention_kernel -s 31 -c 1 
 timeout 600 ncu $SECS --clock-control none -k regex:gemm2_bf16 -s 126 -c 4 -f -o gpurun_out/${TAG}_gemm python tools/profile_forward.py 2 > gpurun_out/${TAG}_ncu3.log 2>&1; echo "ncu gemm exit=$?"
 timeout 600 ncu $SECS --clock-control none -k regex:ln_ab_kernel\|skinny_linear -s 61 -c 3 -f -o gpurun_out/${TAG}_pointwise python tools/profile_forward.py 2 > gpurun_out/${TAG}_ncu4.log 2>&1; echo "ncu pointwise exit=$?"
 ls -la gpurun_out | tail -14
+# voxelization row: bench line + launch list with DRAM bytes (condense with tools/summarize_voxel_profile.py <tag>)
+cp gpurun_out/${TAG}_gpu_tests.log gpurun_out/${TAG}_voxel_gpu_tests.log
+timeout 120 python tools/bench_voxelize.py 2000000 > gpurun_out/${TAG}_voxel_bench.json 2> gpurun_out/${TAG}_voxel_bench.err; echo "voxel bench exit=$?"
+timeout 120 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/${TAG}_voxel_launches.csv -k "regex:voxel|radix|scan|segment|gather|label|sort_key" python tools/profile_voxelize.py > gpurun_out/${TAG}_ncu5.log 2>&1; echo "ncu voxel exit=$?"
+# the reference's deployment path on the same GPU (also embedded in the bench line as torch_eager_gpu)
+timeout 200 python bench.py --impl torch-eager --steps 5 --warmup 2 > gpurun_out/${TAG}_torch_eager.log 2>&1; echo "torch-eager exit=$?"; tail -c 600 gpurun_out/${TAG}_torch_eager.log
