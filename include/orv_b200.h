@@ -112,6 +112,10 @@ int orvb_gemm_bf16(const orvb_gemm_args* args, void* stream);
  * < 0 = CTA-pair kernel (tcgen05 cta_group::2), 256 x (-value) tiles, the width that fills the last wave of the
  * device's SM pairs best. */
 int orvb_gemm_tile_width(int32_t m, int32_t n, int32_t epilogue);
+/* Test hook: orvb_gemm_bf16 with a forced tile.  bn in {64, 128, 192, 256} = single-CTA kernel with that N tile; -bn
+ * (a multiple of 16 in 32..256) = CTA-pair kernel.  Used by the bit-identity test of the two kernels and by the tile
+ * sweeps under tools/. */
+int orvb_gemm_bf16_bn(const orvb_gemm_args* args, int bn, void* stream);
 
 /* Non-causal multi-head attention over a packed QKV buffer (reference a8: F.scaled_dot_product_attention).
  * qkv: bf16 [batch * seq_len, 3 * heads * 64] with Q | K | V column blocks; out: bf16 [batch * seq_len, heads*64].

@@ -132,7 +132,7 @@ class VoxelizeArgs(C.Structure):
 # Every symbol include/orv_b200.h declares; tests check the .so exports all of them.
 EXPORTED_SYMBOLS = [
     "orvb_version", "orvb_last_error", "orvb_check_device",
-    "orvb_gemm_bf16", "orvb_gemm_tile_width", "orvb_attention_bf16", "orvb_attention_set_rescale_threshold",
+    "orvb_gemm_bf16", "orvb_gemm_bf16_bn", "orvb_gemm_tile_width", "orvb_attention_bf16", "orvb_attention_set_rescale_threshold",
     "orvb_attention_set_debug", "orvb_ln_modulate", "orvb_skinny_linear",
     "orvb_patchify", "orvb_unpatchify",
     "orvb_model_create", "orvb_model_destroy", "orvb_model_bind_weights", "orvb_workspace_bytes",
