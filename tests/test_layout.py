@@ -35,6 +35,11 @@ def test_header_symbols_are_exported_by_the_library():
         assert hasattr(lib, sym), f"liborv_b200.so does not export {sym}"
     assert lib.orvb_version() == 100
     assert isinstance(lib.orvb_last_error(), bytes)
+    # ... and nothing else: every orvb_* symbol the library exports is declared in the header
+    import subprocess
+    nm = subprocess.run(["nm", "-D", "--defined-only", str(L.LIB_PATH)], capture_output=True, text=True, check=True)
+    exported = {ln.split()[-1] for ln in nm.stdout.splitlines() if ln.split() and ln.split()[-1].startswith("orvb_")}
+    assert exported == declared, exported ^ declared
 
 
 def test_ctypes_structs_match_header_sizes():
