@@ -25,7 +25,14 @@ _mod = None
 
 
 def available() -> bool:
-    return (OUT / f"{NAME}.so").exists() or REF_OPS.exists()
+    """True when the reference module can actually be loaded (prebuilt file or sources to build it from)."""
+    if not ((OUT / f"{NAME}.so").exists() or REF_OPS.exists()):
+        return False
+    try:
+        load()
+        return True
+    except Exception:  # noqa: BLE001  (a prebuilt module from another torch build, a missing compiler, ...)
+        return False
 
 
 def build(verbose: bool = False):
