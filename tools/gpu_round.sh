@@ -21,3 +21,5 @@ timeout 120 python tools/bench_voxelize.py 2000000 > gpurun_out/${TAG}_voxel_ben
 timeout 120 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/${TAG}_voxel_launches.csv -k "regex:voxel|radix|scan|segment|gather|label|sort_key" python tools/profile_voxelize.py > gpurun_out/${TAG}_ncu5.log 2>&1; echo "ncu voxel exit=$?"
 # the reference's deployment path on the same GPU (also embedded in the bench line as torch_eager_gpu)
 timeout 200 python bench.py --impl torch-eager --steps 5 --warmup 2 > gpurun_out/${TAG}_torch_eager.log 2>&1; echo "torch-eager exit=$?"; tail -c 600 gpurun_out/${TAG}_torch_eager.log
+# does batching clips into one forward raise throughput? (B = 2, 4)
+for B in 2 4; do timeout 200 python tools/bench_batch.py $B 3 > gpurun_out/${TAG}_batch$B.log 2>&1; echo "batch $B exit=$?"; tail -c 500 gpurun_out/${TAG}_batch$B.log; done
