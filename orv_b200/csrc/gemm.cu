@@ -404,6 +404,27 @@ __host__ __device__ constexpr int g2_epi_warps(int epi) {
 }
 __host__ __device__ constexpr int g2_threads(int epi) { return (4 + g2_epi_warps(epi)) * 32; }
 
+// In-kernel timeline of the first and the last cluster (tools/profile_gemm_timeline.py): where the ~20 us per launch
+// go in which the tensor pipe is idle (prologue, first-TMA fill, last epilogue, teardown).  Compiled in only with
+// -DORVB_GEMM_TIMELINE; the default build contains none of it.  Layout: [first | last cluster][CTA rank][32 slots].
+#ifdef ORVB_GEMM_TIMELINE
+__device__ long long* g_gemm_dbg = nullptr;
+#define G2_STAMP_VALUE(slot, value)                                                                          \
+  do {                                                                                                       \
+    long long* d_ = g_gemm_dbg;                                                                              \
+    if (d_ != nullptr && lane == 0 && (cluster_id == 0 || cluster_id == num_clusters - 1))                   \
+      d_[(cluster_id == 0 ? 0 : 64) + static_cast<int>(rank) * 32 + (slot)] = static_cast<long long>(value); \
+  } while (0)
+#define G2_STAMP(slot) G2_STAMP_VALUE(slot, clock64())
+#else
+#define G2_STAMP_VALUE(slot, value) \
+  do {                              \
+  } while (0)
+#define G2_STAMP(slot) \
+  do {                 \
+  } while (0)
+#endif
+
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2_threads(EPI), 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -429,6 +450,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   const int num_k = (p.K + BK - 1) / BK;
   const int half_bn = bn >> 1;
 
+  if (warp == 0) G2_STAMP(0);  // kernel entry
   pdl_launch_dependents();  // the next kernel's CTAs may be scheduled (and run their prologue) as SMs free up
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -454,7 +476,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   cluster_sync_all();  // barriers of BOTH CTAs initialised before any remote arrive / TMA credit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) G2_STAMP(1);  // prologue done (barriers, TMEM, cluster sync)
   pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
+  if (warp == 0) G2_STAMP(2);  // previous kernel's outputs visible
 
   if (warp == 0) {
     // ================================ TMA producer (both CTAs) ================================
@@ -477,12 +501,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
           tma_load_2d_pair(sb, &tma_b, leader_full, kb * BK, b_row);
         }
         __syncwarp();
+        if (tile == cluster_id && kb == 0) G2_STAMP(3);  // first stage requested
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
     }
+    G2_STAMP(4);  // last stage requested
   } else if (warp == 1 && rank == 0) {
     // ================================ MMA issuer (leader CTA) ================================
     const uint32_t idesc = umma_idesc_bf16(256, bn, 0, 0);
@@ -497,6 +523,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       for (int kb = 0; kb < num_k; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
+        if (tile == cluster_id && kb == 0) G2_STAMP(5);  // first operands landed
         const uint32_t sa = smem_u32(smem + stage * G2_STAGE_BYTES);
         const uint64_t a_desc = umma_desc_sw128(sa);
         const uint64_t b_desc = umma_desc_sw128(sa + G2_A_BYTES);
@@ -515,11 +542,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
           phase ^= 1;
         }
       }
+      if (tile == cluster_id) G2_STAMP(6);  // first tile's MMAs issued
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
       }
     }
+    G2_STAMP(7);  // all MMAs issued
   } else if (warp >= 4) {
     // ================================ epilogue (both CTAs) ====================================
     constexpr int EW = g2_epi_warps(EPI);
@@ -535,6 +564,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       const int n_blk = tile / p.num_m_tiles;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      if (warp == 4) {
+        if (tile == cluster_id) G2_STAMP(8);  // first accumulator complete
+        G2_STAMP(10);                         // (overwritten per tile: the last accumulator complete)
+      }
       const int row0 = m_blk * 256 + static_cast<int>(rank) * BM + ew * 32;
       const int row = row0 + lane;
       const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * G2_ACC_COLS) + (static_cast<uint32_t>(ew * 32) << 16);
@@ -581,6 +614,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+      if (warp == 4) {
+        if (tile == cluster_id) G2_STAMP(9);  // first tile's epilogue units done (this warp)
+        G2_STAMP(11);                         // (overwritten per tile: the last tile's)
+        G2_STAMP_VALUE(14, (tile - cluster_id) / num_clusters + 1);  // tiles this cluster has processed
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -590,8 +628,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
 
   // ---- teardown: nobody may exit (or free TMEM) while the peer can still touch this CTA's memory ----
   if (warp >= 4 && lane == 0) bulk_wait_group<0>();  // staged output tiles fully written
+  if (warp == 4) G2_STAMP(12);  // this warp's output stores complete
   tc_fence_before();
   cluster_sync_all();
+  if (warp == 0) G2_STAMP(13);  // teardown barrier passed
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc_pair(tmem_base, 512);
@@ -824,6 +864,16 @@ extern "C" int orvb_gemm_bf16_bn(const orvb_gemm_args* args, int bn, void* strea
   if (rc != ORVB_OK) return rc;
   return gemm_launch_prepared(ta, tb, to, p, bn_used, args->epilogue, static_cast<cudaStream_t>(stream));
 }
+
+#ifdef ORVB_GEMM_TIMELINE
+// Measurement hook (timeline builds only): installs (or clears, with NULL) a device buffer of 128 int64 that the first
+// and the last cluster of the next CTA-pair GEMM launches fill with clock64() stamps.
+extern "C" int orvb_gemm_set_debug(void* dev_buf) {
+  long long* ptr = static_cast<long long*>(dev_buf);
+  ORVB_CHECK_CUDA(cudaMemcpyToSymbol(orvb::g_gemm_dbg, &ptr, sizeof(ptr)));
+  return ORVB_OK;
+}
+#endif
 
 // Which kernel / tile width orvb_gemm_bf16 picks for an [m, n] output on this device: > 0 = single-CTA kernel with that
 // N tile, < 0 = CTA-pair kernel with N tile -value.  Pure host arithmetic (148 SMs assumed when no GPU is present).
