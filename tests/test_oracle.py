@@ -173,3 +173,85 @@ def test_rope_matches_independent_ports():
     freqs_cis = torch.polar(torch.ones_like(ang), ang)[None]  # [1, S, d/2]
     want_l4, _ = llama4_rope(x.transpose(1, 2), x.transpose(1, 2), freqs_cis)
     assert torch.allclose(got, want_l4.transpose(1, 2), rtol=0, atol=1e-5)
+
+
+def _exact_prediction(sched, t, seed=0, shape=(2, 3, 4, 5)):
+    """A denoiser that knows the truth: x_t = alpha x0 + sigma eps and the v-target v = alpha eps - sigma x0
+    (Salimans & Ho 2022), in fp32."""
+    g = torch.Generator().manual_seed(seed)
+    x0, eps = torch.randn(shape, generator=g), torch.randn(shape, generator=g)
+    a = sched.alphas_cumprod[t]
+    alpha, sigma = float(a ** 0.5), float((1 - a) ** 0.5)
+    return x0, eps, alpha * x0 + sigma * eps, alpha * eps - sigma * x0
+
+
+def test_ddim_step_is_the_published_update():
+    """DDIM with eta = 0 (Song et al. 2021, eq. 12) must map the exact marginal at t onto the exact marginal at t_prev
+    when the network is exact: x_prev = alpha_prev x0 + sigma_prev eps.  Pins the oracle's coefficient algebra
+    (v -> x0, the x / x0 recombination, the `final_alpha_cumprod = 1` last step) against the published algorithm,
+    independently of my recollection of diffusers' code."""
+    s = O.Scheduler("ddim")
+    s.set_timesteps(10)
+    for t in s.timesteps.tolist():
+        x0, eps, x_t, v = _exact_prediction(s, t, seed=t)
+        a_t, a_prev, prev = s._alphas(t)
+        want = float(a_prev ** 0.5) * x0 + float((1 - a_prev) ** 0.5) * eps
+        got = s.step_ddim(v, t, x_t)
+        assert torch.allclose(got, want, rtol=0, atol=2e-5), (t, (got - want).abs().max())
+        if prev < 0:
+            assert torch.allclose(got, x0, rtol=0, atol=2e-5)  # the last step lands on the clean sample
+
+
+def test_dpm_step_is_sde_dpm_solver_pp():
+    """CogVideoXDPMScheduler is SDE-DPM-Solver++ (Lu et al. 2022, data prediction): first order
+        x_prev = (sigma_prev / sigma_t) e^{-h} x_t + alpha_prev (1 - e^{-2h}) x0 + sigma_prev sqrt(1 - e^{-2h}) z,
+    second order (2M) with D = (1 + 1/(2r)) x0_t - 1/(2r) x0_back, r = h_back / h, h = lambda_prev - lambda_t,
+    lambda = log(alpha / sigma).  With an exact denoiser the update must keep the marginal: mean alpha_prev x0 +
+    sigma_prev e^{-h} eps, total noise variance sigma_prev^2."""
+    import math
+    s = O.Scheduler("dpm")
+    s.set_timesteps(10)
+    ts = s.timesteps.tolist()
+    lam = lambda a: -math.inf if float(a) == 0.0 else math.log(float(a ** 0.5) / float((1 - a) ** 0.5))  # noqa: E731
+    for i, t in enumerate(ts[:-1]):  # the last step (prev < 0) has sigma_prev = 0; covered by the goldens
+        x0, eps, x_t, v = _exact_prediction(s, t, seed=100 + t)
+        a_t, a_prev, prev = s._alphas(t)
+        al_p, sg_p, sg_t = float(a_prev ** 0.5), float((1 - a_prev) ** 0.5), float((1 - a_t) ** 0.5)
+        h = lam(a_prev) - lam(a_t)
+        noises = []
+        # first-order step (no history)
+        got, x0_hat = s.step_dpm(v, None, t, None, x_t, torch.Generator().manual_seed(7), noises)
+        assert torch.allclose(x0_hat, x0, rtol=0, atol=2e-5)
+        want = (sg_p / sg_t) * math.exp(-h) * x_t + al_p * (1 - math.exp(-2 * h)) * x0 \
+            + sg_p * math.sqrt(1 - math.exp(-2 * h)) * noises[-1]
+        assert torch.allclose(got, want, rtol=0, atol=5e-5), (t, (got - want).abs().max())
+        marginal = al_p * x0 + sg_p * math.exp(-h) * eps + sg_p * math.sqrt(1 - math.exp(-2 * h)) * noises[-1]
+        assert torch.allclose(got, marginal, rtol=0, atol=5e-5)
+        assert abs((sg_p * math.exp(-h)) ** 2 + sg_p ** 2 * (1 - math.exp(-2 * h)) - sg_p ** 2) < 1e-12
+        # second-order step: history = an (inexact) previous data prediction at the previous, noisier timestep
+        if i > 0:
+            t_back = ts[i - 1]
+            old = x0 + 0.1 * eps
+            r = (lam(a_t) - lam(s.alphas_cumprod[t_back])) / h
+            d = (1 + 1 / (2 * r)) * x0 - (1 / (2 * r)) * old
+            noises = []
+            got2, _ = s.step_dpm(v, old, t, t_back, x_t, torch.Generator().manual_seed(8), noises)
+            want2 = (sg_p / sg_t) * math.exp(-h) * x_t + al_p * (1 - math.exp(-2 * h)) * d \
+                + sg_p * math.sqrt(1 - math.exp(-2 * h)) * noises[-1]
+            assert torch.allclose(got2, want2, rtol=0, atol=5e-5), (t, (got2 - want2).abs().max())
+
+
+def test_noise_schedule_follows_the_published_transforms():
+    """alphas_cumprod = scaled-linear betas (LDM), SNR divided by snr_shift_scale, then the zero-terminal-SNR rescale
+    of Lin et al. 2023 (Algorithm 1: shift sqrt(alpha_bar) so the last value is 0, scale so the first is unchanged)."""
+    base = O.Scheduler("ddim", snr_shift_scale=1.0, rescale_betas_zero_snr=False).alphas_cumprod
+    betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=torch.float64) ** 2
+    assert torch.allclose(base, torch.cumprod(1 - betas, 0), rtol=0, atol=1e-15)
+    shifted = O.Scheduler("ddim", snr_shift_scale=3.0, rescale_betas_zero_snr=False).alphas_cumprod
+    snr = lambda a: a / (1 - a)  # noqa: E731
+    assert torch.allclose(snr(shifted), snr(base) / 3.0, rtol=1e-12, atol=0)
+    final = O.Scheduler("ddim").alphas_cumprod
+    s_in, s_out = shifted.sqrt(), final.sqrt()
+    assert float(s_out[-1]) == 0.0 and abs(float(s_out[0] - s_in[0])) < 1e-15
+    ratio = (s_out[:-1] / (s_in[:-1] - s_in[-1]))
+    assert float(ratio.max() - ratio.min()) < 1e-12  # one affine map of sqrt(alpha_bar)
