@@ -132,7 +132,7 @@ class VoxelizeArgs(C.Structure):
 # Every symbol include/orv_b200.h declares; tests check the .so exports all of them.
 EXPORTED_SYMBOLS = [
     "orvb_version", "orvb_last_error", "orvb_check_device",
-    "orvb_gemm_bf16", "orvb_gemm_bf16_bn", "orvb_gemm_tile_width", "orvb_attention_bf16", "orvb_attention_set_rescale_threshold",
+    "orvb_gemm_bf16", "orvb_gemm_bf16_bn", "orvb_gemm_chain", "orvb_gemm_tile_width", "orvb_attention_bf16", "orvb_attention_set_rescale_threshold",
     "orvb_attention_set_debug", "orvb_ln_modulate", "orvb_skinny_linear",
     "orvb_patchify", "orvb_unpatchify",
     "orvb_model_create", "orvb_model_destroy", "orvb_model_bind_weights", "orvb_workspace_bytes",
@@ -167,6 +167,9 @@ def load() -> C.CDLL:
     if hasattr(lib, "orvb_gemm_bf16_bn"):
         lib.orvb_gemm_bf16_bn.argtypes = [C.POINTER(GemmArgs), c_int, c_void_p]
         lib.orvb_gemm_bf16_bn.restype = c_int
+    if hasattr(lib, "orvb_gemm_chain"):
+        lib.orvb_gemm_chain.argtypes = [C.POINTER(GemmArgs), C.POINTER(GemmArgs), c_void_p, C.c_size_t, c_void_p]
+        lib.orvb_gemm_chain.restype = c_int
     if hasattr(lib, "orvb_attention_set_rescale_threshold"):
         lib.orvb_attention_set_rescale_threshold.argtypes = [c_float]
         lib.orvb_attention_set_rescale_threshold.restype = None

@@ -15,11 +15,15 @@
 #include <vector>
 
 #include "common.cuh"
+#include <stdlib.h>
+
 #include "pointwise.cuh"
 #include "ptx.cuh"
 
 namespace orvb {
 int gemm_run(const orvb_gemm_args* a, cudaStream_t stream);
+int gemm_chain_run(const orvb_gemm_args* first, const orvb_gemm_args* second, uint32_t* counters, size_t counters_bytes,
+                   cudaStream_t stream);
 }
 
 struct orvb_model {
@@ -82,6 +86,8 @@ struct Workspace {
   bf16 *x, *xn, *qkv, *att, *ffh, *patches, *ctrl, *yout, *qkv_mv, *att_mv, *tmp_mv;
   float *tsin, *t1, *temb, *osin, *o1, *oemb, *act_in, *act_h, *act_emb, *emb, *mod;
   bf16* ab;
+  uint32_t* chain_done;  // stripe counters of the experimental FF1 -> FF2 chain (ORVB_FF_CHAIN=1)
+  size_t chain_done_bytes;
   size_t bytes;
 };
 
@@ -134,6 +140,8 @@ static void carve(const orvb_config& c, const Geometry& g, uint8_t* base, Worksp
     ws->tmp_mv = reinterpret_cast<bf16*>(take(mv * (g.B / g.V) * g.Fp * g.V * tok * D * 2));
   }
   carve_modulation(c, g, take, ws);
+  ws->chain_done_bytes = (R / 256 + 2) * 4;  // last, so that every other offset is what it was without it
+  ws->chain_done = reinterpret_cast<uint32_t*>(take(ws->chain_done_bytes));
   ws->bytes = off;
 }
 
@@ -236,6 +244,16 @@ static void prof_end(orvb_model* m, cudaStream_t st) {
     ++m->launches;                  \
   } while (0)
 #define ORVB_CLS(c) (m->cur_cls = (c))
+
+// ORVB_FF_CHAIN=1 routes FF1 + FF2 through the experimental chained launch (default: off).
+static bool ff_chain_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ORVB_FF_CHAIN");
+    v = (e != nullptr && atoi(e) != 0) ? 1 : 0;
+  }
+  return v != 0;
+}
 
 static orvb_gemm_args gemm_base(const void* a, const void* w, const void* bias, void* out, int M, int N, int K,
                                 int lda, int ldo, int epi) {
@@ -536,13 +554,19 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
     ORVB_TRY(ln_modulate_launch(&ln, st));
 
     orvb_gemm_args f1 = gemm_base(ws.xn, bw.ff1_w, bw.ff1_b, ws.ffh, g.R, g.FF, D, D, g.FF, ORVB_EPI_GELU);
-    ORVB_CLS(ORVB_PC_FF1);
-    ORVB_TRY(gemm_run(&f1, st));
     orvb_gemm_args f2 = gemm_base(ws.ffh, bw.ff2_w, bw.ff2_b, ws.x, g.R, D, g.FF, g.FF, D, ORVB_EPI_GATE_RESID);
     f2.resid = ws.x; f2.ldr = D; f2.gate = mod2; f2.gate_ld = 6 * D; f2.gate_text_off = 5 * D; f2.gate_video_off = 2 * D;
     f2.rowmap = rm;
-    ORVB_CLS(ORVB_PC_FF2);
-    ORVB_TRY(gemm_run(&f2, st));
+    if (ff_chain_enabled() && g.R > 128) {
+      // experimental, opt-in: both GEMMs in one persistent launch (gemm.cu, gemm2_chain_kernel)
+      ORVB_CLS(ORVB_PC_FF1);
+      ORVB_TRY(gemm_chain_run(&f1, &f2, ws.chain_done, ws.chain_done_bytes, st));
+    } else {
+      ORVB_CLS(ORVB_PC_FF1);
+      ORVB_TRY(gemm_run(&f1, st));
+      ORVB_CLS(ORVB_PC_FF2);
+      ORVB_TRY(gemm_run(&f2, st));
+    }
 
     if (a->tap_hidden != nullptr && a->tap_layer == l) {
       ORVB_CHECK_CUDA(cudaMemcpyAsync(a->tap_hidden, ws.x, static_cast<size_t>(g.R) * D * 2, cudaMemcpyDeviceToDevice, st));

@@ -31,8 +31,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
          row_remap=(0, 0, 0), resid: Optional[torch.Tensor] = None, resid_mod: int = 0, resid_views: int = 1,
          resid_view_stride: int = 0, gate: Optional[torch.Tensor] = None, gate_text_off: int = 0,
          gate_video_off: int = 0, rm: Optional[L.RowMap] = None, qk_dim: int = 0, q_norm=None, k_norm=None,
-         qk_eps: float = 1e-6, rope=None, bn: int = 0) -> torch.Tensor:
-    """out = epilogue(a @ w.T)  — a [M,K] bf16, w [N,K] bf16 (nn.Linear layout)."""
+         qk_eps: float = 1e-6, rope=None, bn: int = 0, launch: bool = True):
+    """out = epilogue(a @ w.T)  — a [M,K] bf16, w [N,K] bf16 (nn.Linear layout).  `launch=False` only fills and
+    returns `(GemmArgs, out)` (used by `gemm_chain`)."""
     _req(a, torch.bfloat16, "a")
     _req(w, torch.bfloat16, "w")
     M, K = a.shape
@@ -69,12 +70,27 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         _req(rope[0], torch.float32, "rope_cos")
         _req(rope[1], torch.float32, "rope_sin")
         args.rope_cos, args.rope_sin = rope[0].data_ptr(), rope[1].data_ptr()
+    if not launch:
+        return args, out
     lib = L.load()
     if bn:
         L.check(lib.orvb_gemm_bf16_bn(C.byref(args), bn, L.current_stream()), "orvb_gemm_bf16")
     else:
         L.check(lib.orvb_gemm_bf16(C.byref(args), L.current_stream()), "orvb_gemm_bf16")
     return out
+
+
+def gemm_chain(first, second) -> torch.Tensor:
+    """EXPERIMENTAL (opt-in): two dependent GEMMs prepared with `gemm(..., launch=False)` — FF1 (+GELU) and FF2
+    (+gate, residual) whose `a` is FF1's `out` — as one persistent launch (`orvb_gemm_chain`).  Returns FF2's out."""
+    (a0, out0), (a1, out1) = first, second
+    lib = L.load()
+    stripes = (a0.m + 255) // 256
+    counters = torch.zeros((stripes + 1,), dtype=torch.int32, device=out0.device)
+    L.check(lib.orvb_gemm_chain(C.byref(a0), C.byref(a1), counters.data_ptr(), counters.numel() * 4,
+                                L.current_stream()), "orvb_gemm_chain")
+    out1._chain_counters = counters  # keeps the scratch alive until the (async) launch has consumed it
+    return out1
 
 
 def attention(qkv: torch.Tensor, batch: int, seq_len: int, heads: int, scale: float,
