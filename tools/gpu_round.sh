@@ -23,3 +23,5 @@ timeout 120 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
 timeout 200 python bench.py --impl torch-eager --steps 5 --warmup 2 > gpurun_out/${TAG}_torch_eager.log 2>&1; echo "torch-eager exit=$?"; tail -c 600 gpurun_out/${TAG}_torch_eager.log
 # does batching clips into one forward raise throughput? (B = 2, 4)
 for B in 2 4; do timeout 200 python tools/bench_batch.py $B 3 > gpurun_out/${TAG}_batch$B.log 2>&1; echo "batch $B exit=$?"; tail -c 500 gpurun_out/${TAG}_batch$B.log; done
+# experimental, opt-in kernels (never on the default path): FF1 -> FF2 chained launch
+ORVB_TEST_EXPERIMENTAL=1 timeout 180 python -m pytest tests/test_zz_gpu_experimental.py -m gpu -q -x > gpurun_out/${TAG}_experimental.log 2>&1; echo "experimental exit=$?"; tail -5 gpurun_out/${TAG}_experimental.log
