@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ORVB_VERSION 100
+#define ORVB_VERSION 101
 
 enum {
   ORVB_OK = 0,
@@ -104,6 +104,10 @@ typedef struct orvb_gemm_args {
   const void* k_norm_w; const void* k_norm_b;
   float qk_eps;
   const float* rope_cos; const float* rope_sin;
+  /* Tight-tolerance test mode: `out` is fp32 [*, ldo] (ldo in fp32 elements) and receives the epilogue's fp32 values
+   * before the bf16 rounding of the product path (same mainloop, same epilogue arithmetic, direct stores).  With
+   * bf16-exact operands the result must match an fp32 reference to rtol 1e-3 / atol 1e-4 (tests/test_gpu_tight.py). */
+  int32_t out_f32;
 } orvb_gemm_args;
 
 /* tcgen05 / TMA GEMM.  Requirements: k % 8 == 0, n % 8 == 0, lda/ldw/ldo % 8 == 0, 16-byte aligned bases. */
@@ -129,6 +133,17 @@ int orvb_gemm_chain(const orvb_gemm_args* first, const orvb_gemm_args* second, v
  * softmax scale = scale (1/sqrt(64) in the reference).  head_dim is fixed at 64 (every shipped config). */
 int orvb_attention_bf16(const void* qkv, void* out, int32_t batch, int32_t seq_len, int32_t heads, float scale,
                         void* stream);
+/* Full form.  The query window [q_row0, q_row0 + q_rows) of every sequence produces a COMPACT output
+ * [batch * q_rows, heads*64] (MVBlock keeps only the video rows, cogvideox_control.py:333); q_rows <= 0 = all rows.
+ * out_f32: tight-tolerance test mode, `out` is fp32 (the normalised accumulator before the bf16 rounding). */
+typedef struct orvb_attention_args {
+  const void* qkv; void* out;
+  int32_t batch, seq_len, heads;
+  float scale;
+  int32_t q_row0, q_rows;
+  int32_t out_f32;
+} orvb_attention_args;
+int orvb_attention(const orvb_attention_args* args, void* stream);
 /* Test hooks of the attention kernel.  The running row max is raised lazily (only when a key tile exceeds it by more
  * than 2^threshold, default 8), which makes the rescale of the TMEM-resident output accumulators rare;
  * orvb_attention_set_rescale_threshold(0) forces that path on almost every tile (negative = restore the default).
@@ -159,6 +174,7 @@ typedef struct orvb_ln_args {
    * are ignored and y = xhat*A + B (what orvb_forward uses: one table build per forward instead of four vector
    * loads per element). */
   const void* ab; int32_t ab_ld;
+  int32_t y_f32;                /* tight-tolerance test mode: y is fp32 [rows, dim] (values before the bf16 rounding) */
 } orvb_ln_args;
 int orvb_ln_modulate(const orvb_ln_args* args, void* stream);
 
@@ -207,6 +223,10 @@ typedef struct orvb_config {
   int32_t action_state_dim; /* 7                                                            */
   int32_t action_compress;  /* 4                                                            */
   int32_t action_hidden;    /* 4 * time_embed_dim                                           */
+  int32_t modulate_text;    /* modulate_encoder_hidden_states: 1 = norm linears are [6D, T] and the text rows are
+                               part of the joint sequence (every 2B / 5B ORV config); 0 = [3D, T], the text never
+                               enters attention or the FFN (cogvideox_control.py:70-99, :404-424, the from-scratch
+                               1.4B configs): the forward runs on the video rows alone, shape.text_len must be 0 */
 } orvb_config;
 
 /* Borrowed device pointers (bf16), one struct per CogVideoXBlock / MVBlock.  to_q/to_k/to_v are passed FUSED:
@@ -285,7 +305,15 @@ typedef struct orvb_forward_args {
   /* 1: the AdaLN tables of this step were installed into `workspace` by orvb_modulation_select; the time / action
    * embeddings and the table build (timesteps, ofs, actions, action_mask) are skipped. */
   int32_t skip_modulation;
+  /* Step-invariant inputs.  The text projection and the patch embeddings of the control latents (depths / labels)
+   * do not depend on the noisy latents, yet the reference recomputes them in each of the 50 forwards of a clip
+   * (cogvideox_control.py:788, :827-846).  ORVB_STATIC_SAVE computes them and also keeps a copy in the workspace;
+   * ORVB_STATIC_REUSE restores that copy instead of recomputing (same bits; `text`, `depths`, `labels` are then only
+   * checked for presence).  The caller uses SAVE on the first step of a clip and REUSE afterwards, on the same
+   * workspace. */
+  int32_t static_mode;
 } orvb_forward_args;
+enum { ORVB_STATIC_COMPUTE = 0, ORVB_STATIC_SAVE = 1, ORVB_STATIC_REUSE = 2 };
 
 int orvb_forward(orvb_model* m, const orvb_forward_args* a, void* stream);
 

@@ -266,10 +266,21 @@ def action_embed(sd, cfg, actions: Tensor, mask: Optional[Tensor]) -> Tensor:
 
 
 def layernorm_zero(sd, prefix, cfg, hidden, enc, temb, action_emb):
-    """ORV CogVideoXLayerNormZero.forward, modulate_encoder_hidden_states=True branches (:101-145)."""
+    """ORV CogVideoXLayerNormZero.forward: modulate_encoder_hidden_states=False branches (:70-99: the linear is
+    [3D, T], the text gets a plain LayerNorm and no gate) and =True branches (:101-145)."""
     D = hidden.shape[-1]
     W, Bv = sd[prefix + ".linear.weight"], sd[prefix + ".linear.bias"]
     eps = cfg["norm_eps"]
+    if not cfg["modulate_encoder_hidden_states"]:
+        e = _ln(sd, prefix + ".norm", enc, eps)
+        if action_emb is None:
+            shift, scale, gate = F.linear(F.silu(temb), W, Bv).chunk(3, dim=-1)
+            h = _ln(sd, prefix + ".norm", hidden, eps) * (1 + scale)[:, None] + shift[:, None]
+            return h, e, gate[:, None], None
+        shift, scale, gate = F.linear(F.silu(temb[:, None] + action_emb), W, Bv).chunk(3, dim=-1)
+        n = hidden.shape[1] // action_emb.size(1)
+        scale, shift, gate = (t.repeat_interleave(n, dim=1) for t in (scale, shift, gate))
+        return _ln(sd, prefix + ".norm", hidden, eps) * (1 + scale) + shift, e, gate, None
     if action_emb is None:
         shift, scale, gate, e_shift, e_scale, e_gate = F.linear(F.silu(temb), W, Bv).chunk(6, dim=-1)
         h = _ln(sd, prefix + ".norm", hidden, eps) * (1 + scale)[:, None] + shift[:, None]
@@ -285,9 +296,9 @@ def layernorm_zero(sd, prefix, cfg, hidden, enc, temb, action_emb):
 
 
 def attention(sd, prefix, cfg, hidden, enc, rope):
-    """ORV CogVideoXAttnProcessor2_0.__call__ (:200-270)."""
-    St = enc.size(1)
-    x = torch.cat([enc, hidden], dim=1)
+    """ORV CogVideoXAttnProcessor2_0.__call__ (:200-270).  enc=None: video tokens only (text_seq_length = 0, :222-226)."""
+    St = enc.size(1) if enc is not None else 0
+    x = torch.cat([enc, hidden], dim=1) if enc is not None else hidden
     B, S, D = x.shape
     H = cfg["num_attention_heads"]
     q = _lin(sd, prefix + ".to_q", x).view(B, S, H, -1).transpose(1, 2)
@@ -305,7 +316,15 @@ def attention(sd, prefix, cfg, hidden, enc, rope):
 
 
 def block(sd, prefix, cfg, hidden, enc, temb, rope, action_emb):
-    """ORV CogVideoXBlock.forward (:394-445), modulate_encoder_hidden_states=True."""
+    """ORV CogVideoXBlock.forward (:394-445).  Without text modulation (:404-424) the attention and the FFN see the
+    video tokens only and the text stream passes through unchanged."""
+    if not cfg["modulate_encoder_hidden_states"]:
+        nh, _, gate, _ = layernorm_zero(sd, prefix + ".norm1", cfg, hidden, enc, temb, action_emb)
+        ah, _ = attention(sd, prefix + ".attn1", cfg, nh, None, rope)
+        hidden = hidden + gate * ah
+        nh, _, gate, _ = layernorm_zero(sd, prefix + ".norm2", cfg, hidden, enc, temb, action_emb)
+        x = _lin(sd, prefix + ".ff.net.2", F.gelu(_lin(sd, prefix + ".ff.net.0.proj", nh), approximate="tanh"))
+        return hidden + gate * x, enc
     nh, ne, gate, e_gate = layernorm_zero(sd, prefix + ".norm1", cfg, hidden, enc, temb, action_emb)
     ah, ae = attention(sd, prefix + ".attn1", cfg, nh, ne, rope)
     hidden = hidden + gate * ah
@@ -341,8 +360,8 @@ def forward(sd: Dict[str, Tensor], cfg: dict, hidden_states: Tensor, encoder_hid
             depths: Optional[Tensor] = None, labels: Optional[Tensor] = None, ofs: Optional[Tensor] = None,
             rope: Optional[Tuple[Tensor, Tensor]] = None, num_views: int = 1, taps: Optional[dict] = None) -> Tensor:
     """CogVideoXTransformer3DModelTraj.forward (:715-948).  Computes in the dtype of `sd` / inputs."""
-    if not cfg["modulate_encoder_hidden_states"]:
-        raise NotImplementedError("oracle covers modulate_encoder_hidden_states=True (every 2B/5B ORV config)")
+    if not cfg["modulate_encoder_hidden_states"] and cfg["multiview"]:
+        raise NotImplementedError("multiview without text modulation: no ORV config ships it")
     V = num_views
     if V > 1:
         Bc, VF = hidden_states.shape[:2]
@@ -540,26 +559,40 @@ def sample_loop(sd, cfg, sched: Scheduler, latents: Tensor, image_latents: Tenso
 def pipeline_call(sd, cfg, kind: str, moments: Tensor, prompt_embeds: Tensor, num_frames: int, height: int,
                   width: int, num_steps: int, guidance_scale: float, generator: torch.Generator,
                   actions: Optional[Tensor] = None, negative_prompt_embeds: Optional[Tensor] = None,
-                  scaling_factor: float = 1.15258426, **fwd_kwargs) -> Tensor:
+                  scaling_factor: float = 1.15258426, num_views: int = 1,
+                  control_moments: Optional[Dict[str, Tensor]] = None, **fwd_kwargs) -> Tensor:
     """CogVideoXImageToVideoPipelineTraj.__call__ for latent-moment inputs and output_type='latent', patch_size_t
-    None (:1227-1489): prepare_latents (:1115-1225: sample first-frame moments, scale, zero-pad to F frames, initial
-    noise) followed by the denoise loop.  RNG draws happen in the reference's order on `generator`."""
+    None (:1227-1489): control latents (:1331-1364: depth / label moments sampled with the GLOBAL RNG — no generator
+    is passed there —, scaled, and duplicated on the channel axis), prepare_latents (:1115-1225: sample first-frame
+    moments, scale, zero-pad every view to F frames, initial noise) followed by the denoise loop.  RNG draws happen in
+    the reference's order on `generator`."""
     dt = prompt_embeds.dtype
     B = prompt_embeds.shape[0]
     if guidance_scale > 1.0:
         prompt_embeds = torch.cat([negative_prompt_embeds, prompt_embeds], dim=0)
+
+    def sample(m: Tensor, gen) -> Tensor:  # DiagonalGaussianDistribution(m).sample(gen), App. A.8
+        mean, logvar = torch.chunk(m, 2, dim=1)
+        std = torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0))
+        return mean + std * torch.randn(mean.shape, generator=gen, dtype=m.dtype)
+
+    for key in ("depths", "labels"):
+        if control_moments is not None and control_moments.get(key) is not None:
+            lat = (scaling_factor * sample(control_moments[key], None)).permute(0, 2, 1, 3, 4)
+            fwd_kwargs[key] = torch.cat([lat, lat], dim=2).to(dt)
     lat_frames = (num_frames - 1) // 4 + 1
-    moments = moments.to(dt)
-    mean, logvar = torch.chunk(moments, 2, dim=1)
-    std = torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0))
-    img = mean + std * torch.randn(mean.shape, generator=generator, dtype=dt)
-    img = (scaling_factor * img).permute(0, 2, 1, 3, 4)  # [B, F_img, C, h, w]
-    pad = torch.zeros(B, lat_frames - img.shape[1], img.shape[2], height // 8, width // 8, dtype=dt)
-    image_latents = torch.cat([img, pad], dim=1)
-    latents = torch.randn((B, lat_frames, img.shape[2], height // 8, width // 8), generator=generator, dtype=dt)
+    V = num_views
+    img = (scaling_factor * sample(moments.to(dt), generator)).permute(0, 2, 1, 3, 4)  # [B, V*F_img, C, h, w]
+    img = img.reshape(B, V, img.shape[1] // V, *img.shape[2:])
+    pad = torch.zeros(B, V, lat_frames - img.shape[2], img.shape[3], height // 8, width // 8, dtype=dt)
+    image_latents = torch.cat([img, pad], dim=2).flatten(1, 2)
+    latents = torch.randn((B, V * lat_frames, img.shape[3], height // 8, width // 8), generator=generator, dtype=dt)
     sched = Scheduler(kind)
-    return sample_loop(sd, cfg, sched, latents, image_latents, prompt_embeds, num_steps, guidance_scale, generator,
-                       actions=actions, **fwd_kwargs)
+    if V > 1:
+        fwd_kwargs["num_views"] = V
+    out = sample_loop(sd, cfg, sched, latents, image_latents, prompt_embeds, num_steps, guidance_scale, generator,
+                      actions=actions, **fwd_kwargs)
+    return out.reshape(B * V, lat_frames, *out.shape[2:])  # 'b (v f) c h w -> (b v) f c h w' (:1476)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -603,7 +636,7 @@ def param_shapes(cfg: dict) -> Dict[str, Tuple[int, ...]]:
     for i in range(cfg["num_layers"]):
         pre = f"transformer_blocks.{i}"
         for n in ("norm1", "norm2"):
-            lin(f"{pre}.{n}.linear", 6 * D, T)
+            lin(f"{pre}.{n}.linear", (6 if cfg["modulate_encoder_hidden_states"] else 3) * D, T)
             ln(f"{pre}.{n}.norm", D)
         attn(f"{pre}.attn1")
         lin(f"{pre}.ff.net.0.proj", 4 * D, D)

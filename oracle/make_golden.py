@@ -37,6 +37,9 @@ FORWARD_CASES = {
     "fwd_multiview_v3": (dict(multiview=True, max_n_view=3, visual_guidance=True), 1, 2, 6, 8,
                          dict(n_actions=4, controls=True, views=3)),
     "fwd_othergeom": (dict(), 1, 2, 4, 10, dict(n_actions=4)),  # geometry != sample_* -> pos-emb recomputed on the fly
+    # modulate_encoder_hidden_states=False (from-scratch 1.4B configs, reference :70-99 / :404-424), with and without actions
+    "fwd_nomodtext_b2": (dict(modulate_encoder_hidden_states=False), 2, 3, 6, 8, dict(n_actions=8)),
+    "fwd_nomodtext_noact": (dict(modulate_encoder_hidden_states=False), 1, 3, 6, 8, dict(n_actions=0)),
 }
 
 
@@ -81,12 +84,38 @@ def run_reference_forward(mod, cfg, sd, inp, rope, ofs, t, V):
     return out
 
 
-def sampler_case(mod, kind, steps, guidance, seed=42):
+# extra pipeline cases (name -> options): control latents through `pipe()` (moments sampled WITHOUT the generator,
+# cogvideox_control.py:1331-1364, hence the global seed) and the 3-view path (config 5)
+PIPELINE_CASES = {
+    "sampler_dpm_3steps_controls": dict(kind="dpm", steps=3, over=dict(visual_guidance=True), controls=True, views=1),
+    "sampler_dpm_3steps_multiview": dict(kind="dpm", steps=3, over=dict(multiview=True, max_n_view=3, visual_guidance=True),
+                                         controls=True, views=3),
+}
+CONTROL_SEED = 11
+
+
+def pipeline_case_inputs(cfg, controls: bool, views: int):
+    """Seeded inputs of a pipeline case: text/actions from synthetic_inputs, first-frame moments per view and (optionally)
+    depth / label VAE moments [B, 32, V*F, h, w] with a non-trivial log-variance."""
+    inp = O.synthetic_inputs(cfg, 1, 3, 6, 8, seed=1, n_actions=8)
+    g = torch.Generator().manual_seed(7)
+    moments = torch.randn(1, 32, views, 6, 8, generator=g)  # first-frame VAE moments [B, 2*16, V*1, h, w]
+    moments[:, 16:] = moments[:, 16:] * 0.5 - 3.0
+    cg = {"actions": inp["actions"]}
+    if controls:
+        for key in ("depths", "labels"):
+            m = torch.randn(1, 32, views * 3, 6, 8, generator=g)
+            m[:, 16:] = m[:, 16:] * 0.5 - 2.0
+            cg[key] = m
+    return inp, moments, cg
+
+
+def sampler_case(mod, kind, steps, guidance, seed=42, over=None, controls=False, views=1):
     """The reference pipeline's __call__ (latent in / latent out) on the small model, fp32 on the CPU."""
     from diffusers.models.autoencoders.autoencoder_kl_cogvideox import AutoencoderKLCogVideoX
     from diffusers.schedulers.scheduling_ddim_cogvideox import CogVideoXDDIMScheduler
     from diffusers.schedulers.scheduling_dpm_cogvideox import CogVideoXDPMScheduler
-    cfg = O.default_config(**BASE)
+    cfg = O.default_config(**dict(BASE, **(over or {})))
     sd = O.synthetic_state_dict(cfg, seed=0, std=0.05)
     model = mod.CogVideoXTransformer3DModelTraj(**cfg)
     model.load_state_dict(sd, strict=False)
@@ -96,20 +125,24 @@ def sampler_case(mod, kind, steps, guidance, seed=42):
     sched = sched_cls(prediction_type="v_prediction", rescale_betas_zero_snr=True, snr_shift_scale=3.0,
                       timestep_spacing="trailing", clip_sample=False)
     pipe = mod.CogVideoXImageToVideoPipelineTraj(None, None, AutoencoderKLCogVideoX(), model, sched)
-    inp = O.synthetic_inputs(cfg, 1, 3, 6, 8, seed=1, n_actions=8)
-    g = torch.Generator().manual_seed(7)
-    moments = torch.randn(1, 32, 1, 6, 8, generator=g)  # first-frame VAE moments [B, 2*16, F=1, h, w]
-    moments[:, 16:] = moments[:, 16:] * 0.5 - 3.0
+    if controls or views > 1:
+        inp, moments, cg = pipeline_case_inputs(cfg, controls, views)
+    else:  # the round-1 cases, byte for byte
+        inp = O.synthetic_inputs(cfg, 1, 3, 6, 8, seed=1, n_actions=8)
+        g = torch.Generator().manual_seed(7)
+        moments = torch.randn(1, 32, 1, 6, 8, generator=g)  # first-frame VAE moments [B, 2*16, F=1, h, w]
+        moments[:, 16:] = moments[:, 16:] * 0.5 - 3.0
+        cg = {} if guidance > 1.0 else {"actions": inp["actions"]}  # the reference cannot run CFG with controls (P5)
     gen = torch.Generator().manual_seed(seed)
-    cg = {} if guidance > 1.0 else {"actions": inp["actions"]}  # the reference cannot run CFG with controls (P5)
     kw = dict(image=moments, prompt="", prompt_embeds=inp["text"], height=48, width=64, num_frames=9,
               num_inference_steps=steps, guidance_scale=guidance, generator=gen, controls_or_guidances=cg,
-              output_type="latent", return_dict=False)
+              output_type="latent", return_dict=False, num_views=views)
     if guidance > 1.0:
         # positional check_inputs quirk (cogvideox_control.py:1261-1270): with CFG the embeds pair only passes
         # validation when `prompt` is None
         kw["prompt"] = None
         kw["negative_prompt_embeds"] = torch.zeros_like(inp["text"])
+    torch.manual_seed(CONTROL_SEED)  # the control-latent draws use the global RNG
     out = pipe(**kw)[0]
     return cfg, sd, inp, moments, out
 
@@ -141,6 +174,12 @@ def main():
     for kind, steps, guidance in (("ddim", 2, 1.0), ("dpm", 4, 1.0), ("dpm", 3, 6.0)):
         cfg, sd, inp, moments, out = sampler_case(mod, kind, steps, guidance)
         name = f"sampler_{kind}_{steps}steps_g{int(guidance)}"
+        torch.save({"name": name, "weights_sha256": digest(sd), "moments": moments, "latents": out.float()},
+                   os.path.join(GOLDEN_DIR, name + ".pt"))
+        print(f"{name}: latents {tuple(out.shape)} mean|x| {out.abs().mean():.4f}")
+    for name, opt in PIPELINE_CASES.items():
+        cfg, sd, inp, moments, out = sampler_case(mod, opt["kind"], opt["steps"], 1.0, over=opt["over"],
+                                                  controls=opt["controls"], views=opt["views"])
         torch.save({"name": name, "weights_sha256": digest(sd), "moments": moments, "latents": out.float()},
                    os.path.join(GOLDEN_DIR, name + ".pt"))
         print(f"{name}: latents {tuple(out.shape)} mean|x| {out.abs().mean():.4f}")

@@ -10,7 +10,8 @@ import os
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "liborv_b200.so"
+# ORVB_LIB_PATH: measurement builds only (e.g. the -DORVB_GEMM_TIMELINE variant tools/ build next to the product library)
+LIB_PATH = Path(os.environ["ORVB_LIB_PATH"]).resolve() if os.environ.get("ORVB_LIB_PATH") else _HERE / "liborv_b200.so"
 
 ORVB_OK = 0
 EPI_BIAS, EPI_GELU, EPI_GATE_RESID, EPI_QKV = 0, 1, 2, 3
@@ -41,6 +42,15 @@ class GemmArgs(C.Structure):
         ("q_norm_w", c_void_p), ("q_norm_b", c_void_p), ("k_norm_w", c_void_p), ("k_norm_b", c_void_p),
         ("qk_eps", c_float),
         ("rope_cos", c_void_p), ("rope_sin", c_void_p),
+        ("out_f32", c_int),
+    ]
+
+
+class AttentionArgs(C.Structure):
+    _fields_ = [
+        ("qkv", c_void_p), ("out", c_void_p),
+        ("batch", c_int), ("seq_len", c_int), ("heads", c_int), ("scale", c_float),
+        ("q_row0", c_int), ("q_rows", c_int), ("out_f32", c_int),
     ]
 
 
@@ -53,6 +63,7 @@ class LnArgs(C.Structure):
         ("in_video_only", c_int),
         ("pre_w", c_void_p), ("pre_b", c_void_p), ("pre_eps", c_float),
         ("ab", c_void_p), ("ab_ld", c_int),
+        ("y_f32", c_int),
     ]
 
 
@@ -64,6 +75,7 @@ class Config(C.Structure):
         ("ofs_embed_dim", c_int), ("flip_sin_to_cos", c_int), ("freq_shift", c_float), ("norm_eps", c_float),
         ("visual_guidance", c_int), ("num_control_keys", c_int), ("multiview", c_int), ("max_n_view", c_int),
         ("action_state_dim", c_int), ("action_compress", c_int), ("action_hidden", c_int),
+        ("modulate_text", c_int),
     ]
 
 
@@ -105,7 +117,11 @@ class ForwardArgs(C.Structure):
         ("out", c_void_p), ("workspace", c_void_p), ("workspace_bytes", C.c_size_t),
         ("tap_hidden", c_void_p), ("tap_layer", c_int),
         ("skip_modulation", c_int),
+        ("static_mode", c_int),
     ]
+
+
+STATIC_COMPUTE, STATIC_SAVE, STATIC_REUSE = 0, 1, 2
 
 
 class SamplerStepArgs(C.Structure):
@@ -132,7 +148,7 @@ class VoxelizeArgs(C.Structure):
 # Every symbol include/orv_b200.h declares; tests check the .so exports all of them.
 EXPORTED_SYMBOLS = [
     "orvb_version", "orvb_last_error", "orvb_check_device",
-    "orvb_gemm_bf16", "orvb_gemm_bf16_bn", "orvb_gemm_chain", "orvb_gemm_tile_width", "orvb_attention_bf16", "orvb_attention_set_rescale_threshold",
+    "orvb_gemm_bf16", "orvb_gemm_bf16_bn", "orvb_gemm_chain", "orvb_gemm_tile_width", "orvb_attention_bf16", "orvb_attention", "orvb_attention_set_rescale_threshold",
     "orvb_attention_set_debug", "orvb_ln_modulate", "orvb_skinny_linear",
     "orvb_patchify", "orvb_unpatchify",
     "orvb_model_create", "orvb_model_destroy", "orvb_model_bind_weights", "orvb_workspace_bytes",
@@ -178,6 +194,8 @@ def load() -> C.CDLL:
     if hasattr(lib, "orvb_attention_bf16"):
         lib.orvb_attention_bf16.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]
         lib.orvb_attention_bf16.restype = c_int
+        lib.orvb_attention.argtypes = [C.POINTER(AttentionArgs), c_void_p]
+        lib.orvb_attention.restype = c_int
     if hasattr(lib, "orvb_ln_modulate"):
         lib.orvb_ln_modulate.argtypes = [C.POINTER(LnArgs), c_void_p]
         lib.orvb_ln_modulate.restype = c_int

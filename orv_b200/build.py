@@ -17,8 +17,11 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
-BUILD = ROOT.parent / "build" / "orv_b200"
-LIB = ROOT / "liborv_b200.so"
+# ORVB_BUILD_VARIANT=<name>: measurement variant (with ORVB_EXTRA_NVCC_FLAGS) built into its own object directory and
+# orv_b200/liborv_b200_<name>.so, so the product library is never replaced by an instrumented one.
+_VARIANT = os.environ.get("ORVB_BUILD_VARIANT", "")
+BUILD = ROOT.parent / "build" / ("orv_b200" + ("_" + _VARIANT if _VARIANT else ""))
+LIB = ROOT / ("liborv_b200" + ("_" + _VARIANT if _VARIANT else "") + ".so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -41,8 +41,8 @@ constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units
 // 1 = ONE MMA-issuing warp, warp-uniform issue.  The one-issuer-per-query-tile variants (3, 11, 19) are ~4 % faster but
 // NOT safe: when the rare lazy-rescale path rewrites an O accumulator (tcgen05.ld -> scale -> tcgen05.st) while a
 // DIFFERENT thread is issuing tcgen05.mma, a few rows come out wrong (forced rescale: 28/30 launches bad with two
-// issuers, 0/60 with one; same signature with two CTAs per SM — profiles/r01_attention_notes.md).  They stay
-// selectable through ORVB_ATT_VARIANT for experiments only.
+// issuers, 0/60 with one; same signature with two CTAs per SM — profiles/r01_attention_notes.md).  They are compiled
+// only into measurement builds (-DORVB_EXPERIMENTAL, ORVB_ATT_VARIANT); the product library does not contain them.
 constexpr int ATT_DEFAULT_VARIANT = 1;
 
 struct AttDev {
@@ -52,6 +52,7 @@ struct AttDev {
   int q_row0, q_rows;       // queries = rows [q_row0, q_row0 + q_rows) of every sequence; output is compact
   float rescale_threshold;  // log2 units by which a tile max must exceed the running max before it is raised
   long long* dbg;           // optional timeline buffer (tools/profile_attention_timeline.py); nullptr in production
+  int out_f32;              // test mode: `out` is fp32 (the normalised accumulator before the bf16 rounding)
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -456,6 +457,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttDev p) {
             float f[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) f[u] = __uint_as_float(o[q * 8 + u]) * ca + xch[2 + c + q * 8 + u] * cb;
+            if (p.out_f32) {
+              float* of = reinterpret_cast<float*>(p.out) +
+                          (static_cast<size_t>(batch) * p.q_rows + q_row) * p.dim + head * ATT_D + c + q * 8;
+              *reinterpret_cast<float4*>(of) = make_float4(f[0], f[1], f[2], f[3]);
+              *reinterpret_cast<float4*>(of + 4) = make_float4(f[4], f[5], f[6], f[7]);
+              continue;
+            }
             uint4 v;
             v.x = pack_bf16(f[0], f[1]);
             v.y = pack_bf16(f[2], f[3]);
@@ -492,7 +500,7 @@ static long long* g_att_dbg = nullptr;
 static float g_att_threshold = -1.f;  // < 0: take ORVB_ATT_THRESHOLD or the default on the next launch
 
 int attention_launch(const void* qkv, void* out, int batch, int seq_len, int heads, float scale, int q_row0,
-                     int q_rows, cudaStream_t stream) {
+                     int q_rows, cudaStream_t stream, int out_f32) {
   ORVB_REQUIRE(qkv && out, ORVB_EINVAL, "orvb_attention_bf16: null pointer");
   ORVB_REQUIRE(batch > 0 && seq_len > 0 && heads > 0, ORVB_ESHAPE, "orvb_attention_bf16: empty problem");
   if (q_rows <= 0) {
@@ -514,6 +522,7 @@ int attention_launch(const void* qkv, void* out, int batch, int seq_len, int hea
   p.q_row0 = q_row0;
   p.q_rows = q_rows;
   p.dbg = g_att_dbg;
+  p.out_f32 = out_f32 ? 1 : 0;
   // Test knob (ORVB_ATT_THRESHOLD or orvb_attention_set_rescale_threshold): 0 raises the running max on (almost) every key tile, i.e. forces the otherwise rare
   // TMEM read-modify-write of the O accumulators (tests/test_gpu_ops.py::test_attention_forced_rescale).
   if (g_att_threshold < 0.f) {
@@ -522,13 +531,15 @@ int attention_launch(const void* qkv, void* out, int batch, int seq_len, int hea
   }
   p.rescale_threshold = g_att_threshold;
   dim3 grid((q_rows + 2 * ATT_BQ - 1) / (2 * ATT_BQ), heads, batch);
-  // A/B switch for measurements: bit 0 = warp-uniform MMA issue, bit 1 = one MMA warp per query tile, 4 = v3 kernel.
+#ifdef ORVB_EXPERIMENTAL
+  // Measurement builds only (-DORVB_EXPERIMENTAL; absent from the product library): ORVB_ATT_VARIANT = issue mode
+  // (bit 0 uniform, bit 1 one issuer per query tile — NOT safe, see ATT_DEFAULT_VARIANT) + 8 * (exp2 emulation: 0 none,
+  // 1 = 25 %, 2 = 50 % of the scores).
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("ORVB_ATT_VARIANT");
     variant = e ? atoi(e) : ATT_DEFAULT_VARIANT;
   }
-  // variant = issue mode (bit 0 uniform, bit 1 dual) + 8 * (exp2 emulation: 0 none, 1 = 25 %, 2 = 50 % of the scores)
   switch (variant) {
     case 1: return launch_attention_v4<false, true, 0>(tm, p, grid, stream);
     case 3: return launch_attention_v4<true, true, 0>(tm, p, grid, stream);
@@ -540,6 +551,10 @@ int attention_launch(const void* qkv, void* out, int batch, int seq_len, int hea
   }
   set_error("orvb_attention_bf16: unknown ORVB_ATT_VARIANT %d (1, 3, 9, 11, 17, 19)", variant);
   return ORVB_EINVAL;
+#else
+  // The product library holds exactly one attention kernel: one warp-uniform MMA issuer, no exp2 emulation.
+  return launch_attention_v4<false, true, 0>(tm, p, grid, stream);
+#endif
 }
 
 }  // namespace orvb
@@ -548,7 +563,15 @@ extern "C" int orvb_attention_bf16(const void* qkv, void* out, int32_t batch, in
                                    float scale, void* stream) {
   int rc = orvb::check_arch();
   if (rc != ORVB_OK) return rc;
-  return orvb::attention_launch(qkv, out, batch, seq_len, heads, scale, 0, seq_len, static_cast<cudaStream_t>(stream));
+  return orvb::attention_launch(qkv, out, batch, seq_len, heads, scale, 0, seq_len, static_cast<cudaStream_t>(stream), 0);
+}
+
+extern "C" int orvb_attention(const orvb_attention_args* a, void* stream) {
+  int rc = orvb::check_arch();
+  if (rc != ORVB_OK) return rc;
+  ORVB_REQUIRE(a != nullptr, ORVB_EINVAL, "orvb_attention: null argument struct");
+  return orvb::attention_launch(a->qkv, a->out, a->batch, a->seq_len, a->heads, a->scale, a->q_row0, a->q_rows,
+                                static_cast<cudaStream_t>(stream), a->out_f32);
 }
 
 

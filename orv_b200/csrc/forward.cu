@@ -32,12 +32,13 @@ struct orvb_model {
   std::vector<orvb_block_weights> blocks;
   std::vector<orvb_block_weights> mv_blocks;
   bool bound = false;
-  // Device metadata owned by the library, one set per user of build_modulation (0: the forward's own workspace,
-  // 1: a modulation schedule buffer) so that alternating between the two never rewrites a table a queued kernel reads.
-  orvb::SkinnyJob* jobs_dev_[2] = {nullptr, nullptr};  // [sites] AdaLN job table
-  orvb::AbSite* ab_sites_dev_[2] = {nullptr, nullptr}; // [sites] LayerNorm A/B-table build descriptors
-  float* jobs_y_base_[2] = {nullptr, nullptr};         // modulation-table base the job table currently points at
-  size_t jobs_site_stride_[2] = {0, 0};
+  // Device copies of the per-block weight pointers (written by orvb_model_bind_weights).  The AdaLN job table
+  // (SkinnyJob per site) and the A/B-fold descriptors (AbSite per site) hold pointers INTO the modulation region they
+  // describe, so they live in that region (carve_modulation) and are rebuilt from these copies by a one-block kernel
+  // at the head of every table build: a captured CUDA graph bakes in a table's address, and a table is never
+  // re-pointed at another workspace; nothing is uploaded from the host after bind time.
+  orvb_block_weights* blocks_dev = nullptr;     // [layers]
+  orvb_block_weights* mv_blocks_dev = nullptr;  // [layers] or null
   int launches = 0;
   // optional per-kernel-class timing (orvb_model_set_profile): CUDA events around every launch
   bool profile = false;
@@ -86,10 +87,17 @@ struct Workspace {
   bf16 *x, *xn, *qkv, *att, *ffh, *patches, *ctrl, *yout, *qkv_mv, *att_mv, *tmp_mv;
   float *tsin, *t1, *temb, *osin, *o1, *oemb, *act_in, *act_h, *act_emb, *emb, *mod;
   bf16* ab;
-  uint32_t* chain_done;  // stripe counters of the experimental FF1 -> FF2 chain (ORVB_FF_CHAIN=1)
+  SkinnyJob* jobs;   // [3 * layers] device table of the batched AdaLN linears (points into `mod`)
+  AbSite* ab_sites;  // [3 * layers + 1] device table of the A/B folds (points into `mod` / `ab`)
+  bf16 *text_cache, *ctrl_cache;  // step-invariant rows kept by ORVB_STATIC_SAVE (text projection, control embeddings)
+  uint32_t* chain_done;  // stripe counters of the FF1 -> FF2 chain
   size_t chain_done_bytes;
   size_t bytes;
 };
+
+// Width of one AdaLN table row in units of D: [shift, scale, gate | enc_shift, enc_scale, enc_gate] when the text is
+// modulated, [shift, scale, gate] otherwise (cogvideox_control.py:57-58).
+static inline int mod_width(const orvb_config& c) { return c.modulate_text ? 6 : 3; }
 
 // Scratch + tables of the modulation prologue (sections 1-2 of the forward) for g.B samples.  Also carved on its own
 // for a whole schedule of timesteps (orvb_modulation_schedule: g.B = steps x batch virtual samples).
@@ -110,8 +118,10 @@ static void carve_modulation(const orvb_config& c, const Geometry& g, Take&& tak
   ws->act_h = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * fa * c.action_hidden * 4));
   ws->act_emb = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * fa * g.T * 4));
   ws->emb = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * g.G * g.T * 4));
-  ws->mod = reinterpret_cast<float*>(take(static_cast<size_t>(g.sites) * g.B * g.G * 6 * D * 4));
+  ws->mod = reinterpret_cast<float*>(take(static_cast<size_t>(g.sites) * g.B * g.G * mod_width(c) * D * 4));
   ws->ab = reinterpret_cast<bf16*>(take(static_cast<size_t>(g.sites) * g.B * g.G * 4 * D * 2));
+  ws->jobs = reinterpret_cast<SkinnyJob*>(take(sizeof(SkinnyJob) * 3 * c.layers));
+  ws->ab_sites = reinterpret_cast<AbSite*>(take(sizeof(AbSite) * (3 * c.layers + 1)));
 }
 
 static void carve(const orvb_config& c, const Geometry& g, uint8_t* base, Workspace* ws) {
@@ -140,8 +150,10 @@ static void carve(const orvb_config& c, const Geometry& g, uint8_t* base, Worksp
     ws->tmp_mv = reinterpret_cast<bf16*>(take(mv * (g.B / g.V) * g.Fp * g.V * tok * D * 2));
   }
   carve_modulation(c, g, take, ws);
-  ws->chain_done_bytes = (R / 256 + 2) * 4;  // last, so that every other offset is what it was without it
+  ws->chain_done_bytes = (R / 256 + 2) * 4;
   ws->chain_done = reinterpret_cast<uint32_t*>(take(ws->chain_done_bytes));
+  ws->text_cache = reinterpret_cast<bf16*>(take(static_cast<size_t>(g.B) * g.St * D * 2));
+  ws->ctrl_cache = reinterpret_cast<bf16*>(take(static_cast<size_t>(g.B) * g.Sv * D * keys * 2));
   ws->bytes = off;
 }
 
@@ -274,12 +286,37 @@ struct ModIn {
 // Sections 1-2 of the forward: time / ofs / action embeddings -> per-group conditioning rows -> every AdaLN table of
 // the model (fp32 `mod`) and their folded LayerNorm form (bf16 `ab`), for g.B samples.  They depend on the timestep,
 // ofs and the actions only, never on the latents.
-static int build_modulation(orvb_model* m, const Geometry& g, const ModIn& in, const Workspace& ws, int slot,
-                            cudaStream_t st) {
-  SkinnyJob*& jobs_dev = m->jobs_dev_[slot];
-  AbSite*& ab_sites_dev = m->ab_sites_dev_[slot];
-  float*& jobs_y_base = m->jobs_y_base_[slot];
-  size_t& jobs_site_stride = m->jobs_site_stride_[slot];
+// Fills the job / site tables of one modulation region (one thread per layer).
+__global__ void fill_tables_kernel(const orvb_block_weights* __restrict__ blocks, const orvb_block_weights* __restrict__ mv_blocks,
+                                   const bf16* norm_out_ln_w, const bf16* norm_out_ln_b, float* mod, bf16* ab,
+                                   SkinnyJob* jobs, AbSite* sites, int layers, size_t site_stride, size_t ab_stride,
+                                   int mod_ld, int text_off, int D) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l == 0)  // norm_out (AdaLayerNorm, shift first, pitch 2D): only the video variant is ever read
+    sites[2 * layers] = AbSite{norm_out_ln_w, norm_out_ln_b, mod + static_cast<size_t>(2 * layers) * site_stride,
+                               2 * D, 0, 0, ab + static_cast<size_t>(2 * layers) * ab_stride};
+  if (l >= layers) return;
+  const orvb_block_weights bw = blocks[l];
+  float* m1 = mod + static_cast<size_t>(2 * l) * site_stride;
+  float* m2 = m1 + site_stride;
+  jobs[2 * l] = SkinnyJob{static_cast<const bf16*>(bw.norm1_lin_w), static_cast<const bf16*>(bw.norm1_lin_b), m1};
+  jobs[2 * l + 1] = SkinnyJob{static_cast<const bf16*>(bw.norm2_lin_w), static_cast<const bf16*>(bw.norm2_lin_b), m2};
+  sites[2 * l] = AbSite{static_cast<const bf16*>(bw.norm1_ln_w), static_cast<const bf16*>(bw.norm1_ln_b), m1, mod_ld,
+                        text_off, 0, ab + static_cast<size_t>(2 * l) * ab_stride};
+  sites[2 * l + 1] = AbSite{static_cast<const bf16*>(bw.norm2_ln_w), static_cast<const bf16*>(bw.norm2_ln_b), m2, mod_ld,
+                            text_off, 0, ab + static_cast<size_t>(2 * l + 1) * ab_stride};
+  if (mv_blocks != nullptr) {
+    // MVBlock.norm1 sites live after the norm_out slot: site index 2L + 1 + l, job index 2L + l
+    const orvb_block_weights mw = mv_blocks[l];
+    const size_t site = static_cast<size_t>(2 * layers + 1 + l);
+    jobs[2 * layers + l] = SkinnyJob{static_cast<const bf16*>(mw.norm1_lin_w), static_cast<const bf16*>(mw.norm1_lin_b),
+                                     mod + site * site_stride};
+    sites[site] = AbSite{static_cast<const bf16*>(mw.norm1_ln_w), static_cast<const bf16*>(mw.norm1_ln_b),
+                         mod + site * site_stride, mod_ld, text_off, 0, ab + site * ab_stride};
+  }
+}
+
+static int build_modulation(orvb_model* m, const Geometry& g, const ModIn& in, const Workspace& ws, cudaStream_t st) {
   const orvb_config& c = m->cfg;
   const orvb_weights& w = m->w;
   const int D = g.D, T = g.T;
@@ -337,50 +374,19 @@ static int build_modulation(orvb_model* m, const Geometry& g, const ModIn& in, c
   }
 
   // ---- 2. all AdaLN tables of the forward in one batched launch (they depend only on emb) ----------
-  const size_t site_stride = static_cast<size_t>(g.B) * g.G * 6 * D;
-  if (jobs_y_base != ws.mod || jobs_site_stride != site_stride) {
-    const int n_jobs = 2 * c.layers + (c.multiview ? c.layers : 0);
-    std::vector<SkinnyJob> jobs(n_jobs);
-    for (int l = 0; l < c.layers; ++l) {
-      const orvb_block_weights& bw = m->blocks[l];
-      jobs[2 * l] = SkinnyJob{static_cast<const bf16*>(bw.norm1_lin_w), static_cast<const bf16*>(bw.norm1_lin_b),
-                              ws.mod + (2 * l) * site_stride};
-      jobs[2 * l + 1] = SkinnyJob{static_cast<const bf16*>(bw.norm2_lin_w), static_cast<const bf16*>(bw.norm2_lin_b),
-                                  ws.mod + (2 * l + 1) * site_stride};
-    }
-    // synchronous small copy: happens once per (model, workspace) pair, outside any graph capture
-    ORVB_CHECK_CUDA(cudaMemcpy(jobs_dev, jobs.data(), jobs.size() * sizeof(SkinnyJob), cudaMemcpyHostToDevice));
+  const int mw = mod_width(c);
+  const size_t site_stride = static_cast<size_t>(g.B) * g.G * mw * D;
+  {
     const size_t ab_stride = static_cast<size_t>(g.B) * g.G * 4 * D;
-    std::vector<AbSite> sites(g.sites);
-    for (int l = 0; l < c.layers; ++l) {
-      const orvb_block_weights& bw = m->blocks[l];
-      sites[2 * l] = AbSite{static_cast<const bf16*>(bw.norm1_ln_w), static_cast<const bf16*>(bw.norm1_ln_b),
-                            ws.mod + (2 * l) * site_stride, 6 * D, 3 * D, 0, ws.ab + (2 * l) * ab_stride};
-      sites[2 * l + 1] = AbSite{static_cast<const bf16*>(bw.norm2_ln_w), static_cast<const bf16*>(bw.norm2_ln_b),
-                                ws.mod + (2 * l + 1) * site_stride, 6 * D, 3 * D, 0, ws.ab + (2 * l + 1) * ab_stride};
-    }
-    // norm_out (AdaLayerNorm, shift first, pitch 2D): only the video variant is ever read
-    sites[2 * c.layers] = AbSite{static_cast<const bf16*>(w.norm_out_ln_w), static_cast<const bf16*>(w.norm_out_ln_b),
-                                 ws.mod + static_cast<size_t>(2 * c.layers) * site_stride, 2 * D, 0, 0,
-                                 ws.ab + static_cast<size_t>(2 * c.layers) * ab_stride};
-    if (c.multiview) {
-      // MVBlock.norm1 sites live after the norm_out slot: site index 2L + 1 + l, job index 2L + l
-      for (int l = 0; l < c.layers; ++l) {
-        const orvb_block_weights& mw = m->mv_blocks[l];
-        const size_t site = static_cast<size_t>(2 * c.layers + 1 + l);
-        jobs[2 * c.layers + l] = SkinnyJob{static_cast<const bf16*>(mw.norm1_lin_w), static_cast<const bf16*>(mw.norm1_lin_b),
-                                           ws.mod + site * site_stride};
-        sites[site] = AbSite{static_cast<const bf16*>(mw.norm1_ln_w), static_cast<const bf16*>(mw.norm1_ln_b),
-                             ws.mod + site * site_stride, 6 * D, 3 * D, 0, ws.ab + site * ab_stride};
-      }
-      ORVB_CHECK_CUDA(cudaMemcpy(jobs_dev, jobs.data(), jobs.size() * sizeof(SkinnyJob), cudaMemcpyHostToDevice));
-    }
-    ORVB_CHECK_CUDA(cudaMemcpy(ab_sites_dev, sites.data(), sites.size() * sizeof(AbSite), cudaMemcpyHostToDevice));
-    jobs_y_base = ws.mod;
-    jobs_site_stride = site_stride;
+    fill_tables_kernel<<<(c.layers + 63) / 64, 64, 0, st>>>(
+        m->blocks_dev, c.multiview ? m->mv_blocks_dev : nullptr, static_cast<const bf16*>(w.norm_out_ln_w),
+        static_cast<const bf16*>(w.norm_out_ln_b), ws.mod, ws.ab, ws.jobs, ws.ab_sites, c.layers, site_stride, ab_stride,
+        mw * D, c.modulate_text ? 3 * D : 0, D);  // no text variant without text modulation: it aliases the video one
+    ORVB_CHECK_CUDA(cudaGetLastError());
+    ++m->launches;
   }
-  ORVB_TRY(skinny_linear_launch(ws.emb, SkinnyJob{nullptr, nullptr, nullptr}, jobs_dev,
-                                2 * c.layers + (c.multiview ? c.layers : 0), g.B * g.G, 6 * D, T, 0, st));
+  ORVB_TRY(skinny_linear_launch(ws.emb, SkinnyJob{nullptr, nullptr, nullptr}, ws.jobs,
+                                2 * c.layers + (c.multiview ? c.layers : 0), g.B * g.G, mw * D, T, 0, st));
   float* mod_out = ws.mod + static_cast<size_t>(2 * c.layers) * site_stride;  // norm_out table, row pitch 2D
   {
     // norm_out.linear is [2D, T]; written with pitch 2D into its slot
@@ -388,7 +394,7 @@ static int build_modulation(orvb_model* m, const Geometry& g, const ModIn& in, c
                                   nullptr, 1, g.B * g.G, 2 * D, T, 0, st));
   }
   // fold LayerNorm affine + (shift, scale) of every site into bf16 A/B tables for the LN kernels
-  ORVB_TRY(ab_combine_launch(ab_sites_dev, g.sites, g.B * g.G, D, st));
+  ORVB_TRY(ab_combine_launch(ws.ab_sites, g.sites, g.B * g.G, D, st));
   return ORVB_OK;
 }
 
@@ -398,7 +404,9 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
   Geometry g;
   int rc = make_geometry(c, a->shape, &g);
   if (rc != ORVB_OK) return rc;
-  ORVB_REQUIRE(a->hidden_states && a->text && a->timesteps && a->out && a->workspace, ORVB_EINVAL,
+  ORVB_REQUIRE(c.modulate_text || a->shape.text_len == 0, ORVB_ESHAPE,
+               "orvb_forward: a model without text modulation runs on the video rows alone (shape.text_len must be 0)");
+  ORVB_REQUIRE(a->hidden_states && (a->text || a->shape.text_len == 0) && a->timesteps && a->out && a->workspace, ORVB_EINVAL,
                "orvb_forward: null input/output/workspace pointer");
   Workspace ws;
   carve(c, g, static_cast<uint8_t*>(a->workspace), &ws);
@@ -421,11 +429,16 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
   if (!a->skip_modulation) {
     ModIn in;
     in.timesteps = a->timesteps; in.ofs = a->ofs; in.actions = a->actions; in.action_mask = a->action_mask;
-    int mrc = build_modulation(m, g, in, ws, 0, st);
+    int mrc = build_modulation(m, g, in, ws, st);
     if (mrc != ORVB_OK) return mrc;
   }
-  const size_t site_stride = static_cast<size_t>(g.B) * g.G * 6 * D;
+  const int mwid = mod_width(c);
+  const int gate_text_off = c.modulate_text ? 5 * D : 2 * D;  // enc_gate, or (no text rows exist) the video gate
+  const size_t site_stride = static_cast<size_t>(g.B) * g.G * mwid * D;
   const size_t ab_stride = static_cast<size_t>(g.B) * g.G * 4 * D;
+  ORVB_REQUIRE(a->static_mode >= ORVB_STATIC_COMPUTE && a->static_mode <= ORVB_STATIC_REUSE, ORVB_EINVAL,
+               "orvb_forward: unknown static_mode %d", a->static_mode);
+  const bool st_save = a->static_mode == ORVB_STATIC_SAVE, st_reuse = a->static_mode == ORVB_STATIC_REUSE;
 
   orvb_rowmap rm;
   rm.seq_len = g.S; rm.text_len = g.St;
@@ -449,7 +462,13 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
     orvb_gemm_args ga = gemm_base(a->text, w.text_w, w.text_b, ws.x, g.B * g.St, D, c.text_embed_dim,
                                   c.text_embed_dim, D, ORVB_EPI_BIAS);
     ga.src_rows = g.St; ga.dst_rows = g.S; ga.dst_offset = 0;
-    if (g.St > 0) ORVB_TRY(gemm_run(&ga, st));
+    const size_t tw = static_cast<size_t>(g.St) * D * 2, xp = static_cast<size_t>(g.S) * D * 2;
+    if (g.St > 0 && st_reuse) {
+      ORVB_CHECK_CUDA(cudaMemcpy2DAsync(ws.x, xp, ws.text_cache, tw, tw, g.B, cudaMemcpyDeviceToDevice, st));
+    } else if (g.St > 0) {
+      ORVB_TRY(gemm_run(&ga, st));
+      if (st_save) ORVB_CHECK_CUDA(cudaMemcpy2DAsync(ws.text_cache, tw, ws.x, xp, tw, g.B, cudaMemcpyDeviceToDevice, st));
+    }
   }
 
   // ---- 4. visual controls (depth / semantic latents), cogvideox_control.py:827-858 -----------------
@@ -461,22 +480,32 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
                  c.num_control_keys);
     ORVB_REQUIRE(w.combine_w != nullptr, ORVB_EINVAL, "orvb_forward: initial_combine_linear is not bound");
     const int ldc = c.num_control_keys * D;
-    int slot = 0;
-    for (int k = 0; k < 2; ++k) {
-      if (ctl[k] == nullptr) continue;
-      ORVB_TRY(patchify_launch(ctl[k], ws.patches, g.B, g.F, c.in_channels, g.H, g.W, c.patch_size, c.patch_size_t, st));
-      orvb_gemm_args ga = gemm_base(ws.patches, w.patch_w, w.patch_b, ws.ctrl + slot * D, g.B * g.Sv, D, g.Kp, g.Kp,
-                                    ldc, w.pos_embed ? ORVB_EPI_GATE_RESID : ORVB_EPI_BIAS);
-      if (w.pos_embed) {
-        ga.resid = w.pos_embed_plain ? w.pos_embed_plain : w.pos_embed; ga.ldr = D; ga.resid_mod = g.Sv; ga.resid_views = 1;
+    const size_t ctrl_bytes = static_cast<size_t>(g.B) * g.Sv * ldc * 2;
+    // patch_embed(control) + pos: independent of the noisy latents (step-invariant)
+    if (st_reuse) {
+      ORVB_CHECK_CUDA(cudaMemcpyAsync(ws.ctrl, ws.ctrl_cache, ctrl_bytes, cudaMemcpyDeviceToDevice, st));
+    } else {
+      int slot = 0;
+      for (int k = 0; k < 2; ++k) {
+        if (ctl[k] == nullptr) continue;
+        ORVB_TRY(patchify_launch(ctl[k], ws.patches, g.B, g.F, c.in_channels, g.H, g.W, c.patch_size, c.patch_size_t, st));
+        orvb_gemm_args ga = gemm_base(ws.patches, w.patch_w, w.patch_b, ws.ctrl + slot * D, g.B * g.Sv, D, g.Kp, g.Kp,
+                                      ldc, w.pos_embed ? ORVB_EPI_GATE_RESID : ORVB_EPI_BIAS);
+        if (w.pos_embed) {
+          ga.resid = w.pos_embed_plain ? w.pos_embed_plain : w.pos_embed; ga.ldr = D; ga.resid_mod = g.Sv; ga.resid_views = 1;
+        }
+        ORVB_TRY(gemm_run(&ga, st));
+        ++slot;
       }
-      ORVB_TRY(gemm_run(&ga, st));
+      if (st_save) ORVB_CHECK_CUDA(cudaMemcpyAsync(ws.ctrl_cache, ws.ctrl, ctrl_bytes, cudaMemcpyDeviceToDevice, st));
+    }
+    // + hidden_states (the step-dependent half, :853-855)
+    for (int slot = 0; slot < c.num_control_keys; ++slot) {
       const long n = static_cast<long>(g.B) * g.Sv * (D / 8);
       add_hidden_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(ws.ctrl, ws.x, g.B * g.Sv, D, ldc,
                                                                                 slot * D, g.Sv, g.S, g.St);
       ORVB_CHECK_CUDA(cudaGetLastError());
       ++m->launches;
-      ++slot;
     }
     orvb_gemm_args ga = gemm_base(ws.ctrl, w.combine_w, w.combine_b, ws.x, g.B * g.Sv, D, ldc, ldc, D,
                                   ORVB_EPI_GATE_RESID);
@@ -517,7 +546,7 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
       ORVB_TRY(gemm_run(&o1, st));
       orvb_gemm_args o2 = gemm_base(ws.tmp_mv, mw.proj_out_w, mw.proj_out_b, ws.x, Mv, D, D, D, D, ORVB_EPI_GATE_RESID);
       o2.mv_tokens = tok; o2.mv_frames = g.Fp; o2.mv_views = g.V; o2.dst_rows = g.S; o2.dst_offset = g.St;
-      o2.resid = ws.x; o2.ldr = D; o2.gate = modv; o2.gate_ld = 6 * D; o2.gate_text_off = 5 * D; o2.gate_video_off = 2 * D;
+      o2.resid = ws.x; o2.ldr = D; o2.gate = modv; o2.gate_ld = mwid * D; o2.gate_text_off = gate_text_off; o2.gate_video_off = 2 * D;
       o2.rowmap = rm0;
       ORVB_TRY(gemm_run(&o2, st));
     }
@@ -544,7 +573,7 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
     ORVB_TRY(attention_launch(ws.qkv, ws.att, g.B, g.S, c.heads, scale, 0, g.S, st));
 
     orvb_gemm_args o = gemm_base(ws.att, bw.out_w, bw.out_b, ws.x, g.R, D, D, D, D, ORVB_EPI_GATE_RESID);
-    o.resid = ws.x; o.ldr = D; o.gate = mod1; o.gate_ld = 6 * D; o.gate_text_off = 5 * D; o.gate_video_off = 2 * D;
+    o.resid = ws.x; o.ldr = D; o.gate = mod1; o.gate_ld = mwid * D; o.gate_text_off = gate_text_off; o.gate_video_off = 2 * D;
     o.rowmap = rm;
     ORVB_CLS(ORVB_PC_OUT);
     ORVB_TRY(gemm_run(&o, st));
@@ -555,7 +584,7 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
 
     orvb_gemm_args f1 = gemm_base(ws.xn, bw.ff1_w, bw.ff1_b, ws.ffh, g.R, g.FF, D, D, g.FF, ORVB_EPI_GELU);
     orvb_gemm_args f2 = gemm_base(ws.ffh, bw.ff2_w, bw.ff2_b, ws.x, g.R, D, g.FF, g.FF, D, ORVB_EPI_GATE_RESID);
-    f2.resid = ws.x; f2.ldr = D; f2.gate = mod2; f2.gate_ld = 6 * D; f2.gate_text_off = 5 * D; f2.gate_video_off = 2 * D;
+    f2.resid = ws.x; f2.ldr = D; f2.gate = mod2; f2.gate_ld = mwid * D; f2.gate_text_off = gate_text_off; f2.gate_video_off = 2 * D;
     f2.rowmap = rm;
     if (ff_chain_enabled() && g.R > 128) {
       // experimental, opt-in: both GEMMs in one persistent launch (gemm.cu, gemm2_chain_kernel)
@@ -615,29 +644,20 @@ extern "C" int orvb_model_create(const orvb_config* cfg, orvb_model** out) {
   ORVB_REQUIRE(cfg->layers > 0 && cfg->ff_dim % 8 == 0 && cfg->time_embed_dim % 8 == 0 && cfg->text_embed_dim % 8 == 0,
                ORVB_ESHAPE, "orvb_model_create: bad layer/ff/time/text dims");
   ORVB_REQUIRE(cfg->patch_size == 2, ORVB_ESHAPE, "orvb_model_create: patch_size must be 2");
+  ORVB_REQUIRE(cfg->modulate_text || !cfg->multiview, ORVB_ESHAPE,
+               "orvb_model_create: multiview without text modulation is not a configuration ORV ships");
   int rc = check_arch();
   if (rc != ORVB_OK) return rc;
   orvb_model* m = new orvb_model();
   m->cfg = *cfg;
-  for (int i = 0; i < 2; ++i) {
-    cudaError_t e = cudaMalloc(&m->jobs_dev_[i], sizeof(SkinnyJob) * 3 * cfg->layers);
-    if (e == cudaSuccess) e = cudaMalloc(&m->ab_sites_dev_[i], sizeof(AbSite) * (3 * cfg->layers + 1));
-    if (e != cudaSuccess) {
-      set_error("orvb_model_create: cudaMalloc(job / site table) failed: %s", cudaGetErrorString(e));
-      orvb_model_destroy(m);
-      return ORVB_ECUDA;
-    }
-  }
   *out = m;
   return ORVB_OK;
 }
 
 extern "C" void orvb_model_destroy(orvb_model* m) {
   if (m == nullptr) return;
-  for (int i = 0; i < 2; ++i) {
-    if (m->jobs_dev_[i]) cudaFree(m->jobs_dev_[i]);
-    if (m->ab_sites_dev_[i]) cudaFree(m->ab_sites_dev_[i]);
-  }
+  if (m->blocks_dev) cudaFree(m->blocks_dev);
+  if (m->mv_blocks_dev) cudaFree(m->mv_blocks_dev);
   for (cudaEvent_t e : m->ev) cudaEventDestroy(e);
   delete m;
 }
@@ -667,7 +687,14 @@ extern "C" int orvb_model_bind_weights(orvb_model* m, const orvb_weights* w) {
   }
   m->w.blocks_host = nullptr;
   m->w.mv_blocks_host = nullptr;
-  m->jobs_y_base_[0] = m->jobs_y_base_[1] = nullptr;
+  // device copies of the per-block pointer structs (read by fill_tables_kernel); synchronous, outside any capture
+  const size_t bb = sizeof(orvb_block_weights) * m->cfg.layers;
+  if (m->blocks_dev == nullptr) ORVB_CHECK_CUDA(cudaMalloc(&m->blocks_dev, bb));
+  ORVB_CHECK_CUDA(cudaMemcpy(m->blocks_dev, m->blocks.data(), bb, cudaMemcpyHostToDevice));
+  if (m->cfg.multiview) {
+    if (m->mv_blocks_dev == nullptr) ORVB_CHECK_CUDA(cudaMalloc(&m->mv_blocks_dev, bb));
+    ORVB_CHECK_CUDA(cudaMemcpy(m->mv_blocks_dev, m->mv_blocks.data(), bb, cudaMemcpyHostToDevice));
+  }
   m->bound = true;
   return ORVB_OK;
 }
@@ -733,7 +760,7 @@ extern "C" int orvb_modulation_schedule(orvb_model* m, const orvb_shape* s, int3
   m->ev_cls.clear();
   ModIn in;
   in.timesteps = timesteps; in.ofs = ofs; in.actions = actions; in.action_mask = action_mask;
-  return build_modulation(m, gv, in, ws, 1, static_cast<cudaStream_t>(stream));
+  return build_modulation(m, gv, in, ws, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int orvb_modulation_select(const orvb_model* m, const orvb_shape* s, int32_t steps, int32_t step,
@@ -748,14 +775,15 @@ extern "C" int orvb_modulation_select(const orvb_model* m, const orvb_shape* s, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t rows1 = static_cast<size_t>(g1.B) * g1.G, rowsv = static_cast<size_t>(gv.B) * gv.G;
   const size_t D = g1.D;
-  // every site: rows [step * B*G, (step+1) * B*G) of its [steps*B*G] row block, mod pitch 6D fp32 / ab pitch 4D bf16
-  ORVB_CHECK_CUDA(cudaMemcpy2DAsync(dst.mod, rows1 * 6 * D * 4, src.mod + static_cast<size_t>(step) * rows1 * 6 * D,
-                                    rowsv * 6 * D * 4, rows1 * 6 * D * 4, g1.sites, cudaMemcpyDeviceToDevice, st));
+  // every site: rows [step * B*G, (step+1) * B*G) of its [steps*B*G] row block, mod pitch 6D (3D without text modulation) fp32 / ab pitch 4D bf16
+  const size_t mwD = static_cast<size_t>(mod_width(m->cfg)) * D;
+  ORVB_CHECK_CUDA(cudaMemcpy2DAsync(dst.mod, rows1 * mwD * 4, src.mod + static_cast<size_t>(step) * rows1 * mwD,
+                                    rowsv * mwD * 4, rows1 * mwD * 4, g1.sites, cudaMemcpyDeviceToDevice, st));
   ORVB_CHECK_CUDA(cudaMemcpy2DAsync(dst.ab, rows1 * 4 * D * 2, src.ab + static_cast<size_t>(step) * rows1 * 4 * D,
                                     rowsv * 4 * D * 2, rows1 * 4 * D * 2, g1.sites, cudaMemcpyDeviceToDevice, st));
   // norm_out's table is packed with row pitch 2D inside its slot
   const size_t so = static_cast<size_t>(2 * m->cfg.layers);
-  ORVB_CHECK_CUDA(cudaMemcpyAsync(dst.mod + so * rows1 * 6 * D, src.mod + so * rowsv * 6 * D + static_cast<size_t>(step) * rows1 * 2 * D,
+  ORVB_CHECK_CUDA(cudaMemcpyAsync(dst.mod + so * rows1 * mwD, src.mod + so * rowsv * mwD + static_cast<size_t>(step) * rows1 * 2 * D,
                                   rows1 * 2 * D * 4, cudaMemcpyDeviceToDevice, st));
   return ORVB_OK;
 }

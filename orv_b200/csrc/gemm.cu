@@ -37,6 +37,7 @@ struct GemmDev {
   const float *rope_cos, *rope_sin;
   int num_m_tiles, num_n_tiles;
   int tma_store;  // pair kernel: stage full 64-column units in shared memory and write them with TMA
+  int out_f32;    // test mode: `out` is fp32, written before the bf16 rounding (direct stores only)
 };
 
 constexpr int BM = 128;
@@ -196,6 +197,14 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float (&v)[64], 
       o.z = pack_bf16(v[j * 8 + 4], v[j * 8 + 5]);
       o.w = pack_bf16(v[j * 8 + 6], v[j * 8 + 7]);
       *reinterpret_cast<uint4*>(stage_row + ((j ^ sw) << 4)) = o;
+    }
+    return;
+  }
+  if (p.out_f32) {
+    float* of = reinterpret_cast<float*>(p.out) + static_cast<size_t>(out_row) * p.ldo + n0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j * 4 < ncols) *reinterpret_cast<float4*>(of + j * 4) = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
     }
     return;
   }
@@ -1070,7 +1079,7 @@ int gemm_prepare(const orvb_gemm_args* a, int bn_override, CUtensorMap* ta, CUte
   rc = make_tmap_2d_bf16(tb, a->w, a->n, a->k, a->ldw, pair ? (-bn) / 2 : bn, BK);
   if (rc != ORVB_OK) return rc;
   // Output through TMA (pair kernel, rows written in place): [32 rows x 64 cols] boxes of the [M, N] output
-  const bool tma_store = pair && a->src_rows == 0 && a->mv_tokens == 0;
+  const bool tma_store = pair && a->src_rows == 0 && a->mv_tokens == 0 && !a->out_f32;
   if (tma_store) {
     rc = make_tmap_2d_bf16(to, a->out, a->m, a->n, a->ldo, 32, 64);
     if (rc != ORVB_OK) return rc;
@@ -1079,6 +1088,7 @@ int gemm_prepare(const orvb_gemm_args* a, int bn_override, CUtensorMap* ta, CUte
   }
   GemmDev d;
   d.tma_store = tma_store ? 1 : 0;
+  d.out_f32 = a->out_f32 ? 1 : 0;
   d.M = a->m; d.N = a->n; d.K = a->k;
   d.out = static_cast<bf16*>(a->out); d.ldo = a->ldo;
   d.bias = static_cast<const bf16*>(a->bias);
@@ -1140,7 +1150,31 @@ int gemm_chain_run(const orvb_gemm_args* first, const orvb_gemm_args* second, ui
     attr_set = true;
   }
   const int tiles = p0.num_m_tiles * p0.num_n_tiles + p1.num_m_tiles * p1.num_n_tiles;
-  const int clusters = sm_count() / 2;  // every cluster must be resident: the stripe dependencies are waited on
+  // Every cluster must be co-resident: the stripe dependencies are waited on inside the kernel.  Ask the driver how
+  // many clusters of this kernel (2 CTAs, 227 KB of shared memory each) the device can hold at once instead of
+  // assuming one per SM pair (MPS partitions, GPCs with an odd number of usable SMs).
+  static int max_clusters = -1;
+  if (max_clusters < 0) {
+    cudaLaunchConfig_t qc = {};
+    qc.gridDim = dim3(sm_count() / 2 * 2);
+    qc.blockDim = dim3(g2_threads(ORVB_EPI_GELU));
+    qc.dynamicSmemBytes = G2_SMEM_BYTES;
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+    qc.attrs = qa;
+    qc.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &qc) != cudaSuccess) { n = 0; (void)cudaGetLastError(); }
+    max_clusters = n;
+  }
+  if (max_clusters < 2) {  // cannot guarantee co-residency: the two-launch path is always correct
+    int rc2 = gemm_launch_prepared(ta0, tb0, to0, p0, bn0, first->epilogue, stream);
+    if (rc2 != ORVB_OK) return rc2;
+    return gemm_launch_prepared(ta1, tb1, to1, p1, bn1, second->epilogue, stream);
+  }
+  int clusters = sm_count() / 2;
+  if (clusters > max_clusters) clusters = max_clusters;
   const int grid = 2 * (tiles < clusters ? tiles : clusters);
   const uint32_t target = 16u * static_cast<uint32_t>(p0.num_n_tiles);  // 8 epilogue warps x 2 CTAs per tile
   ORVB_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(g2_threads(ORVB_EPI_GELU)), G2_SMEM_BYTES, stream, true, ta0, tb0, to0,

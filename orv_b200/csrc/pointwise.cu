@@ -47,7 +47,21 @@ struct LnDev {
   int in_video_only;
   const bf16* ab;  // optional pre-combined table: per group row [text A | text B | video A | video B], each `dim`
   int ab_ld;
+  int y_f32;       // test mode: y is fp32 (generic kernel only)
 };
+
+__device__ __forceinline__ void ln_store8(const LnDev& p, int row, int c, const float (&o)[8]) {
+  if (p.y_f32) {
+    float* yf = reinterpret_cast<float*>(p.y) + static_cast<size_t>(row) * p.dim + c * 8;
+    *reinterpret_cast<float4*>(yf) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(yf + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    return;
+  }
+  uint4 u;
+  u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]);
+  u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
+  *reinterpret_cast<uint4*>(p.y + static_cast<size_t>(row) * p.dim + c * 8) = u;
+}
 
 template <int MAXC>
 __device__ __forceinline__ void ln_stats(const float (&v)[MAXC][8], int nchunks, int lane, int dim, float eps,
@@ -115,7 +129,6 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const LnDev p) {
       }
     }
   }
-  bf16* yr = p.y + static_cast<size_t>(row) * p.dim;
   if (p.ab != nullptr) {
     // y = xhat * A_g + B_g with A = w * (1 + scale), B = b * (1 + scale) + shift folded once per forward
     // (ab_combine_kernel): one memory phase, every load issued before the reductions.
@@ -141,10 +154,7 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const LnDev p) {
         unpack8(bv[i], b8);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * a8[j] + b8[j];
-        uint4 u;
-        u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]);
-        u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
-        *reinterpret_cast<uint4*>(yr + c * 8) = u;
+        ln_store8(p, row, c, o);
       }
     }
     return;
@@ -184,10 +194,7 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const LnDev p) {
         o[4] = o[4] * (1.f + s1.x) + h1.x; o[5] = o[5] * (1.f + s1.y) + h1.y;
         o[6] = o[6] * (1.f + s1.z) + h1.z; o[7] = o[7] * (1.f + s1.w) + h1.w;
       }
-      uint4 u;
-      u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]);
-      u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
-      *reinterpret_cast<uint4*>(yr + c * 8) = u;
+      ln_store8(p, row, c, o);
     }
   }
 }
@@ -320,13 +327,15 @@ int ln_modulate_launch(const orvb_ln_args* a, cudaStream_t stream) {
   d.mod = a->mod; d.mod_ld = a->mod_ld; d.text_off = a->text_off; d.video_off = a->video_off;
   d.scale_first = a->scale_first; d.rm = a->rowmap; d.in_video_only = a->in_video_only;
   d.ab = static_cast<const bf16*>(a->ab); d.ab_ld = a->ab_ld;
+  d.y_f32 = a->y_f32 ? 1 : 0;
   ORVB_REQUIRE(d.ab == nullptr || (a->ab_ld % 8 == 0 && a->ab_ld >= 4 * a->dim), ORVB_ESHAPE,
                "orvb_ln_modulate: ab_ld must be a multiple of 8 and >= 4*dim");
   const int rows_per_block = 8;
   dim3 grid((a->rows + rows_per_block - 1) / rows_per_block);
   const int nchunks = a->dim / 8;
   // A then B must be adjacent in a table row (ab_combine writes them so) for the staged copy of the hot kernel
-  if (d.ab != nullptr && d.pre_w == nullptr && !d.in_video_only && d.rm.seq_len > 0 && d.rm.text_len >= 8 &&
+  if (d.ab != nullptr && !d.y_f32 && d.pre_w == nullptr && !d.in_video_only && d.rm.seq_len > 0 &&
+      (d.rm.text_len >= 8 || d.rm.text_len == 0) &&
       (d.rm.tokens_per_group <= 0 || d.rm.tokens_per_group >= 8) && d.rm.seq_len - d.rm.text_len >= 8) {
     const int smem = 2 * 2 * nchunks * 16;
     if (nchunks <= 32 * 8) ORVB_CHECK_CUDA(launch_kernel(ln_ab_kernel<8>, grid, dim3(256), smem, stream, true, d));

@@ -30,7 +30,7 @@ int unpatchify_launch(const void* y, void* out, int B, int F, int C, int H, int 
                       cudaStream_t stream);
 int sampler_step_launch(const orvb_sampler_step_args* a, cudaStream_t stream);
 int attention_launch(const void* qkv, void* out, int batch, int seq_len, int heads, float scale, int q_row0,
-                     int q_rows, cudaStream_t stream);
+                     int q_rows, cudaStream_t stream, int out_f32 = 0);
 // (b v)(text | f s) rows -> (b f)(v text | v s) rows, `width` bf16 per row (MVBlock rearranges, :328-331)
 int mv_gather_launch(const void* src, void* dst, int clips, int views, int frames, int text_len, int tokens,
                      int width, cudaStream_t stream);

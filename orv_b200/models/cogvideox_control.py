@@ -356,6 +356,8 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
         V = num_views if (c.multiview and num_views > 1) else 1
         B, Fr = Bc * V, VF // V
         self._ensure_native((Fr, H, W, V))
+        if not c.modulate_encoder_hidden_states:
+            text_len = 0  # the kernels run on the video rows alone (see forward)
         ts = torch.as_tensor(timesteps, dtype=torch.float32).reshape(-1)
         steps = ts.numel()
         act_rows, masks, is_masks, action_frames = None, None, None, 0
@@ -438,7 +440,8 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
             ofs_embed_dim=c.ofs_embed_dim or 0, flip_sin_to_cos=int(bool(c.flip_sin_to_cos)),
             freq_shift=float(c.freq_shift), norm_eps=float(c.norm_eps), visual_guidance=int(bool(c.visual_guidance)),
             num_control_keys=c.num_control_keys, multiview=int(bool(c.multiview)), max_n_view=c.max_n_view,
-            action_state_dim=7, action_compress=4, action_hidden=4 * c.time_embed_dim)
+            action_state_dim=7, action_compress=4, action_hidden=4 * c.time_embed_dim,
+            modulate_text=int(bool(c.modulate_encoder_hidden_states)))
 
     def _build_pack(self):
         """Copies every weight the kernels read into ONE contiguous bf16 arena (256-byte aligned slots, q/k/v
@@ -447,9 +450,8 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("CogVideoXTransformer3DModelTraj (orv_b200) runs on CUDA only: move the model to a "
                                "B200 with .to('cuda') — there is no CPU path")
-        if not self.config.modulate_encoder_hidden_states:
-            raise NotImplementedError("orv_b200 implements modulate_encoder_hidden_states=True (all 2B/5B ORV "
-                                      "configs); the from-scratch 1.4B variants are out of scope")
+        if not self.config.modulate_encoder_hidden_states and self.config.multiview:
+            raise NotImplementedError("multiview without text modulation: no ORV config ships this combination")
         entries = []  # (key, [(param, rows_slice or None)], shape, pad_cols)
 
         def add(key, *params, pad_cols=0):
@@ -637,6 +639,7 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
         _tap: Optional[Tuple[int, torch.Tensor]] = None,
         _static_out: bool = False,
         _mod_step: Optional[int] = None,
+        _static_mode: int = L.STATIC_COMPUTE,
     ):
         c = self.config
         if timestep_cond is not None:
@@ -664,14 +667,21 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
         if Cin != c.in_channels:
             raise RuntimeError(f"expected {c.in_channels} input channels, got {hidden_states.shape=}")
         St = encoder_hidden_states.shape[1]
+        if encoder_hidden_states.shape[0] != B:
+            raise RuntimeError(f"Sizes of tensors must match except in dimension 1. Expected size {encoder_hidden_states.shape[0]} "
+                               f"but got size {B} for tensor number 1 in the list.")  # torch.cat in patch_embed
         pos_key = (Fr, H, W, V)
         if (not c.use_rotary_positional_embeddings) and St != c.max_text_seq_length:
             raise RuntimeError(f"The size of tensor a ({St + (Fr // (c.patch_size_t or 1)) * (H // 2) * (W // 2)}) must "
                                f"match the size of the positional table (text length {c.max_text_seq_length})")
         self._ensure_native(pos_key)
+        if not c.modulate_encoder_hidden_states:
+            # Reference :404-424: the text stream never enters attention or the FFN and is dropped before norm_out, so
+            # the output does not depend on it: the kernels run on the video rows alone.
+            St = 0
 
         hs = hidden_states.to(torch.bfloat16).contiguous()
-        text = encoder_hidden_states.to(torch.bfloat16).contiguous()
+        text = encoder_hidden_states.to(torch.bfloat16).contiguous() if St > 0 else None
         if not torch.is_tensor(timestep):
             timestep = torch.tensor([timestep], device=dev)
         ts = timestep.to(device=dev, dtype=torch.float32).reshape(-1)
@@ -782,7 +792,7 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
 
         a = L.ForwardArgs()
         a.shape = shape
-        a.hidden_states, a.text, a.timesteps = hs.data_ptr(), text.data_ptr(), sm.ts.data_ptr()
+        a.hidden_states, a.text, a.timesteps = hs.data_ptr(), L.ptr(text), sm.ts.data_ptr()
         a.ofs = ofs_val
         a.actions = sm.act.data_ptr() if act_in is not None else None
         a.action_mask = sm.mask.data_ptr() if mask_u8 is not None else None
@@ -795,18 +805,19 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
         else:
             a.tap_layer = -1
         a.skip_modulation = 1 if sched is not None else 0
+        a.static_mode = int(_static_mode)
 
         def launch():
             L.check(lib.orvb_forward(self._handle, C.byref(a), L.current_stream()), "orvb_forward")
 
-        gkey = (wkey, hs.data_ptr(), text.data_ptr(), L.ptr(depths), L.ptr(labels), L.ptr(rope_cos), L.ptr(rope_sin),
-                ofs_val, mask_u8 is not None, sched is not None)
+        gkey = (wkey, hs.data_ptr(), L.ptr(text), L.ptr(depths), L.ptr(labels), L.ptr(rope_cos), L.ptr(rope_sin),
+                ofs_val, mask_u8 is not None, sched is not None, int(_static_mode))
         if self.use_cuda_graph and _tap is None and not self._profiling:
             ent = self._graphs.get(gkey)
             if ent is None:
                 # first sighting of this (shape, addresses) combination: run eagerly (also sets kernel
                 # attributes and uploads the AdaLN job table, neither of which may happen during capture)
-                if len(self._graphs) >= 8:
+                if len(self._graphs) >= 12:
                     self._graphs.pop(next(iter(self._graphs)))
                 self._graphs[gkey] = False
                 launch()

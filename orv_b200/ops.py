@@ -31,7 +31,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
          row_remap=(0, 0, 0), resid: Optional[torch.Tensor] = None, resid_mod: int = 0, resid_views: int = 1,
          resid_view_stride: int = 0, gate: Optional[torch.Tensor] = None, gate_text_off: int = 0,
          gate_video_off: int = 0, rm: Optional[L.RowMap] = None, qk_dim: int = 0, q_norm=None, k_norm=None,
-         qk_eps: float = 1e-6, rope=None, bn: int = 0, launch: bool = True):
+         qk_eps: float = 1e-6, rope=None, bn: int = 0, launch: bool = True, out_f32: bool = False):
     """out = epilogue(a @ w.T)  — a [M,K] bf16, w [N,K] bf16 (nn.Linear layout).  `launch=False` only fills and
     returns `(GemmArgs, out)` (used by `gemm_chain`)."""
     _req(a, torch.bfloat16, "a")
@@ -39,13 +39,15 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     M, K = a.shape
     N = w.shape[0]
     assert w.shape[1] == K
+    odt = torch.float32 if out_f32 else torch.bfloat16  # out_f32: tight-tolerance test mode (fp32 before the rounding)
     if out is None:
         rows = M if row_remap[0] == 0 else (M // row_remap[0]) * row_remap[1]
-        out = torch.empty((rows, N), dtype=torch.bfloat16, device=a.device)
-    _req(out, torch.bfloat16, "out")
+        out = torch.empty((rows, N), dtype=odt, device=a.device)
+    _req(out, odt, "out")
     args = L.GemmArgs()
+    args.out_f32 = int(out_f32)
     args.a, args.w = a.data_ptr(), w.data_ptr()
-    args.out = out.data_ptr() + out_col_offset * 2
+    args.out = out.data_ptr() + out_col_offset * out.element_size()
     args.bias = L.ptr(bias)
     args.m, args.n, args.k = M, N, K
     args.lda, args.ldw = a.stride(0), w.stride(0)
@@ -94,20 +96,26 @@ def gemm_chain(first, second) -> torch.Tensor:
 
 
 def attention(qkv: torch.Tensor, batch: int, seq_len: int, heads: int, scale: float,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, q_row0: int = 0, q_rows: int = 0, out_f32: bool = False) -> torch.Tensor:
+    """Non-causal attention over the packed Q | K | V buffer; `q_row0/q_rows` select a query window (compact output);
+    `out_f32` is the tight-tolerance test mode (fp32 output before the bf16 rounding)."""
     _req(qkv, torch.bfloat16, "qkv")
     assert qkv.shape == (batch * seq_len, 3 * heads * 64)
+    nq = q_rows if q_rows > 0 else seq_len
+    odt = torch.float32 if out_f32 else torch.bfloat16
     if out is None:
-        out = torch.empty((batch * seq_len, heads * 64), dtype=torch.bfloat16, device=qkv.device)
-    L.check(L.load().orvb_attention_bf16(qkv.data_ptr(), out.data_ptr(), batch, seq_len, heads, scale,
-                                         L.current_stream()), "orvb_attention_bf16")
+        out = torch.empty((batch * nq, heads * 64), dtype=odt, device=qkv.device)
+    _req(out, odt, "out")
+    a = L.AttentionArgs(qkv=qkv.data_ptr(), out=out.data_ptr(), batch=batch, seq_len=seq_len, heads=heads, scale=scale,
+                        q_row0=q_row0, q_rows=q_rows, out_f32=int(out_f32))
+    L.check(L.load().orvb_attention(C.byref(a), L.current_stream()), "orvb_attention")
     return out
 
 
 def ln_modulate(x: torch.Tensor, ln_w, ln_b, eps: float, mod: Optional[torch.Tensor] = None, text_off: int = 0,
                 video_off: int = 0, scale_first: bool = False, rm: Optional[L.RowMap] = None,
                 in_video_only: bool = False, out: Optional[torch.Tensor] = None,
-                ab: Optional[torch.Tensor] = None) -> torch.Tensor:
+                ab: Optional[torch.Tensor] = None, out_f32: bool = False) -> torch.Tensor:
     """LayerNorm + AdaLN modulate.  `ab` (bf16 [groups, 4*dim] = text A | text B | video A | video B per group) is the
     folded form the forward uses: y = xhat * A + B with A = w (1 + scale), B = b (1 + scale) + shift."""
     _req(x, torch.bfloat16, "x")
@@ -118,8 +126,9 @@ def ln_modulate(x: torch.Tensor, ln_w, ln_b, eps: float, mod: Optional[torch.Ten
         nb = rows_in // rmap.seq_len
         rows = nb * (rmap.seq_len - rmap.text_len)
     if out is None:
-        out = torch.empty((rows, dim), dtype=torch.bfloat16, device=x.device)
+        out = torch.empty((rows, dim), dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
     a = L.LnArgs()
+    a.y_f32 = int(out_f32)
     a.x, a.y = x.data_ptr(), out.data_ptr()
     a.ln_w, a.ln_b = L.ptr(ln_w), L.ptr(ln_b)
     a.rows, a.dim, a.eps = rows, dim, eps

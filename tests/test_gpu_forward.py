@@ -2,6 +2,7 @@
 import pytest
 import torch
 
+from _gates import assert_forward_close
 from oracle import flat_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -58,6 +59,7 @@ def run_case(cfg, B, Fr, H, W, controls=False, rope=False, ofs=None, n_actions=8
     torch.cuda.synchronize()
     assert out.shape == ref.shape
     assert torch.isfinite(out.float()).all()
+    assert_forward_close(out, ref, 1.5e-2, 3e-2, 8e-2, "small forward vs fp32 oracle")  # mean, max-abs, worst row
     return rel_err(out, ref), m
 
 
@@ -74,6 +76,13 @@ def test_forward_small_no_actions_batch2():
 
 def test_forward_small_controls():
     e, _ = run_case(small_cfg(visual_guidance=True), 2, 3, 6, 8, controls=True)
+    assert e < 1.5e-2, e
+
+
+@pytest.mark.parametrize("use_actions", [True, False])
+def test_forward_small_no_text_modulation(use_actions):
+    """modulate_encoder_hidden_states=False (reference :70-99, :404-424; the from-scratch 1.4B configs)."""
+    e, _ = run_case(small_cfg(modulate_encoder_hidden_states=False), 2, 3, 6, 8, use_actions=use_actions)
     assert e < 1.5e-2, e
 
 

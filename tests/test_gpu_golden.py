@@ -5,10 +5,14 @@ import os
 import pytest
 import torch
 
+from _gates import assert_forward_close, forward_errors
 from oracle import flat_oracle as O
 from oracle import make_golden as G
 
 pytestmark = pytest.mark.gpu
+# Gates of a bf16 forward against an fp32 reference (2-layer goldens).  Yardstick: the reference's own deployed
+# precision (eager torch bf16) sits at mean 7.5e-3, max-abs/max 1.2e-2, worst row 5e-2 on these cases.
+MEAN_TOL, MAX_TOL, ROW_TOL = 1.5e-2, 3e-2, 8e-2
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
@@ -25,11 +29,10 @@ def _rel(a, b):
     return ((a - b).abs().mean() / b.abs().mean()).item()
 
 
-@pytest.mark.parametrize("name", ["fwd_actions", "fwd_noactions_b2", "fwd_controls_b2", "fwd_rope_pt2_ofs",
-                                  "fwd_othergeom", "fwd_multiview_v3"])
+@pytest.mark.parametrize("name", sorted(G.FORWARD_CASES))
 def test_forward_vs_reference_golden(name):
-    """bf16 kernels + bf16-rounded weights/inputs vs the reference's fp32 run: mean relative error < 1.5e-2
-    (2 layers; torch-bf16 itself sits at ~5e-3 here)."""
+    """bf16 kernels + bf16-rounded weights/inputs vs the reference's fp32 run (2 layers): mean, max-abs and worst-row
+    gates.  Includes the modulate_encoder_hidden_states=False cases (reference :70-99, :404-424)."""
     blob = torch.load(os.path.join(GOLDEN, name + ".pt"), weights_only=False)
     cfg, sd, inp, rope, ofs, t, V = G.build_case(name)
     m = _model(cfg, sd)
@@ -44,7 +47,7 @@ def test_forward_vs_reference_golden(name):
                 image_rotary_emb=(rope[0].cuda(), rope[1].cuda()) if rope else None, return_dict=False,
                 num_views=V)[0]
     assert out.shape == blob["output"].shape
-    assert _rel(out, blob["output"]) < 1.5e-2
+    assert_forward_close(out, blob["output"], MEAN_TOL, MAX_TOL, ROW_TOL, name)
 
 
 def test_eval_time_action_mask_bug_compat():
@@ -93,7 +96,7 @@ def test_pipeline_ddim_vs_reference_golden():
                generator=torch.Generator().manual_seed(42), controls_or_guidances={"actions": inp["actions"]},
                output_type="latent", return_dict=False)[0]
     assert out.shape == blob["latents"].shape and out.dtype == torch.float32
-    assert _rel(out, blob["latents"]) < 2e-2
+    assert_forward_close(out, blob["latents"], 2e-2, 4e-2, 1e-1, "pipeline ddim golden")
 
 
 @pytest.mark.parametrize("kind,steps,guidance", [("dpm", 4, 1.0), ("ddim", 3, 1.0)])
@@ -118,7 +121,111 @@ def test_pipeline_fused_bf16_vs_oracle_pipeline(kind, steps, guidance):
     with torch.no_grad():
         ref = O.pipeline_call(sdb, cfg, kind, moments, inp["text"].bfloat16(), 9, 48, 64, steps, guidance,
                               torch.Generator().manual_seed(42), actions=inp["actions"].bfloat16())
-    assert out.dtype == torch.bfloat16 and _rel(out, ref) < 3e-2
+    assert out.dtype == torch.bfloat16
+    assert_forward_close(out, ref, 3e-2, 6e-2, 1.5e-1, f"fused {kind} pipeline vs oracle pipeline (both bf16)")
+
+
+def _pipe(cfg, sd, kind="dpm"):
+    from orv_b200 import CogVideoXDDIMScheduler, CogVideoXDPMScheduler, CogVideoXImageToVideoPipelineTraj
+    from orv_b200.models.pipeline_control import default_vae_config
+    sch = (CogVideoXDDIMScheduler if kind == "ddim" else CogVideoXDPMScheduler)(timestep_spacing="trailing")
+    return CogVideoXImageToVideoPipelineTraj(None, None, default_vae_config(), _model(cfg, sd), sch)
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_pipeline_cfg_guidance6_vs_reference_golden(fused):
+    """Classifier-free guidance through `pipe()` (guidance 6: negative | positive prompt batch, fp32 CFG combine,
+    cogvideox_control.py:1409-1437) against the reference pipeline's own 3-step DPM run.  fused=False: fp32 latents as
+    in the golden run (torch-op scheduler path); fused=True: bf16 latents, `orvb_sampler_step` doing the CFG combine
+    + DPM update, CUDA-graph replay of the batch-2 forward.  The reference cannot run CFG together with actions (P5),
+    so the golden has none."""
+    blob = torch.load(os.path.join(GOLDEN, "sampler_dpm_3steps_g6.pt"), weights_only=False)
+    cfg = O.default_config(**G.BASE)
+    sd = O.synthetic_state_dict(cfg, seed=0, std=0.05)
+    pipe = _pipe(cfg, sd)
+    inp = O.synthetic_inputs(cfg, 1, 3, 6, 8, seed=1, n_actions=8)
+    dt = torch.bfloat16 if fused else torch.float32
+    text = inp["text"].cuda().to(dt)
+    out = pipe(image=blob["moments"].to(dt), prompt=None, prompt_embeds=text, negative_prompt_embeds=torch.zeros_like(text),
+               height=48, width=64, num_frames=9, num_inference_steps=3, guidance_scale=6.0,
+               generator=torch.Generator().manual_seed(42), controls_or_guidances={}, output_type="latent",
+               return_dict=False)[0]
+    assert out.shape == blob["latents"].shape and out.dtype == dt
+    if fused:  # bf16 noise draws differ from the golden's fp32 ones: compare with the oracle pipeline in bf16 instead
+        sdb = {k: v.bfloat16() for k, v in sd.items()}
+        with torch.no_grad():
+            ref = O.pipeline_call(sdb, cfg, "dpm", blob["moments"].bfloat16(), inp["text"].bfloat16(), 9, 48, 64, 3, 6.0,
+                                  torch.Generator().manual_seed(42), actions=None,
+                                  negative_prompt_embeds=torch.zeros_like(inp["text"]).bfloat16())
+        assert_forward_close(out, ref, 4e-2, 8e-2, 2e-1, "CFG g=6 fused bf16 vs oracle pipeline bf16")
+    else:
+        # guidance 6 amplifies the bf16 forward noise of (cond - uncond) sixfold
+        assert_forward_close(out, blob["latents"], 4e-2, 8e-2, 2e-1, "CFG g=6 vs reference golden")
+
+
+@pytest.mark.parametrize("name", sorted(G.PIPELINE_CASES))
+def test_pipeline_controls_multiview_vs_reference_golden(name):
+    """Depth / label VAE moments through `pipe()` — sampled with the global RNG, scaled, duplicated on the channel axis
+    (cogvideox_control.py:1331-1364) — and the 3-view path (num_views=3, config 5) against the reference pipeline's
+    own output (fp32 golden, CPU RNG streams reproduced exactly: the draws happen on the host in both)."""
+    opt = G.PIPELINE_CASES[name]
+    blob = torch.load(os.path.join(GOLDEN, name + ".pt"), weights_only=False)
+    cfg = O.default_config(**dict(G.BASE, **opt["over"]))
+    sd = O.synthetic_state_dict(cfg, seed=0, std=0.05)
+    pipe = _pipe(cfg, sd, opt["kind"])
+    inp, moments, cg = G.pipeline_case_inputs(cfg, opt["controls"], opt["views"])
+    torch.manual_seed(G.CONTROL_SEED)
+    out = pipe(image=moments, prompt="", prompt_embeds=inp["text"].cuda(), height=48, width=64, num_frames=9,
+               num_inference_steps=opt["steps"], guidance_scale=1.0, generator=torch.Generator().manual_seed(42),
+               controls_or_guidances=cg, output_type="latent", return_dict=False, num_views=opt["views"])[0]
+    assert out.shape == blob["latents"].shape
+    assert_forward_close(out, blob["latents"], 2e-2, 4e-2, 1e-1, name)
+
+
+def test_pipeline_static_cache_and_schedule_are_bit_identical(monkeypatch):
+    """The step-invariant cache (text projection + control embeddings computed by the first iteration only) and the
+    per-clip modulation schedule must not change a single bit of a fused bf16 run with controls."""
+    opt = G.PIPELINE_CASES["sampler_dpm_3steps_controls"]
+    cfg = O.default_config(**dict(G.BASE, **opt["over"]))
+    sd = O.synthetic_state_dict(cfg, seed=0, std=0.05)
+    inp, moments, cg = G.pipeline_case_inputs(cfg, True, 1)
+    outs = []
+    for static, sched in (("1", "1"), ("0", "1"), ("0", "0")):
+        monkeypatch.setenv("ORVB_STATIC_CACHE", static)
+        monkeypatch.setenv("ORVB_MOD_SCHEDULE", sched)
+        pipe = _pipe(cfg, sd)
+        for rep in range(2):  # the second call replays captured graphs
+            torch.manual_seed(G.CONTROL_SEED)
+            outs.append(pipe(image=moments.bfloat16(), prompt="", prompt_embeds=inp["text"].cuda().bfloat16(), height=48,
+                             width=64, num_frames=9, num_inference_steps=4, guidance_scale=1.0,
+                             generator=torch.Generator().manual_seed(42), controls_or_guidances=cg, output_type="latent",
+                             return_dict=False)[0].clone())
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+
+
+def test_graph_replay_alternating_two_shapes():
+    """the AdaLN job / site tables live in the workspace they describe, so a captured graph of shape A must
+    stay correct after shape B ran (per-step modulation path, direct model calls, graph replay on)."""
+    cfg = O.default_config(**G.BASE)
+    sd = O.synthetic_state_dict(cfg, seed=0, std=0.05)
+    m = _model(cfg, sd)
+    assert m.use_cuda_graph
+    cases = {}
+    for B in (1, 3):
+        inp = O.synthetic_inputs(cfg, B, 3, 6, 8, seed=B, n_actions=8)
+        cases[B] = (inp["hidden_states"].cuda().bfloat16(), inp["text"].cuda().bfloat16(),
+                    {"actions": inp["actions"].cuda().bfloat16()})
+    outs = {B: [] for B in cases}
+    with torch.no_grad():
+        for rnd in range(4):  # round 0 eager, round 1 captures, rounds 2-3 replay — always alternating A, B, A, B
+            for B, (hs, text, cg) in cases.items():
+                for t in (801.0, 301.0):
+                    outs[B].append(m(hs, text, cg, torch.full((B,), t, device="cuda"), return_dict=False)[0].clone())
+    for B in cases:
+        for i in range(2, len(outs[B])):
+            assert torch.equal(outs[B][i], outs[B][i % 2]), (B, i)
+        assert not torch.equal(outs[B][0], outs[B][1])
 
 
 def test_full_size_config2_forward_vs_fp32_oracle():
@@ -154,7 +261,10 @@ def test_full_size_config2_forward_vs_fp32_oracle():
     e_ours, e_torch = _rel(out, ref), _rel(tb, ref)
     print(f"full-size rel err: ours {e_ours:.3e}  torch-bf16 {e_torch:.3e}")
     assert e_ours < 1.25 * e_torch + 1e-3
-    assert e_ours < 2e-2
+    _, mx_t, row_t = forward_errors(tb, ref)
+    # max-abs and worst-row gates, absolute and against the reference's deployed precision on the same inputs
+    _, mx, row = assert_forward_close(out, ref, 2e-2, 5e-2, 1e-1, "config 2 full size (3 layers)")
+    assert mx < 1.5 * mx_t + 5e-3 and row < 1.5 * row_t + 5e-3, (mx, mx_t, row, row_t)
 
 
 def _full_geometry_case(cfg_over, B, Fr, H, W, *, controls=False, rope=False, ofs=None, views=1, n_actions=16):
@@ -189,6 +299,9 @@ def _full_geometry_case(cfg_over, B, Fr, H, W, *, controls=False, rope=False, of
                 num_views=views)[0]
     torch.cuda.synchronize()
     assert out.shape == ref.shape and torch.isfinite(out.float()).all()
+    _, mx_t, row_t = forward_errors(tb, ref)
+    _, mx, row = assert_forward_close(out, ref, 2e-2, 5e-2, 1e-1, "full geometry")
+    assert mx < 1.5 * mx_t + 5e-3 and row < 1.5 * row_t + 5e-3, (mx, mx_t, row, row_t)
     return _rel(out, ref), _rel(tb, ref)
 
 
@@ -254,3 +367,4 @@ def test_full_size_config1_ddim_two_steps_pipeline():
     e = _rel(out, ref)
     print(f"config 1 (2 DDIM steps, 30 layers): rel diff vs CPU bf16 oracle pipeline {e:.3e}")
     assert e < 3e-2
+    assert_forward_close(out, ref, 3e-2, 1e-1, 2e-1, "config 1 pipeline (both sides bf16, 30 layers)")

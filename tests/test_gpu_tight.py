@@ -1,0 +1,207 @@
+"""North-star tolerance (rtol = 1e-3, atol = 1e-4) on the floating-point kernels, through the C ABI on a B200.
+
+The product path stores bf16 (one rounding of 2^-9 relative per tensor), which no bf16 implementation — the
+reference's included — can hold to 1e-3 / 1e-4 against fp32 (SURVEY probes P3 / P11).  What CAN be held to it is the
+arithmetic in front of that rounding.  Every kernel therefore has a test-only fp32 output (`out_f32` / `y_f32`: same
+mainloop, same epilogue code, the store skips the bf16 pack); with bf16-exact operands the fp32 result is compared with
+a float64 torch evaluation of the same operator at exactly the north-star tolerance.  Reference lines:
+cogvideox_control.py:117-145 (LayerNormZero), :243-258 (QK-LayerNorm, RoPE, SDPA), :419-443 (gated residuals, FFN).
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+RTOL, ATOL = 1e-3, 1e-4
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from orv_b200 import ops as _ops
+    return _ops
+
+
+def _bf(*shape, k=1.0, seed=None, gen=None):
+    return (torch.randn(*shape, device=DEV, generator=gen) * k).bfloat16()
+
+
+def _close(got, ref, rtol=RTOL, atol=ATOL):
+    assert got.dtype == torch.float32
+    got, ref = got.double(), ref.double()
+    assert torch.isfinite(got).all()
+    bad = (got - ref).abs() > atol + rtol * ref.abs()
+    assert not bad.any(), (f"{int(bad.sum())} of {bad.numel()} elements outside rtol={rtol} atol={atol}; "
+                           f"max abs err {(got - ref).abs().max().item():.3e}")
+
+
+# bn: 0 = the width the library picks, > 0 single-CTA kernel, < 0 CTA-pair kernel with that tile width
+@pytest.mark.parametrize("M,N,K,bn", [(300, 256, 192, 0), (517, 1920, 256, 0), (130, 136, 72, -64), (128, 192, 128, 192),
+                                      (1000, 384, 512, -176), (3226, 1920, 1920, 0)])
+def test_gemm_bias_f32(ops, M, N, K, bn):
+    torch.manual_seed(M + N)
+    a, w, b = _bf(M, K, k=0.5), _bf(N, K, k=0.25), _bf(N)
+    out = ops.gemm(a, w, b, bn=bn, out_f32=True)
+    _close(out, a.double() @ w.double().T + b.double())
+
+
+def test_gemm_gate_resid_rowmap_f32(ops):
+    from orv_b200 import _lib as L
+    torch.manual_seed(2)
+    B, S, St, tpf, G, D, K = 2, 330, 26, 76, 5, 256, 192
+    M = B * S
+    a, w, b, x = _bf(M, K, k=0.5), _bf(D, K, k=0.1), _bf(D), _bf(M, D)
+    gate = torch.randn(B * G, 6 * D, device=DEV)
+    rm = ops.rowmap(S, St, tpf, G)
+    s = torch.arange(M, device=DEV) % S
+    grp = (torch.arange(M, device=DEV) // S) * G + torch.where(s < St, torch.zeros_like(s), 1 + (s - St) // tpf)
+    gvec = torch.where((s < St)[:, None], gate[grp][:, 5 * D:6 * D], gate[grp][:, 2 * D:3 * D]).double()
+    ref = x.double() + gvec * (a.double() @ w.double().T + b.double())
+    out = ops.gemm(a, w, b, epilogue=L.EPI_GATE_RESID, resid=x, gate=gate, gate_text_off=5 * D, gate_video_off=2 * D,
+                   rm=rm, out_f32=True)
+    _close(out, ref)
+
+
+def _rope64(x, cos, sin):
+    xr, xi = x.reshape(*x.shape[:-1], -1, 2).unbind(-1)
+    rot = torch.stack([-xi, xr], dim=-1).flatten(-2)
+    return x * cos + rot * sin
+
+
+@pytest.mark.parametrize("rope", [False, True])
+def test_gemm_qkv_norm_rope_f32(ops, rope):
+    from orv_b200 import _lib as L
+    torch.manual_seed(3)
+    S, St, D, K = 300, 20, 128, 128
+    a, w, b = _bf(S, K, k=0.5), _bf(3 * D, K, k=0.1), _bf(3 * D)
+    qn = ((1 + 0.1 * torch.randn(64, device=DEV)).bfloat16(), (0.1 * torch.randn(64, device=DEV)).bfloat16())
+    kn = ((1 + 0.1 * torch.randn(64, device=DEV)).bfloat16(), (0.1 * torch.randn(64, device=DEV)).bfloat16())
+    ang = torch.rand(S - St, 32, device=DEV) * 6.28
+    cos = torch.cos(ang).repeat_interleave(2, dim=1).contiguous()
+    sin = torch.sin(ang).repeat_interleave(2, dim=1).contiguous()
+    out = ops.gemm(a, w, b, epilogue=L.EPI_QKV, qk_dim=D, q_norm=qn, k_norm=kn, rm=ops.rowmap(S, St, 0, 1),
+                   rope=(cos, sin) if rope else None, out_f32=True)
+    lin = a.double() @ w.double().T + b.double()
+    q, k, v = lin.split(D, dim=1)
+
+    def hn(t, p):
+        t = torch.nn.functional.layer_norm(t.view(S, D // 64, 64), (64,), p[0].double(), p[1].double(), 1e-6)
+        if rope:
+            t = torch.cat([t[:St], _rope64(t[St:], cos.double()[:, None], sin.double()[:, None])], dim=0)
+        return t.reshape(S, D)
+
+    _close(out, torch.cat([hn(q, qn), hn(k, kn), v], 1))
+
+
+def test_gemm_gelu_f32(ops):
+    """GELU-tanh epilogue.  The kernel evaluates tanh with MUFU.TANH (`tanh.approx.f32`, max relative error 2^-11 on
+    tanh, PTX ISA): |err(gelu)| <= 0.5 |x| 2^-11, i.e. up to 5e-4 absolute for x in [-4, -1.3] where gelu itself is
+    small — the one place a shipped kernel deliberately leaves the 1e-4 absolute band.  Asserted: rtol 1e-3 with the
+    derived bound atol = 0.5 * max|x| * 2^-11 everywhere, and the north-star pair for x >= -1."""
+    from orv_b200 import _lib as L
+    torch.manual_seed(1)
+    a, w, b = _bf(1000, 256, k=0.5), _bf(512, 256, k=0.1), _bf(512)
+    out = ops.gemm(a, w, b, epilogue=L.EPI_GELU, out_f32=True)
+    x = a.double() @ w.double().T + b.double()
+    ref = torch.nn.functional.gelu(x, approximate="tanh")
+    _close(out, ref, rtol=RTOL, atol=0.5 * x.abs().max().item() * 2.0 ** -11)
+    sel = x >= -1.0
+    _close(out[sel], ref[sel])
+
+
+def _exact_softmax_case(B, S, H, seed, spread=6):
+    """Q, K with small integer entries (Q rows one-hot times 1 or 2, K entries in [-3, 3]) so every score q.k is an
+    integer in [-spread, spread]; with softmax scale = ln 2 the kernel's exp2(score - max) is an exact power of two,
+    exactly representable in the bf16 P operand: the only roundings left are fp32 accumulations."""
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    D = H * 64
+    q = torch.zeros(B * S, H, 64, device=DEV)
+    hot = torch.randint(0, 64, (B * S, H), device=DEV, generator=g)
+    amp = torch.randint(1, 3, (B * S, H), device=DEV, generator=g).float()
+    q.scatter_(2, hot[..., None], amp[..., None])
+    k = torch.randint(-(spread // 2), spread // 2 + 1, (B * S, H, 64), device=DEV, generator=g).float()
+    v = torch.randn(B * S, H, 64, device=DEV, generator=g)
+    qkv = torch.cat([q.reshape(B * S, D), k.reshape(B * S, D), v.reshape(B * S, D)], dim=1).bfloat16().contiguous()
+    return qkv
+
+
+def _attention_ref64(qkv, B, S, H, scale, q_row0=0, q_rows=0):
+    D = H * 64
+    q, k, v = (t.double().view(B, S, H, 64).transpose(1, 2) for t in qkv.split(D, dim=1))
+    if q_rows > 0:
+        q = q[:, :, q_row0:q_row0 + q_rows]
+    p = torch.softmax(q @ k.transpose(-1, -2) * scale, dim=-1)
+    return (p @ v).transpose(1, 2).reshape(-1, D)
+
+
+@pytest.mark.parametrize("B,S,H", [(1, 300, 2), (2, 1000, 3), (1, 3226, 4)])
+@pytest.mark.parametrize("threshold", [-1.0, 0.0])  # default lazy row max / forced O-accumulator rescale on every tile
+def test_attention_exact_probabilities_f32(ops, B, S, H, threshold):
+    from orv_b200 import _lib as L
+    lib = L.load()
+    qkv = _exact_softmax_case(B, S, H, seed=S)
+    scale = math.log(2.0)
+    lib.orvb_attention_set_rescale_threshold(threshold)
+    try:
+        out = ops.attention(qkv, B, S, H, scale, out_f32=True)
+        torch.cuda.synchronize()
+    finally:
+        lib.orvb_attention_set_rescale_threshold(-1.0)
+    _close(out, _attention_ref64(qkv, B, S, H, scale))
+
+
+def test_attention_query_window_exact_f32(ops):
+    """The MVBlock form: only rows [q_row0, q_row0 + q_rows) are queries, compact output (cogvideox_control.py:333)."""
+    B, S, H, q0, nq = 2, 700, 2, 60, 640
+    qkv = _exact_softmax_case(B, S, H, seed=7)
+    scale = math.log(2.0)
+    out = ops.attention(qkv, B, S, H, scale, q_row0=q0, q_rows=nq, out_f32=True)
+    _close(out, _attention_ref64(qkv, B, S, H, scale, q0, nq))
+
+
+def test_attention_random_f32_error_is_the_bf16_p_rounding(ops):
+    """Random Q/K (probabilities NOT exactly representable): the fp32 output differs from float64 only by the bf16
+    rounding of P in front of the PV tensor-core contraction (relative 2^-9 per probability, averaged over the keys) —
+    the same rounding torch's flash kernel applies.  Bound: 2e-3 of the output range, per element and per row."""
+    B, S, H = 1, 1500, 3
+    g = torch.Generator(device=DEV).manual_seed(5)
+    qkv = torch.randn(B * S, 3 * H * 64, device=DEV, generator=g).bfloat16()
+    out = ops.attention(qkv, B, S, H, 0.125, out_f32=True)
+    ref = _attention_ref64(qkv, B, S, H, 0.125)
+    err = (out.double() - ref).abs()
+    assert err.max().item() < 2e-3 * ref.abs().max().item()
+    row = err.norm(dim=1) / ref.norm(dim=1)
+    assert row.max().item() < 4e-3
+
+
+@pytest.mark.parametrize("use_ab", [False, True])
+def test_ln_modulate_f32(ops, use_ab):
+    torch.manual_seed(4)
+    B, S, St, tpf, G, D = 2, 330, 26, 76, 5, 256
+    M = B * S
+    x = _bf(M, D)
+    w, b = (1 + 0.1 * torch.randn(D, device=DEV)).bfloat16(), (0.1 * torch.randn(D, device=DEV)).bfloat16()
+    mod = torch.randn(B * G, 6 * D, device=DEV) * 0.3
+    rm = ops.rowmap(S, St, tpf, G)
+    s = torch.arange(M, device=DEV) % S
+    grp = (torch.arange(M, device=DEV) // S) * G + torch.where(s < St, torch.zeros_like(s), 1 + (s - St) // tpf)
+    is_text = (s < St)[:, None]
+    shift = torch.where(is_text, mod[grp][:, 3 * D:4 * D], mod[grp][:, 0:D]).double()
+    scale = torch.where(is_text, mod[grp][:, 4 * D:5 * D], mod[grp][:, D:2 * D]).double()
+    xhat = torch.nn.functional.layer_norm(x.double(), (D,), None, None, 1e-5)
+    if use_ab:
+        # folded tables as the forward builds them (bf16): A = w (1 + scale), B = b (1 + scale) + shift
+        sh, sc = mod.view(B * G, 2, 3, D)[:, :, 0], mod.view(B * G, 2, 3, D)[:, :, 1]  # [groups, video|text, D]
+        A = (w.float() * (1 + sc)).bfloat16()
+        Bt = (b.float() * (1 + sc) + sh).bfloat16()
+        ab = torch.stack([A[:, 1], Bt[:, 1], A[:, 0], Bt[:, 0]], dim=1).reshape(B * G, 4 * D).contiguous()
+        a_row = torch.where(is_text, ab[grp][:, 0:D], ab[grp][:, 2 * D:3 * D]).double()
+        b_row = torch.where(is_text, ab[grp][:, D:2 * D], ab[grp][:, 3 * D:4 * D]).double()
+        ref = xhat * a_row + b_row
+        out = ops.ln_modulate(x, None, None, 1e-5, rm=rm, ab=ab, out_f32=True)
+    else:
+        ref = (xhat * w.double() + b.double()) * (1 + scale) + shift
+        out = ops.ln_modulate(x, w, b, 1e-5, mod=mod, text_off=3 * D, video_off=0, rm=rm, out_f32=True)
+    _close(out, ref)

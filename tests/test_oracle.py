@@ -59,6 +59,26 @@ def test_sampler_matches_reference_pipeline_golden(kind, steps, guidance):
     torch.testing.assert_close(lat, blob["latents"], rtol=RTOL, atol=ATOL)
 
 
+@pytest.mark.parametrize("name", sorted(G.PIPELINE_CASES))
+def test_pipeline_controls_multiview_match_reference_golden(name):
+    """Control latents through the pipeline (moments -> sample with the global RNG -> scale -> channel dup,
+    cogvideox_control.py:1331-1364) and the 3-view path, against the reference pipeline's own output."""
+    opt = G.PIPELINE_CASES[name]
+    blob = load(name)
+    cfg = O.default_config(**dict(G.BASE, **opt["over"]))
+    sd = O.synthetic_state_dict(cfg, seed=0, std=0.05)
+    assert G.digest(sd) == blob["weights_sha256"]
+    inp, moments, cg = G.pipeline_case_inputs(cfg, opt["controls"], opt["views"])
+    assert torch.equal(moments, blob["moments"])
+    torch.manual_seed(G.CONTROL_SEED)
+    with torch.no_grad():
+        lat = O.pipeline_call(sd, cfg, opt["kind"], moments, inp["text"], 9, 48, 64, opt["steps"], 1.0,
+                              torch.Generator().manual_seed(42), actions=cg["actions"], num_views=opt["views"],
+                              control_moments={k: cg.get(k) for k in ("depths", "labels")})
+    assert lat.shape == blob["latents"].shape
+    torch.testing.assert_close(lat, blob["latents"], rtol=RTOL, atol=ATOL)
+
+
 def test_patchify_closed_form_matches_reshape_chain():
     """Integer index maps: bit-exact."""
     for (Fr, C, H, W, pt) in [(3, 4, 6, 8, None), (4, 4, 6, 8, 2), (5, 32, 40, 60, None)]:

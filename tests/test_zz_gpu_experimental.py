@@ -58,7 +58,7 @@ def test_forward_with_ff_chain_matches_default(monkeypatch):
         "from oracle import flat_oracle as O\n"
         "from orv_b200 import CogVideoXTransformer3DModelTraj\n"
         "cfg = O.default_config(num_attention_heads=4, attention_head_dim=64, num_layers=2, sample_width=24, "
-        "sample_height=16, sample_frames=9, text_embed_dim=128, max_text_seq_length=16)\n"
+        "sample_height=16, sample_frames=9, text_embed_dim=128, max_text_seq_length=16, modulate_encoder_hidden_states=True)\n"
         "sd = O.synthetic_state_dict(cfg, seed=0, std=0.05)\n"
         "inp = O.synthetic_inputs(cfg, 1, 3, 16, 24, seed=1, n_actions=8)\n"
         "m = CogVideoXTransformer3DModelTraj(**cfg); m.load_state_dict(sd, strict=False); m.action_embed.mask = False\n"
