@@ -120,14 +120,6 @@ int orvb_gemm_tile_width(int32_t m, int32_t n, int32_t epilogue);
  * (a multiple of 16 in 32..256) = CTA-pair kernel.  Used by the bit-identity test of the two kernels and by the tile
  * sweeps under tools/. */
 int orvb_gemm_bf16_bn(const orvb_gemm_args* args, int bn, void* stream);
-/* EXPERIMENTAL, opt-in (not on any default path; unverified on hardware at the time of writing): `first` (ORVB_EPI_GELU)
- * and `second` (ORVB_EPI_GATE_RESID, whose A operand is the first problem's output) — the FF1 / FF2 pair of a block,
- * reference a9 — as ONE persistent CTA-pair launch with per-row-stripe dependency counters, which removes a kernel
- * boundary and FF1's partial last wave.  `counters`: device scratch of at least ceil(m / 256) uint32 (zeroed by the
- * call).  orvb_forward takes this path only when the environment has ORVB_FF_CHAIN=1. */
-int orvb_gemm_chain(const orvb_gemm_args* first, const orvb_gemm_args* second, void* counters, size_t counters_bytes,
-                    void* stream);
-
 /* Non-causal multi-head attention over a packed QKV buffer (reference a8: F.scaled_dot_product_attention).
  * qkv: bf16 [batch * seq_len, 3 * heads * 64] with Q | K | V column blocks; out: bf16 [batch * seq_len, heads*64].
  * softmax scale = scale (1/sqrt(64) in the reference).  head_dim is fixed at 64 (every shipped config). */
@@ -337,6 +329,10 @@ int orvb_modulation_select(const orvb_model* m, const orvb_shape* shape, int32_t
 /* Number of kernel launches orvb_forward enqueued in its most recent call on this model (for bench.py's
  * `gpu_launches`). */
 int orvb_last_launch_count(const orvb_model* m);
+/* ORVB_PC_* class (below) of every kernel that call launched, in launch order: writes min(count, capacity) entries and
+ * returns the count.  bench.py joins this list with the device-side activity records (CUPTI, through torch.profiler)
+ * of the graph-replayed forwards to attribute device time per kernel class. */
+int orvb_last_launch_classes(const orvb_model* m, int32_t* classes_out, int32_t capacity);
 
 /* Optional per-kernel-class timing of orvb_forward (CUDA events recorded on the launch stream around every
  * launch; the forward then synchronises at its end, so enable it for measurement only).  orvb_model_set_profile

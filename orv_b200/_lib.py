@@ -148,11 +148,11 @@ class VoxelizeArgs(C.Structure):
 # Every symbol include/orv_b200.h declares; tests check the .so exports all of them.
 EXPORTED_SYMBOLS = [
     "orvb_version", "orvb_last_error", "orvb_check_device",
-    "orvb_gemm_bf16", "orvb_gemm_bf16_bn", "orvb_gemm_chain", "orvb_gemm_tile_width", "orvb_attention_bf16", "orvb_attention", "orvb_attention_set_rescale_threshold",
+    "orvb_gemm_bf16", "orvb_gemm_bf16_bn", "orvb_gemm_tile_width", "orvb_attention_bf16", "orvb_attention", "orvb_attention_set_rescale_threshold",
     "orvb_attention_set_debug", "orvb_ln_modulate", "orvb_skinny_linear",
     "orvb_patchify", "orvb_unpatchify",
     "orvb_model_create", "orvb_model_destroy", "orvb_model_bind_weights", "orvb_workspace_bytes",
-    "orvb_forward", "orvb_last_launch_count", "orvb_model_set_profile", "orvb_model_get_profile",
+    "orvb_forward", "orvb_last_launch_count", "orvb_last_launch_classes", "orvb_model_set_profile", "orvb_model_get_profile",
     "orvb_modulation_bytes", "orvb_modulation_schedule", "orvb_modulation_select",
     "orvb_sampler_step",
     "orvb_dynamic_voxelize", "orvb_voxelize_workspace_bytes", "orvb_hard_voxelize",
@@ -183,9 +183,6 @@ def load() -> C.CDLL:
     if hasattr(lib, "orvb_gemm_bf16_bn"):
         lib.orvb_gemm_bf16_bn.argtypes = [C.POINTER(GemmArgs), c_int, c_void_p]
         lib.orvb_gemm_bf16_bn.restype = c_int
-    if hasattr(lib, "orvb_gemm_chain"):
-        lib.orvb_gemm_chain.argtypes = [C.POINTER(GemmArgs), C.POINTER(GemmArgs), c_void_p, C.c_size_t, c_void_p]
-        lib.orvb_gemm_chain.restype = c_int
     if hasattr(lib, "orvb_attention_set_rescale_threshold"):
         lib.orvb_attention_set_rescale_threshold.argtypes = [c_float]
         lib.orvb_attention_set_rescale_threshold.restype = None
@@ -221,6 +218,8 @@ def load() -> C.CDLL:
         lib.orvb_forward.restype = c_int
         lib.orvb_last_launch_count.argtypes = [c_void_p]
         lib.orvb_last_launch_count.restype = c_int
+        lib.orvb_last_launch_classes.argtypes = [c_void_p, C.POINTER(c_int), c_int]
+        lib.orvb_last_launch_classes.restype = c_int
         lib.orvb_model_set_profile.argtypes = [c_void_p, c_int]
         lib.orvb_model_set_profile.restype = c_int
         lib.orvb_model_get_profile.argtypes = [c_void_p, C.POINTER(c_float), C.POINTER(c_int)]

@@ -22,8 +22,6 @@
 
 namespace orvb {
 int gemm_run(const orvb_gemm_args* a, cudaStream_t stream);
-int gemm_chain_run(const orvb_gemm_args* first, const orvb_gemm_args* second, uint32_t* counters, size_t counters_bytes,
-                   cudaStream_t stream);
 }
 
 struct orvb_model {
@@ -40,6 +38,7 @@ struct orvb_model {
   orvb_block_weights* blocks_dev = nullptr;     // [layers]
   orvb_block_weights* mv_blocks_dev = nullptr;  // [layers] or null
   int launches = 0;
+  std::vector<int> launch_cls;  // profile class of every kernel launch of the most recent call, in launch order
   // optional per-kernel-class timing (orvb_model_set_profile): CUDA events around every launch
   bool profile = false;
   int cur_cls = 0;
@@ -90,8 +89,6 @@ struct Workspace {
   SkinnyJob* jobs;   // [3 * layers] device table of the batched AdaLN linears (points into `mod`)
   AbSite* ab_sites;  // [3 * layers + 1] device table of the A/B folds (points into `mod` / `ab`)
   bf16 *text_cache, *ctrl_cache;  // step-invariant rows kept by ORVB_STATIC_SAVE (text projection, control embeddings)
-  uint32_t* chain_done;  // stripe counters of the FF1 -> FF2 chain
-  size_t chain_done_bytes;
   size_t bytes;
 };
 
@@ -150,8 +147,6 @@ static void carve(const orvb_config& c, const Geometry& g, uint8_t* base, Worksp
     ws->tmp_mv = reinterpret_cast<bf16*>(take(mv * (g.B / g.V) * g.Fp * g.V * tok * D * 2));
   }
   carve_modulation(c, g, take, ws);
-  ws->chain_done_bytes = (R / 256 + 2) * 4;
-  ws->chain_done = reinterpret_cast<uint32_t*>(take(ws->chain_done_bytes));
   ws->text_cache = reinterpret_cast<bf16*>(take(static_cast<size_t>(g.B) * g.St * D * 2));
   ws->ctrl_cache = reinterpret_cast<bf16*>(take(static_cast<size_t>(g.B) * g.Sv * D * keys * 2));
   ws->bytes = off;
@@ -231,6 +226,10 @@ __global__ void add_hidden_kernel(bf16* __restrict__ ctrl, const bf16* __restric
   *reinterpret_cast<uint4*>(ctrl + static_cast<size_t>(r) * ld_ctrl + col_off + c * 8) = a;
 }
 
+static inline void note_launch(orvb_model* m) {
+  ++m->launches;
+  m->launch_cls.push_back(m->cur_cls);
+}
 static void prof_begin(orvb_model* m, cudaStream_t st) {
   if (!m->profile) return;
   if (m->ev_used + 2 > m->ev.size()) {
@@ -253,19 +252,9 @@ static void prof_end(orvb_model* m, cudaStream_t st) {
     int _rc = (expr);               \
     if (_rc != ORVB_OK) return _rc; \
     prof_end(m, st);                \
-    ++m->launches;                  \
+    note_launch(m);                 \
   } while (0)
 #define ORVB_CLS(c) (m->cur_cls = (c))
-
-// ORVB_FF_CHAIN=1 routes FF1 + FF2 through the experimental chained launch (default: off).
-static bool ff_chain_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("ORVB_FF_CHAIN");
-    v = (e != nullptr && atoi(e) != 0) ? 1 : 0;
-  }
-  return v != 0;
-}
 
 static orvb_gemm_args gemm_base(const void* a, const void* w, const void* bias, void* out, int M, int N, int K,
                                 int lda, int ldo, int epi) {
@@ -329,7 +318,7 @@ static int build_modulation(orvb_model* m, const Geometry& g, const ModIn& in, c
     timestep_sinusoid_kernel<<<(n + 255) / 256, 256, 0, st>>>(a->timesteps, ws.tsin, g.B, D, c.flip_sin_to_cos,
                                                               c.freq_shift, 0.f, 0);
     ORVB_CHECK_CUDA(cudaGetLastError());
-    ++m->launches;
+    note_launch(m);
     ORVB_TRY(skinny_linear_launch(ws.tsin, SkinnyJob{static_cast<const bf16*>(w.time1_w), static_cast<const bf16*>(w.time1_b), ws.t1},
                                   nullptr, 1, g.B, T, D, 1, st));
     ORVB_TRY(skinny_linear_launch(ws.t1, SkinnyJob{static_cast<const bf16*>(w.time2_w), static_cast<const bf16*>(w.time2_b), ws.temb},
@@ -342,7 +331,7 @@ static int build_modulation(orvb_model* m, const Geometry& g, const ModIn& in, c
     timestep_sinusoid_kernel<<<(od / 2 + 255) / 256, 256, 0, st>>>(nullptr, ws.osin, 1, od, c.flip_sin_to_cos,
                                                                     c.freq_shift, a->ofs, 1);
     ORVB_CHECK_CUDA(cudaGetLastError());
-    ++m->launches;
+    note_launch(m);
     ORVB_TRY(skinny_linear_launch(ws.osin, SkinnyJob{static_cast<const bf16*>(w.ofs1_w), static_cast<const bf16*>(w.ofs1_b), ws.o1},
                                   nullptr, 1, 1, T, od, 1, st));
     ORVB_TRY(skinny_linear_launch(ws.o1, SkinnyJob{static_cast<const bf16*>(w.ofs2_w), static_cast<const bf16*>(w.ofs2_b), ws.oemb},
@@ -359,7 +348,7 @@ static int build_modulation(orvb_model* m, const Geometry& g, const ModIn& in, c
     actions_to_f32_kernel<<<(rows * kpad + 255) / 256, 256, 0, st>>>(static_cast<const bf16*>(a->actions), ws.act_in,
                                                                      rows, act_k, kpad);
     ORVB_CHECK_CUDA(cudaGetLastError());
-    ++m->launches;
+    note_launch(m);
     ORVB_TRY(skinny_linear_launch(ws.act_in, SkinnyJob{static_cast<const bf16*>(w.act1_w), static_cast<const bf16*>(w.act1_b), ws.act_h},
                                   nullptr, 1, rows, c.action_hidden, kpad, 2, st));
     ORVB_TRY(skinny_linear_launch(ws.act_h, SkinnyJob{static_cast<const bf16*>(w.act2_w), static_cast<const bf16*>(w.act2_b), ws.act_emb},
@@ -370,7 +359,7 @@ static int build_modulation(orvb_model* m, const Geometry& g, const ModIn& in, c
     build_emb_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws.temb, oemb, ws.act_emb, a->action_mask,
                                                       static_cast<const bf16*>(w.act_mask_embed), ws.emb, g.B, g.G, T);
     ORVB_CHECK_CUDA(cudaGetLastError());
-    ++m->launches;
+    note_launch(m);
   }
 
   // ---- 2. all AdaLN tables of the forward in one batched launch (they depend only on emb) ----------
@@ -383,7 +372,7 @@ static int build_modulation(orvb_model* m, const Geometry& g, const ModIn& in, c
         static_cast<const bf16*>(w.norm_out_ln_b), ws.mod, ws.ab, ws.jobs, ws.ab_sites, c.layers, site_stride, ab_stride,
         mw * D, c.modulate_text ? 3 * D : 0, D);  // no text variant without text modulation: it aliases the video one
     ORVB_CHECK_CUDA(cudaGetLastError());
-    ++m->launches;
+    note_launch(m);
   }
   ORVB_TRY(skinny_linear_launch(ws.emb, SkinnyJob{nullptr, nullptr, nullptr}, ws.jobs,
                                 2 * c.layers + (c.multiview ? c.layers : 0), g.B * g.G, mw * D, T, 0, st));
@@ -421,6 +410,7 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
   const int D = g.D, T = g.T;
   const int pt = c.patch_size_t > 0 ? c.patch_size_t : 1;
   m->launches = 0;
+  m->launch_cls.clear();
   m->ev_used = 0;
   m->ev_cls.clear();
   ORVB_CLS(ORVB_PC_PROLOGUE);
@@ -505,7 +495,7 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
       add_hidden_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(ws.ctrl, ws.x, g.B * g.Sv, D, ldc,
                                                                                 slot * D, g.Sv, g.S, g.St);
       ORVB_CHECK_CUDA(cudaGetLastError());
-      ++m->launches;
+      note_launch(m);
     }
     orvb_gemm_args ga = gemm_base(ws.ctrl, w.combine_w, w.combine_b, ws.x, g.B * g.Sv, D, ldc, ldc, D,
                                   ORVB_EPI_GATE_RESID);
@@ -586,16 +576,10 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
     orvb_gemm_args f2 = gemm_base(ws.ffh, bw.ff2_w, bw.ff2_b, ws.x, g.R, D, g.FF, g.FF, D, ORVB_EPI_GATE_RESID);
     f2.resid = ws.x; f2.ldr = D; f2.gate = mod2; f2.gate_ld = mwid * D; f2.gate_text_off = gate_text_off; f2.gate_video_off = 2 * D;
     f2.rowmap = rm;
-    if (ff_chain_enabled() && g.R > 128) {
-      // experimental, opt-in: both GEMMs in one persistent launch (gemm.cu, gemm2_chain_kernel)
-      ORVB_CLS(ORVB_PC_FF1);
-      ORVB_TRY(gemm_chain_run(&f1, &f2, ws.chain_done, ws.chain_done_bytes, st));
-    } else {
-      ORVB_CLS(ORVB_PC_FF1);
-      ORVB_TRY(gemm_run(&f1, st));
-      ORVB_CLS(ORVB_PC_FF2);
-      ORVB_TRY(gemm_run(&f2, st));
-    }
+    ORVB_CLS(ORVB_PC_FF1);
+    ORVB_TRY(gemm_run(&f1, st));
+    ORVB_CLS(ORVB_PC_FF2);
+    ORVB_TRY(gemm_run(&f2, st));
 
     if (a->tap_hidden != nullptr && a->tap_layer == l) {
       ORVB_CHECK_CUDA(cudaMemcpyAsync(a->tap_hidden, ws.x, static_cast<size_t>(g.R) * D * 2, cudaMemcpyDeviceToDevice, st));
@@ -756,6 +740,7 @@ extern "C" int orvb_modulation_schedule(orvb_model* m, const orvb_shape* s, int3
   ORVB_REQUIRE(tables_bytes >= ws.bytes, ORVB_ENOMEM, "orvb_modulation_schedule: buffer too small (%zu < %zu)", tables_bytes, ws.bytes);
   ORVB_REQUIRE((gv.Fa > 0) == (actions != nullptr), ORVB_EINVAL, "orvb_modulation_schedule: shape.action_frames and the actions pointer disagree");
   m->launches = 0;
+  m->launch_cls.clear();
   m->ev_used = 0;
   m->ev_cls.clear();
   ModIn in;
@@ -798,6 +783,13 @@ extern "C" int orvb_forward(orvb_model* m, const orvb_forward_args* a, void* str
 }
 
 extern "C" int orvb_last_launch_count(const orvb_model* m) { return m ? m->launches : 0; }
+
+extern "C" int orvb_last_launch_classes(const orvb_model* m, int32_t* classes_out, int32_t capacity) {
+  if (m == nullptr) return 0;
+  const int n = static_cast<int>(m->launch_cls.size());
+  for (int i = 0; i < n && i < capacity && classes_out != nullptr; ++i) classes_out[i] = m->launch_cls[i];
+  return n;
+}
 
 extern "C" int orvb_model_set_profile(orvb_model* m, int enable) {
   using namespace orvb;

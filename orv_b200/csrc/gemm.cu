@@ -649,277 +649,6 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
 
 
 // ---------------------------------------------------------------------------------------------------
-// EXPERIMENTAL, OPT-IN (ORVB_FF_CHAIN=1 / orvb_gemm_chain; no default path launches it, and it has not run on a GPU
-// yet): two dependent GEMMs — FF1 (+GELU) and FF2 (+gate, residual) of one transformer block — as ONE persistent
-// CTA-pair launch.  Why: every GEMM launch carries ~20 us in which the tensor pipe is idle (prologue, grid-wide wait
-// for the previous kernel's slowest CTA, cold pipeline fill, exposed last epilogue, teardown; DESIGN.md lead 2), and
-// FF1's last wave is 62 % full.  Here the tile list spans both problems, in row-stripe-major order: tiles
-// [0, tiles0) are FF1, [tiles0, tiles0 + tiles1) FF2.  An FF2 tile of row stripe m reads rows [256 m, 256 m + 256) of
-// the FF1 OUTPUT, so its TMA warp first polls done[m] (acquire) until every FF1 tile of that stripe has been stored:
-// each of the 16 epilogue warps of a cluster adds 1 (release) after its TMA stores of the tile have completed
-// (cp.async.bulk.wait_group 0) — target = 16 * (FF1 tiles per stripe).  Tiles are handed out round-robin in index
-// order to clusters that are all resident (grid <= SM count, one CTA per SM) and every dependency points at a smaller
-// tile index, processed by warps that never wait on a counter, so the schedule cannot dead-lock; the poll is bounded
-// (trap) like every other wait in this library.
-// ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* ptr) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
-  return v;
-}
-__device__ __forceinline__ void red_release_gpu_add_u32(uint32_t* ptr, uint32_t v) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-
-template <int EPI0, int EPI1>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2_threads(EPI0), 1)
-gemm2_chain_kernel(const __grid_constant__ CUtensorMap tma_a0, const __grid_constant__ CUtensorMap tma_b0,
-                   const __grid_constant__ CUtensorMap tma_o0, const __grid_constant__ CUtensorMap tma_a1,
-                   const __grid_constant__ CUtensorMap tma_b1, const __grid_constant__ CUtensorMap tma_o1,
-                   const GemmDev p0, const GemmDev p1, const int bn0, const int bn1, uint32_t* done,
-                   const uint32_t target) {
-  static_assert(g2_epi_warps(EPI0) == 8 && g2_epi_warps(EPI1) == 8, "the chain kernel assumes eight epilogue warps");
-  constexpr int STAGES = G2_STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* out_stage = smem + STAGES * G2_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + G2_OUT_STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int cluster_id = blockIdx.x >> 1;
-  const int num_clusters = gridDim.x >> 1;
-  const int tiles0 = p0.num_m_tiles * p0.num_n_tiles;
-  const int num_tiles = tiles0 + p1.num_m_tiles * p1.num_n_tiles;
-  const int num_k0 = (p0.K + BK - 1) / BK;
-  const int num_k1 = (p1.K + BK - 1) / BK;
-
-  // tile -> (problem, 256-row stripe, column tile), stripe-major inside each problem
-  auto decode = [&](int tile, int& prob, int& m_blk, int& n_blk) {
-    if (tile < tiles0) {
-      prob = 0;
-      m_blk = tile / p0.num_n_tiles;
-      n_blk = tile - m_blk * p0.num_n_tiles;
-    } else {
-      const int t = tile - tiles0;
-      prob = 1;
-      m_blk = t / p1.num_n_tiles;
-      n_blk = t - m_blk * p1.num_n_tiles;
-    }
-  };
-
-  pdl_launch_dependents();
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tma_a0);
-    tma_prefetch_desc(&tma_b0);
-    tma_prefetch_desc(&tma_a1);
-    tma_prefetch_desc(&tma_b1);
-    if (p0.tma_store) tma_prefetch_desc(&tma_o0);
-    if (p1.tma_store) tma_prefetch_desc(&tma_o1);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 2 * 8);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 2) {
-    tmem_alloc_pair(tmem_slot, 512);
-    tmem_relinquish_pair();
-  }
-  tc_fence_before();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();
-
-  if (warp == 0) {
-    // ================================ TMA producer (both CTAs) ================================
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      int prob, m_blk, n_blk;
-      decode(tile, prob, m_blk, n_blk);
-      const int bn = prob ? bn1 : bn0;
-      const int half_bn = bn >> 1;
-      const int num_k = prob ? num_k1 : num_k0;
-      const CUtensorMap* ta = prob ? &tma_a1 : &tma_a0;
-      const CUtensorMap* tb = prob ? &tma_b1 : &tma_b0;
-      const uint32_t stage_tx = 2u * static_cast<uint32_t>(G2_A_BYTES + half_bn * BK * 2);
-      if (prob == 1) {
-        // rows [256 m_blk, +256) of the first problem's output must be complete in global memory
-        if (lane == 0) {
-          const long long t0 = clock64();
-          while (ld_acquire_gpu_u32(done + m_blk) < target) {
-            __nanosleep(64);
-            if (clock64() - t0 > 8000000000LL) __trap();  // a protocol bug must not hang the GPU
-          }
-        }
-        __syncwarp();
-        fence_proxy_async_all();  // the TMA loads below (async proxy) observe what the acquire made visible
-      }
-      const int a_row = m_blk * 256 + static_cast<int>(rank) * BM;
-      const int b_row = n_blk * bn + static_cast<int>(rank) * half_bn;
-      for (int kb = 0; kb < num_k; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * G2_STAGE_BYTES;
-        uint8_t* sb = sa + G2_A_BYTES;
-        const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
-        if (elect_one()) {
-          if (rank == 0) mbar_expect_tx(&full_bar[stage], stage_tx);
-          tma_load_2d_pair(sa, ta, leader_full, kb * BK, a_row);
-          tma_load_2d_pair(sb, tb, leader_full, kb * BK, b_row);
-        }
-        __syncwarp();
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-    }
-  } else if (warp == 1 && rank == 0) {
-    // ================================ MMA issuer (leader CTA) ================================
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int prob = tile < tiles0 ? 0 : 1;
-      const int num_k = prob ? num_k1 : num_k0;
-      const uint32_t idesc = umma_idesc_bf16(256, prob ? bn1 : bn0, 0, 0);
-      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * G2_ACC_COLS);
-      for (int kb = 0; kb < num_k; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * G2_STAGE_BYTES);
-        const uint64_t a_desc = umma_desc_sw128(sa);
-        const uint64_t b_desc = umma_desc_sw128(sa + G2_A_BYTES);
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            umma_f16_ss_pair(d_tmem, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc,
-                             static_cast<uint32_t>((kb | k) != 0));
-          }
-          tc_commit_pair(&empty_bar[stage], 3);
-          if (kb == num_k - 1) tc_commit_pair(&tfull_bar[acc], 3);
-        }
-        __syncwarp();
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
-      }
-    }
-  } else if (warp >= 4) {
-    // ================================ epilogue (both CTAs) ====================================
-    constexpr int NBUF = 1;                  // eight warps share the 32 KB of staging: one [32 x 64] tile each
-    const int ew = (warp - 4) & 3;
-    const int unit_par = (warp - 4) >> 2;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    uint32_t stores = 0;
-    uint8_t* my_stage = out_stage + (warp - 4) * (NBUF * 32 * 128);
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      int prob, m_blk, n_blk;
-      decode(tile, prob, m_blk, n_blk);
-      const int bn = prob ? bn1 : bn0;
-      const int pM = prob ? p1.M : p0.M;
-      const int pN = prob ? p1.N : p0.N;
-      const bool p_tma = (prob ? p1.tma_store : p0.tma_store) != 0;
-      const CUtensorMap* to = prob ? &tma_o1 : &tma_o0;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const int row0 = m_blk * 256 + static_cast<int>(rank) * BM + ew * 32;
-      const int row = row0 + lane;
-      const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * G2_ACC_COLS) + (static_cast<uint32_t>(ew * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < bn; c += 64) {
-        const int n0 = n_blk * bn + c;
-        if (n0 >= pN || row0 >= pM) break;  // warp-uniform
-        if (((c >> 6) & 1) != unit_par) continue;
-        uint32_t r0[32], r1[32];
-        tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c), r0);
-        tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c + 32), r1);
-        tmem_ld_wait();
-        const bool staged = p_tma && (bn - c >= 64);
-        uint8_t* sbuf = my_stage + (stores % NBUF) * (32 * 128);
-        if (staged && stores >= NBUF) {
-          if (lane == 0) bulk_wait_group_read<NBUF - 1>();
-          __syncwarp();
-        }
-        if (row < pM) {
-          float v[64];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            v[j] = __uint_as_float(r0[j]);
-            v[32 + j] = __uint_as_float(r1[j]);
-          }
-          int ncols = bn - c;
-          if (ncols > 64) ncols = 64;
-          if (pN - n0 < ncols) ncols = pN - n0;
-          if (prob == 0)
-            epilogue_unit<EPI0>(p0, v, row, n0, ncols, staged ? sbuf + lane * 128 : nullptr, lane & 7);
-          else
-            epilogue_unit<EPI1>(p1, v, row, n0, ncols, staged ? sbuf + lane * 128 : nullptr, lane & 7);
-        }
-        if (staged) {
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(to, sbuf, n0, row0);
-            bulk_commit_group();
-          }
-          ++stores;
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
-      if (prob == 0) {
-        // publish this warp's share of the first problem's tile: direct stores of every lane, then the TMA stores
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) {
-          bulk_wait_group<0>();      // my TMA stores of this tile have been written
-          fence_proxy_async_all();
-          red_release_gpu_add_u32(done + m_blk, 1u);
-        }
-        __syncwarp();
-      }
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
-      }
-    }
-  }
-
-  if (warp >= 4 && lane == 0) bulk_wait_group<0>();
-  tc_fence_before();
-  cluster_sync_all();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc_pair(tmem_base, 512);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
 template <int BN, int EPI>
@@ -1120,67 +849,6 @@ int gemm_run(const orvb_gemm_args* a, cudaStream_t stream) {
 }
 
 
-// EXPERIMENTAL (see gemm2_chain_kernel): `first` (GELU epilogue) and `second` (gate + residual epilogue, reading the
-// first's output as its A operand) in one persistent launch.  `counters`: >= ceil(m / 256) uint32, zeroed here.
-int gemm_chain_run(const orvb_gemm_args* first, const orvb_gemm_args* second, uint32_t* counters, size_t counters_bytes,
-                   cudaStream_t stream) {
-  ORVB_REQUIRE(first && second && counters, ORVB_EINVAL, "gemm chain: null pointer");
-  ORVB_REQUIRE(first->epilogue == ORVB_EPI_GELU && second->epilogue == ORVB_EPI_GATE_RESID, ORVB_EINVAL,
-               "gemm chain: only FF1 (GELU) -> FF2 (gate + residual) is instantiated");
-  ORVB_REQUIRE(first->m == second->m && first->m > BM, ORVB_ESHAPE, "gemm chain: both problems need the same m > 128");
-  ORVB_REQUIRE(second->a == first->out && second->lda == first->ldo && second->k == first->n, ORVB_ESHAPE,
-               "gemm chain: the second problem's A operand must be the first problem's output");
-  ORVB_REQUIRE(first->src_rows == 0 && first->mv_tokens == 0, ORVB_ESHAPE,
-               "gemm chain: the first problem must write its rows in place (stripe dependencies)");
-  CUtensorMap ta0, tb0, to0, ta1, tb1, to1;
-  GemmDev p0, p1;
-  int bn0, bn1;
-  int rc = gemm_prepare(first, 0, &ta0, &tb0, &to0, &p0, &bn0);
-  if (rc != ORVB_OK) return rc;
-  rc = gemm_prepare(second, 0, &ta1, &tb1, &to1, &p1, &bn1);
-  if (rc != ORVB_OK) return rc;
-  ORVB_REQUIRE(bn0 < 0 && bn1 < 0 && p0.num_m_tiles == p1.num_m_tiles, ORVB_ESHAPE, "gemm chain: CTA-pair tiles expected");
-  ORVB_REQUIRE(counters_bytes >= static_cast<size_t>(p0.num_m_tiles) * 4, ORVB_ENOMEM,
-               "gemm chain: %zu bytes of counters < %d stripes", counters_bytes, p0.num_m_tiles);
-  ORVB_CHECK_CUDA(cudaMemsetAsync(counters, 0, static_cast<size_t>(p0.num_m_tiles) * 4, stream));
-  static bool attr_set = false;
-  auto kern = gemm2_chain_kernel<ORVB_EPI_GELU, ORVB_EPI_GATE_RESID>;
-  if (!attr_set) {
-    ORVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
-    attr_set = true;
-  }
-  const int tiles = p0.num_m_tiles * p0.num_n_tiles + p1.num_m_tiles * p1.num_n_tiles;
-  // Every cluster must be co-resident: the stripe dependencies are waited on inside the kernel.  Ask the driver how
-  // many clusters of this kernel (2 CTAs, 227 KB of shared memory each) the device can hold at once instead of
-  // assuming one per SM pair (MPS partitions, GPCs with an odd number of usable SMs).
-  static int max_clusters = -1;
-  if (max_clusters < 0) {
-    cudaLaunchConfig_t qc = {};
-    qc.gridDim = dim3(sm_count() / 2 * 2);
-    qc.blockDim = dim3(g2_threads(ORVB_EPI_GELU));
-    qc.dynamicSmemBytes = G2_SMEM_BYTES;
-    cudaLaunchAttribute qa[1];
-    qa[0].id = cudaLaunchAttributeClusterDimension;
-    qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
-    qc.attrs = qa;
-    qc.numAttrs = 1;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, kern, &qc) != cudaSuccess) { n = 0; (void)cudaGetLastError(); }
-    max_clusters = n;
-  }
-  if (max_clusters < 2) {  // cannot guarantee co-residency: the two-launch path is always correct
-    int rc2 = gemm_launch_prepared(ta0, tb0, to0, p0, bn0, first->epilogue, stream);
-    if (rc2 != ORVB_OK) return rc2;
-    return gemm_launch_prepared(ta1, tb1, to1, p1, bn1, second->epilogue, stream);
-  }
-  int clusters = sm_count() / 2;
-  if (clusters > max_clusters) clusters = max_clusters;
-  const int grid = 2 * (tiles < clusters ? tiles : clusters);
-  const uint32_t target = 16u * static_cast<uint32_t>(p0.num_n_tiles);  // 8 epilogue warps x 2 CTAs per tile
-  ORVB_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(g2_threads(ORVB_EPI_GELU)), G2_SMEM_BYTES, stream, true, ta0, tb0, to0,
-                                ta1, tb1, to1, p0, p1, -bn0, -bn1, counters, target));
-  return ORVB_OK;
-}
 }  // namespace orvb
 
 extern "C" int orvb_gemm_bf16(const orvb_gemm_args* args, void* stream) {
@@ -1207,15 +875,6 @@ extern "C" int orvb_gemm_bf16_bn(const orvb_gemm_args* args, int bn, void* strea
   rc = gemm_prepare(args, bn, &ta, &tb, &to, &p, &bn_used);
   if (rc != ORVB_OK) return rc;
   return gemm_launch_prepared(ta, tb, to, p, bn_used, args->epilogue, static_cast<cudaStream_t>(stream));
-}
-
-// EXPERIMENTAL, opt-in: FF1 (+GELU) -> FF2 (+gate, residual) as one persistent launch (see gemm2_chain_kernel).
-extern "C" int orvb_gemm_chain(const orvb_gemm_args* first, const orvb_gemm_args* second, void* counters,
-                               size_t counters_bytes, void* stream) {
-  using namespace orvb;
-  int rc = check_arch();
-  if (rc != ORVB_OK) return rc;
-  return gemm_chain_run(first, second, static_cast<uint32_t*>(counters), counters_bytes, static_cast<cudaStream_t>(stream));
 }
 
 #ifdef ORVB_GEMM_TIMELINE

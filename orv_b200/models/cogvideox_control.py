@@ -221,6 +221,7 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
         self._pos_cache: Dict[Tuple, torch.Tensor] = {}
         self._bound_pos_key = None
         self.last_launch_count = 0
+        self.last_launch_classes = []  # ORVB_PC_* class of every kernel of the most recent forward, in launch order
 
     # -------------------------------------------------------------------------------------------------------
     # reference helpers
@@ -662,7 +663,15 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
         Bc = hidden_states.shape[0]
         if V > 1:  # 'b (v f) c h w -> (b v) f c h w' (a view: (v f) is contiguous) and text repeated per view (:756-759)
             hidden_states = hidden_states.reshape(Bc * V, hidden_states.shape[1] // V, *hidden_states.shape[2:])
-            encoder_hidden_states = encoder_hidden_states.repeat_interleave(V, dim=0)
+            # the repeated text keeps ONE address while the caller's tensor is unchanged (same storage, same version
+            # counter): a fresh copy per call would defeat the (shape, address)-keyed CUDA-graph replay
+            tkey = (encoder_hidden_states.data_ptr(), encoder_hidden_states._version, tuple(encoder_hidden_states.shape),
+                    encoder_hidden_states.dtype, V)
+            cached = self.__dict__.get("_text_rep")
+            if cached is None or cached[0] != tkey:
+                cached = (tkey, encoder_hidden_states.repeat_interleave(V, dim=0).to(torch.bfloat16).contiguous())
+                self.__dict__["_text_rep"] = cached
+            encoder_hidden_states = cached[1]
         B, Fr, Cin, H, W = hidden_states.shape
         if Cin != c.in_channels:
             raise RuntimeError(f"expected {c.in_channels} input channels, got {hidden_states.shape=}")
@@ -810,6 +819,11 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
         def launch():
             L.check(lib.orvb_forward(self._handle, C.byref(a), L.current_stream()), "orvb_forward")
 
+        def launch_classes():
+            buf = (C.c_int32 * 4096)()
+            n = lib.orvb_last_launch_classes(self._handle, buf, 4096)
+            return list(buf[:min(n, 4096)])
+
         gkey = (wkey, hs.data_ptr(), L.ptr(text), L.ptr(depths), L.ptr(labels), L.ptr(rope_cos), L.ptr(rope_sin),
                 ofs_val, mask_u8 is not None, sched is not None, int(_static_mode))
         if self.use_cuda_graph and _tap is None and not self._profiling:
@@ -822,19 +836,22 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
                 self._graphs[gkey] = False
                 launch()
                 self.last_launch_count = lib.orvb_last_launch_count(self._handle)
+                self.last_launch_classes = launch_classes()
             else:
                 if ent is False:
                     graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(graph):
                         launch()
                     ent = SimpleNamespace(graph=graph, keep=(hs, text, depths, labels, rope_cos, rope_sin, ws, sm),
-                                          launches=lib.orvb_last_launch_count(self._handle))
+                                          launches=lib.orvb_last_launch_count(self._handle), classes=launch_classes())
                     self._graphs[gkey] = ent
                 ent.graph.replay()
                 self.last_launch_count = ent.launches
+                self.last_launch_classes = ent.classes
         else:
             launch()
             self.last_launch_count = lib.orvb_last_launch_count(self._handle)
+            self.last_launch_classes = launch_classes()
         if not _static_out:
             out = out.clone()
         if V > 1:  # '(b v) f c h w -> b (v f) c h w' (:942)

@@ -234,8 +234,12 @@ class CogVideoXImageToVideoPipelineTraj:
         latent_padding = torch.zeros(padding_shape, device=device, dtype=dtype)
         image_latents = torch.cat([image_latents, latent_padding], dim=2)
         if p_t is not None:
-            # reference quirk (:1212-1214): uses size(1) = n_views of the 6-D tensor
-            first_frame = image_latents[:, :, : image_latents.size(1) % p_t, ...]
+            # reference quirk (:1212-1214): uses size(1) = n_views of the 6-D tensor, so with ONE view
+            # and p_t = 2 a frame is prepended although num_frames was already padded by __call__, and the channel
+            # concatenation of the denoise loop then fails in the reference (:1413).  Reproduced by default;
+            # `pipe.fix_patch_t_padding = True` uses the frame count per view (what diffusers' own pipeline intends).
+            n = image_latents.size(2) if getattr(self, "fix_patch_t_padding", False) else image_latents.size(1)
+            first_frame = image_latents[:, :, : n % p_t, ...]
             image_latents = torch.cat([first_frame, image_latents], dim=2)
         image_latents = image_latents.flatten(1, 2)
         if latents is None:

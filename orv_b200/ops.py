@@ -33,7 +33,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
          gate_video_off: int = 0, rm: Optional[L.RowMap] = None, qk_dim: int = 0, q_norm=None, k_norm=None,
          qk_eps: float = 1e-6, rope=None, bn: int = 0, launch: bool = True, out_f32: bool = False):
     """out = epilogue(a @ w.T)  — a [M,K] bf16, w [N,K] bf16 (nn.Linear layout).  `launch=False` only fills and
-    returns `(GemmArgs, out)` (used by `gemm_chain`)."""
+    returns `(GemmArgs, out)`."""
     _req(a, torch.bfloat16, "a")
     _req(w, torch.bfloat16, "w")
     M, K = a.shape
@@ -80,19 +80,6 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     else:
         L.check(lib.orvb_gemm_bf16(C.byref(args), L.current_stream()), "orvb_gemm_bf16")
     return out
-
-
-def gemm_chain(first, second) -> torch.Tensor:
-    """EXPERIMENTAL (opt-in): two dependent GEMMs prepared with `gemm(..., launch=False)` — FF1 (+GELU) and FF2
-    (+gate, residual) whose `a` is FF1's `out` — as one persistent launch (`orvb_gemm_chain`).  Returns FF2's out."""
-    (a0, out0), (a1, out1) = first, second
-    lib = L.load()
-    stripes = (a0.m + 255) // 256
-    counters = torch.zeros((stripes + 1,), dtype=torch.int32, device=out0.device)
-    L.check(lib.orvb_gemm_chain(C.byref(a0), C.byref(a1), counters.data_ptr(), counters.numel() * 4,
-                                L.current_stream()), "orvb_gemm_chain")
-    out1._chain_counters = counters  # keeps the scratch alive until the (async) launch has consumed it
-    return out1
 
 
 def attention(qkv: torch.Tensor, batch: int, seq_len: int, heads: int, scale: float,
