@@ -108,6 +108,9 @@ typedef struct orvb_gemm_args {
    * before the bf16 rounding of the product path (same mainloop, same epilogue arithmetic, direct stores).  With
    * bf16-exact operands the result must match an fp32 reference to rtol 1e-3 / atol 1e-4 (tests/test_gpu_tight.py). */
   int32_t out_f32;
+  /* Optional DEVICE scalar added to every modulation-group index (the row of `gate`) — lets one captured launch
+   * sequence walk through the per-step slices of a modulation schedule (orvb_forward_args.schedule).  NULL = 0. */
+  const int32_t* group_offset;
 } orvb_gemm_args;
 
 /* tcgen05 / TMA GEMM.  Requirements: k % 8 == 0, n % 8 == 0, lda/ldw/ldo % 8 == 0, 16-byte aligned bases. */
@@ -167,6 +170,7 @@ typedef struct orvb_ln_args {
    * loads per element). */
   const void* ab; int32_t ab_ld;
   int32_t y_f32;                /* tight-tolerance test mode: y is fp32 [rows, dim] (values before the bf16 rounding) */
+  const int32_t* group_offset;  /* optional DEVICE scalar added to every group index (row of mod / ab); NULL = 0 */
 } orvb_ln_args;
 int orvb_ln_modulate(const orvb_ln_args* args, void* stream);
 
@@ -304,6 +308,12 @@ typedef struct orvb_forward_args {
    * checked for presence).  The caller uses SAVE on the first step of a clip and REUSE afterwards, on the same
    * workspace. */
   int32_t static_mode;
+  /* Modulation schedule read in place (preferred over orvb_modulation_select's copies: 22 MB per step for the 2B
+   * model).  schedule = the buffer orvb_modulation_schedule filled for `schedule_steps` steps of this shape;
+   * schedule_row_offset = DEVICE int32 holding step * (batch * (action_frames + 1)), written by the caller before each
+   * forward (a 4-byte device write instead of the table copies; the launch sequence itself — and a CUDA graph captured
+   * from it — is the same for every step).  Implies skip_modulation. */
+  const void* schedule; int32_t schedule_steps; const int32_t* schedule_row_offset;
 } orvb_forward_args;
 enum { ORVB_STATIC_COMPUTE = 0, ORVB_STATIC_SAVE = 1, ORVB_STATIC_REUSE = 2 };
 

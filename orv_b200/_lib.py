@@ -43,6 +43,7 @@ class GemmArgs(C.Structure):
         ("qk_eps", c_float),
         ("rope_cos", c_void_p), ("rope_sin", c_void_p),
         ("out_f32", c_int),
+        ("group_offset", c_void_p),
     ]
 
 
@@ -64,6 +65,7 @@ class LnArgs(C.Structure):
         ("pre_w", c_void_p), ("pre_b", c_void_p), ("pre_eps", c_float),
         ("ab", c_void_p), ("ab_ld", c_int),
         ("y_f32", c_int),
+        ("group_offset", c_void_p),
     ]
 
 
@@ -118,6 +120,7 @@ class ForwardArgs(C.Structure):
         ("tap_hidden", c_void_p), ("tap_layer", c_int),
         ("skip_modulation", c_int),
         ("static_mode", c_int),
+        ("schedule", c_void_p), ("schedule_steps", c_int), ("schedule_row_offset", c_void_p),
     ]
 
 

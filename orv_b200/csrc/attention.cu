@@ -44,7 +44,6 @@ constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units
 // issuers, 0/60 with one; same signature with two CTAs per SM — profiles/r01_attention_notes.md).  They are compiled
 // only into measurement builds (-DORVB_EXPERIMENTAL, ORVB_ATT_VARIANT); the product library does not contain them.
 constexpr int ATT_DEFAULT_VARIANT = 1;
-constexpr int ATT_DEFAULT_STAGGER = 0;  // clocks (ORVB_ATT_STAGGER overrides; see the softmax loop)
 
 struct AttDev {
   bf16* out;
@@ -54,7 +53,6 @@ struct AttDev {
   float rescale_threshold;  // log2 units by which a tile max must exceed the running max before it is raised
   long long* dbg;           // optional timeline buffer (tools/profile_attention_timeline.py); nullptr in production
   int out_f32;              // test mode: `out` is fp32 (the normalised accumulator before the bf16 rounding)
-  int stagger_clk;          // clocks by which the softmax warps of query tile 1 start behind those of tile 0
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -373,16 +371,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttDev p) {
     const int sw = row_in_tile & 7;
     const float scale = p.scale_log2;
 
-    // The two query tiles run the same loop on the same four MUFU units.  Started together they stay in lockstep: all
-    // 16 warps compute exponentials at once (MUFU saturated) and then all of them sit in the MUFU-free part of the
-    // iteration (barrier hops, S copy, fences) together.  Tile 1 therefore starts half an iteration late, so that its
-    // MUFU-free part falls into tile 0's exponentials and vice versa.
-    if (t == 1 && p.stagger_clk > 0) {
-      const long long t0 = clock64();
-      while (clock64() - t0 < p.stagger_clk) {
-      }
-    }
-
     for (int j = 0; j < n_kv; ++j) {
       A4_STAMP(warp, j, 0);
       mbar_wait(my_s_full, static_cast<uint32_t>(j & 1));
@@ -539,12 +527,6 @@ int attention_launch(const void* qkv, void* out, int batch, int seq_len, int hea
   p.q_rows = q_rows;
   p.dbg = g_att_dbg;
   p.out_f32 = out_f32 ? 1 : 0;
-  static int stagger = -1;
-  if (stagger < 0) {
-    const char* e = getenv("ORVB_ATT_STAGGER");
-    stagger = e ? atoi(e) : ATT_DEFAULT_STAGGER;
-  }
-  p.stagger_clk = stagger;
   // Test knob (ORVB_ATT_THRESHOLD or orvb_attention_set_rescale_threshold): 0 raises the running max on (almost) every key tile, i.e. forces the otherwise rare
   // TMEM read-modify-write of the O accumulators (tests/test_gpu_ops.py::test_attention_forced_rescale).
   if (g_att_threshold < 0.f) {

@@ -387,6 +387,26 @@ static int build_modulation(orvb_model* m, const Geometry& g, const ModIn& in, c
   return ORVB_OK;
 }
 
+// Buffer layout: the modulation scratch + tables of carve_modulation() for steps x batch virtual samples (step-major).
+static int schedule_layout(const orvb_model* m, const orvb_shape* s, int steps, uint8_t* base, Geometry* g1, Geometry* gv,
+                           Workspace* ws) {
+  ORVB_REQUIRE(m && s && steps > 0, ORVB_EINVAL, "orvb_modulation_*: bad arguments");
+  int rc = make_geometry(m->cfg, *s, g1);
+  if (rc != ORVB_OK) return rc;
+  *gv = *g1;
+  gv->B = g1->B * steps;
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    uint8_t* p = base ? base + off : nullptr;
+    off += align_up(n);
+    return p;
+  };
+  memset(ws, 0, sizeof(*ws));
+  carve_modulation(m->cfg, *gv, take, ws);
+  ws->bytes = off;
+  return ORVB_OK;
+}
+
 static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t st) {
   const orvb_config& c = m->cfg;
   const orvb_weights& w = m->w;
@@ -415,8 +435,26 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
   m->ev_cls.clear();
   ORVB_CLS(ORVB_PC_PROLOGUE);
 
-  // ---- 1-2. modulation tables (skipped when the caller installed this step's slice of a schedule) ----
-  if (!a->skip_modulation) {
+  // ---- 1-2. modulation tables (skipped when the caller installed this step's slice of a schedule, or when the
+  //           schedule is read in place through a device-side row offset) ----
+  const float* tab_mod = ws.mod;
+  const bf16* tab_ab = ws.ab;
+  size_t tab_rows = static_cast<size_t>(g.B) * g.G;  // rows per site table
+  const int32_t* goff = nullptr;
+  if (a->schedule != nullptr) {
+    ORVB_REQUIRE(a->schedule_steps > 0 && a->schedule_row_offset != nullptr, ORVB_EINVAL,
+                 "orvb_forward: schedule given without schedule_steps / schedule_row_offset");
+    Geometry g1, gv;
+    Workspace sw;
+    int src = schedule_layout(m, &a->shape, a->schedule_steps, const_cast<uint8_t*>(static_cast<const uint8_t*>(a->schedule)),
+                              &g1, &gv, &sw);
+    if (src != ORVB_OK) return src;
+    tab_mod = sw.mod;
+    tab_ab = sw.ab;
+    tab_rows = static_cast<size_t>(gv.B) * gv.G;
+    goff = a->schedule_row_offset;
+  }
+  if (!a->skip_modulation && a->schedule == nullptr) {
     ModIn in;
     in.timesteps = a->timesteps; in.ofs = a->ofs; in.actions = a->actions; in.action_mask = a->action_mask;
     int mrc = build_modulation(m, g, in, ws, st);
@@ -424,8 +462,8 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
   }
   const int mwid = mod_width(c);
   const int gate_text_off = c.modulate_text ? 5 * D : 2 * D;  // enc_gate, or (no text rows exist) the video gate
-  const size_t site_stride = static_cast<size_t>(g.B) * g.G * mwid * D;
-  const size_t ab_stride = static_cast<size_t>(g.B) * g.G * 4 * D;
+  const size_t site_stride = tab_rows * mwid * D;
+  const size_t ab_stride = tab_rows * 4 * D;
   ORVB_REQUIRE(a->static_mode >= ORVB_STATIC_COMPUTE && a->static_mode <= ORVB_STATIC_REUSE, ORVB_EINVAL,
                "orvb_forward: unknown static_mode %d", a->static_mode);
   const bool st_save = a->static_mode == ORVB_STATIC_SAVE, st_reuse = a->static_mode == ORVB_STATIC_REUSE;
@@ -511,14 +549,14 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
       // ---- MVBlock (cogvideox_control.py:313-348): cross-view attention per (clip, frame) ----
       const orvb_block_weights& mw = m->mv_blocks[l];
       const size_t site = static_cast<size_t>(2 * c.layers + 1 + l);
-      const float* modv = ws.mod + site * site_stride;
+      const float* modv = tab_mod + site * site_stride;
       const int clips = g.B / g.V, tok = g.Hp * g.Wp, Smv = g.V * (g.St + tok);
       orvb_rowmap rm0 = rm;
       rm0.tokens_per_group = 0;  // norm1(temb) only: every row of a sample uses its time-only group
       orvb_ln_args lnv;
       memset(&lnv, 0, sizeof(lnv));
       lnv.x = ws.x; lnv.y = ws.xn; lnv.rows = g.R; lnv.dim = D; lnv.eps = c.norm_eps; lnv.rowmap = rm0;
-      lnv.ab = ws.ab + site * ab_stride; lnv.ab_ld = 4 * D;
+      lnv.ab = tab_ab + site * ab_stride; lnv.ab_ld = 4 * D; lnv.group_offset = goff;
       ORVB_CLS(ORVB_PC_LN);
       ORVB_TRY(ln_modulate_launch(&lnv, st));
       orvb_gemm_args q = gemm_base(ws.xn, mw.qkv_w, mw.qkv_b, ws.qkv, g.R, 3 * D, D, D, 3 * D, ORVB_EPI_QKV);
@@ -537,18 +575,18 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
       orvb_gemm_args o2 = gemm_base(ws.tmp_mv, mw.proj_out_w, mw.proj_out_b, ws.x, Mv, D, D, D, D, ORVB_EPI_GATE_RESID);
       o2.mv_tokens = tok; o2.mv_frames = g.Fp; o2.mv_views = g.V; o2.dst_rows = g.S; o2.dst_offset = g.St;
       o2.resid = ws.x; o2.ldr = D; o2.gate = modv; o2.gate_ld = mwid * D; o2.gate_text_off = gate_text_off; o2.gate_video_off = 2 * D;
-      o2.rowmap = rm0;
+      o2.rowmap = rm0; o2.group_offset = goff;
       ORVB_TRY(gemm_run(&o2, st));
     }
     const orvb_block_weights& bw = m->blocks[l];
-    const float* mod1 = ws.mod + (2 * l) * site_stride;
-    const float* mod2 = ws.mod + (2 * l + 1) * site_stride;
+    const float* mod1 = tab_mod + (2 * l) * site_stride;
+    const float* mod2 = tab_mod + (2 * l + 1) * site_stride;
     orvb_ln_args ln;
     memset(&ln, 0, sizeof(ln));
     ln.x = ws.x; ln.y = ws.xn; ln.ln_w = bw.norm1_ln_w; ln.ln_b = bw.norm1_ln_b;
     ln.rows = g.R; ln.dim = D; ln.eps = c.norm_eps;
     ln.rowmap = rm;
-    ln.ab = ws.ab + (2 * l) * ab_stride; ln.ab_ld = 4 * D;
+    ln.ab = tab_ab + (2 * l) * ab_stride; ln.ab_ld = 4 * D; ln.group_offset = goff;
     ORVB_CLS(ORVB_PC_LN);
     ORVB_TRY(ln_modulate_launch(&ln, st));
 
@@ -564,18 +602,18 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
 
     orvb_gemm_args o = gemm_base(ws.att, bw.out_w, bw.out_b, ws.x, g.R, D, D, D, D, ORVB_EPI_GATE_RESID);
     o.resid = ws.x; o.ldr = D; o.gate = mod1; o.gate_ld = mwid * D; o.gate_text_off = gate_text_off; o.gate_video_off = 2 * D;
-    o.rowmap = rm;
+    o.rowmap = rm; o.group_offset = goff;
     ORVB_CLS(ORVB_PC_OUT);
     ORVB_TRY(gemm_run(&o, st));
 
-    ln.ab = ws.ab + (2 * l + 1) * ab_stride;
+    ln.ab = tab_ab + (2 * l + 1) * ab_stride;
     ORVB_CLS(ORVB_PC_LN);
     ORVB_TRY(ln_modulate_launch(&ln, st));
 
     orvb_gemm_args f1 = gemm_base(ws.xn, bw.ff1_w, bw.ff1_b, ws.ffh, g.R, g.FF, D, D, g.FF, ORVB_EPI_GELU);
     orvb_gemm_args f2 = gemm_base(ws.ffh, bw.ff2_w, bw.ff2_b, ws.x, g.R, D, g.FF, g.FF, D, ORVB_EPI_GATE_RESID);
     f2.resid = ws.x; f2.ldr = D; f2.gate = mod2; f2.gate_ld = mwid * D; f2.gate_text_off = gate_text_off; f2.gate_video_off = 2 * D;
-    f2.rowmap = rm;
+    f2.rowmap = rm; f2.group_offset = goff;
     ORVB_CLS(ORVB_PC_FF1);
     ORVB_TRY(gemm_run(&f1, st));
     ORVB_CLS(ORVB_PC_FF2);
@@ -595,7 +633,7 @@ static int forward_impl(orvb_model* m, const orvb_forward_args* a, cudaStream_t 
     ln.ln_w = w.norm_out_ln_w; ln.ln_b = w.norm_out_ln_b; ln.eps = c.norm_eps;
     ORVB_CLS(ORVB_PC_HEAD);
     ln.rowmap = rm; ln.in_video_only = 1;
-    ln.ab = ws.ab + static_cast<size_t>(2 * c.layers) * ab_stride; ln.ab_ld = 4 * D;
+    ln.ab = tab_ab + static_cast<size_t>(2 * c.layers) * ab_stride; ln.ab_ld = 4 * D; ln.group_offset = goff;
     ORVB_TRY(ln_modulate_launch(&ln, st));
     orvb_gemm_args po = gemm_base(ws.xn, w.proj_out_w, w.proj_out_b, ws.yout, g.B * g.Sv, g.Nout, D, D, g.Nout,
                                   ORVB_EPI_BIAS);
@@ -694,28 +732,6 @@ extern "C" size_t orvb_workspace_bytes(const orvb_model* m, const orvb_shape* s)
 }
 
 // ---- modulation schedule: the AdaLN tables of many timesteps at once ------------------------------------------
-namespace orvb {
-// Buffer layout: the modulation scratch + tables of carve_modulation() for steps x batch virtual samples (step-major).
-static int schedule_layout(const orvb_model* m, const orvb_shape* s, int steps, uint8_t* base, Geometry* g1, Geometry* gv,
-                           Workspace* ws) {
-  ORVB_REQUIRE(m && s && steps > 0, ORVB_EINVAL, "orvb_modulation_*: bad arguments");
-  int rc = make_geometry(m->cfg, *s, g1);
-  if (rc != ORVB_OK) return rc;
-  *gv = *g1;
-  gv->B = g1->B * steps;
-  size_t off = 0;
-  auto take = [&](size_t n) {
-    uint8_t* p = base ? base + off : nullptr;
-    off += align_up(n);
-    return p;
-  };
-  memset(ws, 0, sizeof(*ws));
-  carve_modulation(m->cfg, *gv, take, ws);
-  ws->bytes = off;
-  return ORVB_OK;
-}
-}  // namespace orvb
-
 extern "C" size_t orvb_modulation_bytes(const orvb_model* m, const orvb_shape* s, int32_t steps) {
   using namespace orvb;
   Geometry g1, gv;

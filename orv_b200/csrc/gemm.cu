@@ -38,6 +38,7 @@ struct GemmDev {
   int num_m_tiles, num_n_tiles;
   int tma_store;  // pair kernel: stage full 64-column units in shared memory and write them with TMA
   int out_f32;    // test mode: `out` is fp32, written before the bf16 rounding (direct stores only)
+  const int* grp_off;  // optional device scalar added to the modulation-group index (schedule slice of this step)
 };
 
 constexpr int BM = 128;
@@ -152,6 +153,7 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float (&v)[64], 
     if (p.gate != nullptr) {
       int s;
       int g = row_group(p.rm, out_row, &s);  // modulation group of the DESTINATION row
+      if (p.grp_off != nullptr) g += *p.grp_off;
       int is_text = (p.rm.seq_len > 0) ? (s < p.rm.text_len) : 0;
       const float* gp = p.gate + static_cast<size_t>(g) * p.gate_ld + (is_text ? p.gate_text_off : p.gate_video_off) + n0;
 #pragma unroll
@@ -818,6 +820,7 @@ int gemm_prepare(const orvb_gemm_args* a, int bn_override, CUtensorMap* ta, CUte
   GemmDev d;
   d.tma_store = tma_store ? 1 : 0;
   d.out_f32 = a->out_f32 ? 1 : 0;
+  d.grp_off = a->group_offset;
   d.M = a->m; d.N = a->n; d.K = a->k;
   d.out = static_cast<bf16*>(a->out); d.ldo = a->ldo;
   d.bias = static_cast<const bf16*>(a->bias);

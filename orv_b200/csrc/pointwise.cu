@@ -48,6 +48,7 @@ struct LnDev {
   const bf16* ab;  // optional pre-combined table: per group row [text A | text B | video A | video B], each `dim`
   int ab_ld;
   int y_f32;       // test mode: y is fp32 (generic kernel only)
+  const int* grp_off;  // optional device scalar added to every group index (schedule slice of this step)
 };
 
 __device__ __forceinline__ void ln_store8(const LnDev& p, int row, int c, const float (&o)[8]) {
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const LnDev p) {
     // y = xhat * A_g + B_g with A = w * (1 + scale), B = b * (1 + scale) + shift folded once per forward
     // (ab_combine_kernel): one memory phase, every load issued before the reductions.
     int is_text;
-    const int g = row_group_pw(p.rm, in_row, &is_text);
+    const int g = row_group_pw(p.rm, in_row, &is_text) + (p.grp_off != nullptr ? *p.grp_off : 0);
     const bf16* ap = p.ab + static_cast<size_t>(g) * p.ab_ld + (is_text ? 0 : 2 * p.dim);
     uint4 av[MAXC], bv[MAXC];
 #pragma unroll
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const LnDev p) {
   const float* scale = nullptr;
   if (p.mod != nullptr) {
     int is_text;
-    const int g = row_group_pw(p.rm, in_row, &is_text);
+    const int g = row_group_pw(p.rm, in_row, &is_text) + (p.grp_off != nullptr ? *p.grp_off : 0);
     const float* base = p.mod + static_cast<size_t>(g) * p.mod_ld + (is_text ? p.text_off : p.video_off);
     shift = p.scale_first ? base + p.dim : base;
     scale = p.scale_first ? base : base + p.dim;
@@ -215,12 +216,13 @@ __global__ void __launch_bounds__(256, 4) ln_ab_kernel(const LnDev p) {
   int t0, t1;
   const int g0 = row_group_pw(p.rm, row0, &t0);
   const int g1 = row_group_pw(p.rm, row_last, &t1);
-  const bf16* ap0 = p.ab + static_cast<size_t>(g0) * p.ab_ld + (t0 ? 0 : 2 * p.dim);
-  const bf16* ap1 = p.ab + static_cast<size_t>(g1) * p.ab_ld + (t1 ? 0 : 2 * p.dim);
   const int row = row0 + warp;
   const bool live = row < p.rows;
   pdl_launch_dependents();
-  pdl_wait();  // x comes from the previous kernel
+  pdl_wait();  // x comes from the previous kernel (and the group offset from an earlier one)
+  const int goff = p.grp_off != nullptr ? *p.grp_off : 0;
+  const bf16* ap0 = p.ab + static_cast<size_t>(g0 + goff) * p.ab_ld + (t0 ? 0 : 2 * p.dim);
+  const bf16* ap1 = p.ab + static_cast<size_t>(g1 + goff) * p.ab_ld + (t1 ? 0 : 2 * p.dim);
   // this warp's row first (longest latency), then the cooperative table copy
   uint4 xr[MAXC];
   if (live) {
@@ -328,6 +330,7 @@ int ln_modulate_launch(const orvb_ln_args* a, cudaStream_t stream) {
   d.scale_first = a->scale_first; d.rm = a->rowmap; d.in_video_only = a->in_video_only;
   d.ab = static_cast<const bf16*>(a->ab); d.ab_ld = a->ab_ld;
   d.y_f32 = a->y_f32 ? 1 : 0;
+  d.grp_off = a->group_offset;
   ORVB_REQUIRE(d.ab == nullptr || (a->ab_ld % 8 == 0 && a->ab_ld >= 4 * a->dim), ORVB_ESHAPE,
                "orvb_ln_modulate: ab_ld must be a multiple of 8 and >= 4*dim");
   const int rows_per_block = 8;

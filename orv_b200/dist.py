@@ -43,9 +43,12 @@ def broadcast_arena(arena: torch.Tensor, src: int = 0) -> torch.Tensor:
 
 
 def broadcast_weights(model, src: int = 0) -> None:
-    """Broadcasts a CogVideoXTransformer3DModelTraj's weight arena.  Parameters alias the arena, so after the
-    call every rank's module holds rank `src`'s weights."""
+    """Broadcasts a CogVideoXTransformer3DModelTraj's weight arena.  bf16 parameters are views into the arena, so they
+    hold rank `src`'s weights right after the call; the few parameters that cannot alias it (zero-padded matrices,
+    non-bf16 tensors) are refreshed from the received arena, so `state_dict()` and a later re-pack agree with it."""
     broadcast_arena(model.weight_arena(), src)
+    if hasattr(model, "sync_parameters_from_arena"):
+        model.sync_parameters_from_arena()
 
 
 def max_over_ranks(value: float, device) -> float:

@@ -217,6 +217,8 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
         self._graphs: Dict[Tuple, Any] = {}
         # Replay the ~220-launch forward as one CUDA graph once a (shape, input-address) combination repeats.
         self.use_cuda_graph = os.environ.get("ORVB_CUDA_GRAPH", "1") != "0"
+        # modulation schedule read in place by the kernels (ORVB_SCHED_IN_PLACE=0: copy step i's slice per forward)
+        self._sched_in_place = os.environ.get("ORVB_SCHED_IN_PLACE", "1") != "0"
         self._profiling = False
         self._pos_cache: Dict[Tuple, torch.Tensor] = {}
         self._bound_pos_key = None
@@ -349,7 +351,13 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
         call, `forward(..., _mod_step=i)` installs step i's tables and skips that part; results are bit-identical.
         The eval-time action-mask draw of the reference (one `torch.rand(B)` per forward, components.py:66-69) is
         made here, once per step and in step order, so the device RNG stream is consumed exactly as without a schedule.
-        `hidden_shape` = shape of the `hidden_states` the forwards will receive ([B, V*F, C, H, W])."""
+        `hidden_shape` = shape of the `hidden_states` the forwards will receive ([B, V*F, C, H, W]).
+
+        Limitation: the mask draws of all steps are made HERE, back to back.  That reproduces the per-forward stream
+        exactly when the sampler's noise comes from a different generator (the CPU generator the reference scripts
+        pass, inference_control_to_video.py:144).  With `generator=None` or a CUDA generator shared with the DPM noise
+        draws, the reference interleaves mask and noise draws step by step; then set ORVB_MOD_SCHEDULE=0 to get
+        the same samples for the same seed (the per-step path interleaves as the reference does)."""
         self._ensure_handle()
         dev = next(self.parameters()).device
         c = self.config
@@ -368,21 +376,23 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
             if res_frames > 0:
                 pad = actions.new_zeros((actions.shape[0], 4 - res_frames, actions.shape[2]))
                 actions = torch.cat([pad, actions], dim=1)
-            rows, mk, im = [], [], []
-            for _ in range(steps):  # one RNG draw per step, in order
-                act_in, is_mask, apply = self.action_embed.prepare(actions.to(dev))
-                if V > 1:
-                    act_in, apply = act_in.repeat_interleave(V, dim=0), apply.repeat_interleave(V, dim=0)
-                if act_in.shape[0] != B:
-                    raise RuntimeError(f"The size of tensor a ({B}) must match the size of tensor b ({act_in.shape[0]}) at "
-                                       "non-singleton dimension 0")
-                rows.append(act_in)
-                mk.append(apply)
-                im.append(is_mask)
-            action_frames = rows[0].shape[1]
-            act_rows = torch.stack(rows).to(torch.bfloat16).contiguous()          # [steps, B, F', k]
-            masks = torch.stack(mk).contiguous() if bool(self.action_embed.mask) else None
-            is_masks = im
+            # The MLP input is the same for every step; only the reference's eval-time mask draw (`torch.rand(B)` per
+            # forward, components.py:66) differs: one draw per step, in step order, on the same device generator.
+            act_in = self.action_embed.mlp_input(actions.to(dev))
+            draws = torch.stack([torch.rand(act_in.shape[0], device=dev) for _ in range(steps)])
+            is_mask_all = draws < 0.1                                              # [steps, B_actions]
+            if V > 1:
+                act_in = act_in.repeat_interleave(V, dim=0)
+            if act_in.shape[0] != B:
+                raise RuntimeError(f"The size of tensor a ({B}) must match the size of tensor b ({act_in.shape[0]}) at "
+                                   "non-singleton dimension 0")
+            action_frames = act_in.shape[1]
+            act_rows = act_in.to(torch.bfloat16).unsqueeze(0).expand(steps, *act_in.shape).contiguous()  # [steps, B, F', k]
+            masks = None
+            if bool(self.action_embed.mask):
+                mk = is_mask_all.repeat_interleave(V, dim=1) if V > 1 else is_mask_all
+                masks = mk.to(torch.uint8).contiguous()
+            is_masks = list(is_mask_all.unbind(0))
         ofs_val = 0.0
         if self.ofs_embedding is not None:
             if ofs is None:
@@ -398,14 +408,29 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
             buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
             self.__dict__["_mod_buf"] = buf
         ptr = (buf.data_ptr() + 255) // 256 * 256
-        ts_dev = ts.repeat_interleave(B).to(dev).contiguous()                      # step-major [steps * B]
+        # step-major [steps * B], uploaded through a cached pinned buffer (a pageable H2D copy would synchronise)
+        pin = self.__dict__.get("_ts_pin")
+        if pin is None or pin.numel() < steps * B:
+            pin = torch.empty(max(steps * B, 256), dtype=torch.float32).pin_memory()
+            self.__dict__["_ts_pin"] = pin
+        pin[: steps * B].copy_(ts.repeat_interleave(B))
+        ts_dev = torch.empty(steps * B, dtype=torch.float32, device=dev)
+        ts_dev.copy_(pin[: steps * B], non_blocking=True)
         L.check(lib.orvb_modulation_schedule(self._handle, C.byref(shape), steps, ts_dev.data_ptr(), ofs_val,
                                              L.ptr(act_rows), L.ptr(masks), ptr, buf.numel() - (ptr - buf.data_ptr()),
                                              L.current_stream()), "orvb_modulation_schedule")
         self.__dict__["last_schedule_launches"] = lib.orvb_last_launch_count(self._handle)
         self.__dict__["_mod_sched"] = SimpleNamespace(
             steps=steps, ptr=ptr, buf=buf, action_frames=action_frames, is_mask=is_masks,
+            row_offset=self._sched_row_offset(dev),
             wkey=(B, V, Fr, H, W, text_len, action_frames, dev.index), keep=(ts_dev, act_rows, masks))
+
+    def _sched_row_offset(self, dev) -> torch.Tensor:
+        t = self.__dict__.get("_sched_off")
+        if t is None or t.device != dev:
+            t = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.__dict__["_sched_off"] = t
+        return t
 
     def clear_modulation_schedule(self) -> None:
         self.__dict__["_mod_sched"] = None
@@ -519,6 +544,7 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
             offsets[key] = (off, n)
             off += (n + 127) // 128 * 128  # 256-byte aligned slots
         arena = torch.zeros(off, dtype=torch.bfloat16, device=dev)
+        unaliased = []  # (parameter, arena view of its values): padded or non-bf16 parameters cannot alias the arena
         with torch.no_grad():
             for key, params, pad_cols in entries:
                 o, _ = offsets[key]
@@ -528,6 +554,7 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
                         cols = p.numel() // rows
                         view = arena[o:o + rows * (cols + pad_cols)].view(rows, cols + pad_cols)
                         view[:, :cols].copy_(p.detach().reshape(rows, cols))
+                        unaliased.append((p, view[:, :cols]))
                         o += rows * (cols + pad_cols)
                     else:
                         n = p.numel()
@@ -535,8 +562,10 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
                         view.copy_(p.detach())
                         if p.dtype == torch.bfloat16:
                             p.data = view  # the parameter now lives in the arena
+                        else:
+                            unaliased.append((p, view))
                         o += n
-        self.__dict__["_pack"] = SimpleNamespace(arena=arena, offsets=offsets, keepalive=[])
+        self.__dict__["_pack"] = SimpleNamespace(arena=arena, offsets=offsets, keepalive=[], unaliased=unaliased)
 
     def _ptr(self, key):
         pk = self._pack
@@ -613,6 +642,16 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
             L.check(lib.orvb_model_bind_weights(self._handle, C.byref(w)), "orvb_model_bind_weights")
             self.__dict__["_bound_pos_key"] = pos_key
             self._graphs.clear()
+
+    def sync_parameters_from_arena(self) -> None:
+        """Writes the arena's values back into the parameters that do not alias it (zero-padded matrices such as
+        action_embed.mlp.0.weight, non-bf16 parameters).  Called after the arena was overwritten from outside — the
+        multi-GPU weight broadcast — so that `state_dict()` and any later re-pack see the received values."""
+        if self._pack is None:
+            return
+        with torch.no_grad():
+            for p, view in self._pack.unaliased:
+                p.copy_(view.reshape(p.shape).to(p.dtype))
 
     def weight_arena(self) -> torch.Tensor:
         """The contiguous bf16 weight arena (built on first use) — the single tensor a multi-GPU launcher
@@ -691,22 +730,24 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
 
         hs = hidden_states.to(torch.bfloat16).contiguous()
         text = encoder_hidden_states.to(torch.bfloat16).contiguous() if St > 0 else None
-        if not torch.is_tensor(timestep):
-            timestep = torch.tensor([timestep], device=dev)
-        ts = timestep.to(device=dev, dtype=torch.float32).reshape(-1)
-        if ts.numel() == 1 and B > 1:
-            ts = ts.expand(B)
-        elif V > 1 and ts.numel() == Bc:
-            ts = ts.repeat_interleave(V)  # multiviews share the same noise level (:778-779)
-        ts = ts.contiguous()
-        if ts.numel() != B:
-            raise RuntimeError(f"timestep has {ts.numel()} entries for batch {B}")
+        sched = self.__dict__.get("_mod_sched") if _mod_step is not None else None
+        ts = None
+        if sched is None:  # (a scheduled step consumed the timesteps when its tables were built)
+            if not torch.is_tensor(timestep):
+                timestep = torch.tensor([timestep], device=dev)
+            ts = timestep.to(device=dev, dtype=torch.float32).reshape(-1)
+            if ts.numel() == 1 and B > 1:
+                ts = ts.expand(B)
+            elif V > 1 and ts.numel() == Bc:
+                ts = ts.repeat_interleave(V)  # multiviews share the same noise level (:778-779)
+            ts = ts.contiguous()
+            if ts.numel() != B:
+                raise RuntimeError(f"timestep has {ts.numel()} entries for batch {B}")
 
         # ---- actions: integer bookkeeping of :805-812 on the host, MLP on the device ----
         act_in = mask_u8 = is_action_mask = None
         action_frames = 0
         actions = controls_or_guidances.get("actions", None)
-        sched = self.__dict__.get("_mod_sched") if _mod_step is not None else None
         if _mod_step is not None:
             if sched is None or not (0 <= _mod_step < sched.steps):
                 raise RuntimeError("_mod_step given but no matching modulation schedule is installed "
@@ -758,8 +799,8 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
             rope_cos = image_rotary_emb[0].to(device=dev, dtype=torch.float32).contiguous()
             rope_sin = image_rotary_emb[1].to(device=dev, dtype=torch.float32).contiguous()
         ofs_val = 0.0
-        if self.ofs_embedding is not None:
-            if ofs is None:
+        if self.ofs_embedding is not None and sched is None:  # (a scheduled step consumed ofs when the tables were built;
+            if ofs is None:                                   #  reading it here would cost a device sync per step)
                 raise RuntimeError("this model has an ofs embedding; pass `ofs`")
             ofs_val = float(ofs.reshape(-1)[0].item()) if torch.is_tensor(ofs) else float(ofs)
 
@@ -788,9 +829,14 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
         if sched is not None:
             if sched.wkey != wkey:
                 raise RuntimeError(f"modulation schedule was built for shape key {sched.wkey}, forward called with {wkey}")
-            L.check(lib.orvb_modulation_select(self._handle, C.byref(shape), sched.steps, _mod_step, sched.ptr, ws_ptr,
-                                               L.current_stream()), "orvb_modulation_select")
-        sm.ts.copy_(ts)
+            if self._sched_in_place:
+                # the kernels read step i's slice of the schedule in place: one 4-byte device write per step
+                sched.row_offset.fill_(_mod_step * B * (action_frames + 1))
+            else:  # copy the slice into the forward workspace (22 MB per step for the 2B model)
+                L.check(lib.orvb_modulation_select(self._handle, C.byref(shape), sched.steps, _mod_step, sched.ptr, ws_ptr,
+                                                   L.current_stream()), "orvb_modulation_select")
+        if sched is None:
+            sm.ts.copy_(ts)
         if act_in is not None:
             if sm.act is None:  # entry first created by a scheduled call (no per-step action input)
                 sm.act = torch.empty_like(act_in)
@@ -814,6 +860,9 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
         else:
             a.tap_layer = -1
         a.skip_modulation = 1 if sched is not None else 0
+        if sched is not None and self._sched_in_place:
+            a.schedule, a.schedule_steps = sched.ptr, sched.steps
+            a.schedule_row_offset = sched.row_offset.data_ptr()
         a.static_mode = int(_static_mode)
 
         def launch():
@@ -825,7 +874,8 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
             return list(buf[:min(n, 4096)])
 
         gkey = (wkey, hs.data_ptr(), L.ptr(text), L.ptr(depths), L.ptr(labels), L.ptr(rope_cos), L.ptr(rope_sin),
-                ofs_val, mask_u8 is not None, sched is not None, int(_static_mode))
+                ofs_val, mask_u8 is not None, (sched.ptr, sched.steps, self._sched_in_place) if sched is not None else None,
+                int(_static_mode))
         if self.use_cuda_graph and _tap is None and not self._profiling:
             ent = self._graphs.get(gkey)
             if ent is None:

@@ -44,10 +44,9 @@ class ActionEmbed(nn.Module):
         )
         self.mask_embed = nn.Embedding(num_embeddings=1, embedding_dim=hidden_size)
 
-    def prepare(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        """Everything of `forward` (components.py:47-71) except the MLP arithmetic.
-
-        Returns (mlp_input [B, F', state*compress*pt], is_mask [B] bool, apply_mask [B] uint8)."""
+    def mlp_input(self, x: torch.Tensor) -> torch.Tensor:
+        """The integer bookkeeping of `forward` in front of the MLP (components.py:47-62): first-frame padding and the
+        compress / patch_size_t reshapes.  [B, F, state] -> [B, F', state*compress*pt]."""
         B, Fr, state_dim = x.shape
         if state_dim != self.state_dim:
             raise ValueError(f"Got mismatched {x.shape=} and {self.state_dim=}.")
@@ -57,9 +56,16 @@ class ActionEmbed(nn.Module):
         if self.patch_size_t > 1:
             _, Fr2, _ = x.shape
             x = x.reshape(B, Fr2 // self.patch_size_t, -1)
-        is_mask = torch.rand(B, device=x.device) < 0.1  # drawn on every call, as the reference does
+        return x.contiguous()
+
+    def prepare(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Everything of `forward` (components.py:47-71) except the MLP arithmetic.
+
+        Returns (mlp_input [B, F', state*compress*pt], is_mask [B] bool, apply_mask [B] uint8)."""
+        x = self.mlp_input(x)
+        is_mask = torch.rand(x.shape[0], device=x.device) < 0.1  # drawn on every call, as the reference does (:66)
         apply = is_mask if self.mask else torch.zeros_like(is_mask)
-        return x.contiguous(), is_mask, apply.to(torch.uint8)
+        return x, is_mask, apply.to(torch.uint8)
 
     def forward(self, x):  # pragma: no cover - the arithmetic lives in liborv_b200
         raise RuntimeError("ActionEmbed runs inside orvb_forward; call the transformer, not this module")

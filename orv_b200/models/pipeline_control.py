@@ -351,8 +351,11 @@ class CogVideoXImageToVideoPipelineTraj:
             if nk not in self._staging:
                 self._staging[nk] = ([torch.empty(latents.shape, dtype=latents.dtype, device=device) for _ in range(2)],
                                      [torch.empty(latents.shape, dtype=latents.dtype).pin_memory() for _ in range(2)],
-                                     [torch.cuda.Event(), torch.cuda.Event()])
-            noise_dev, noise_pin, noise_evt = self._staging[nk]
+                                     [torch.cuda.Event(), torch.cuda.Event()],
+                                     [torch.cuda.Event(), torch.cuda.Event()], torch.cuda.Stream(device=device))
+            noise_dev, noise_pin, noise_evt, used_evt, copy_stream = self._staging[nk]
+            for ev in used_evt:  # "the sampler step that last read this slot has run": trivially true at the start
+                ev.record()
         # Persistent device staging (keyed by shape): the transformer reads its large inputs in place, so stable
         # addresses let one captured CUDA graph serve every iteration of every clip.
         def stage(name, t):
@@ -428,14 +431,20 @@ class CogVideoXImageToVideoPipelineTraj:
                                 nz = randn_tensor(latents.shape, generator, "cpu", latents.dtype)
                             noise_evt[slot].synchronize()  # the H2D that last used this pinned slot has finished
                             noise_pin[slot].copy_(nz)
-                            noise_dev[slot].copy_(noise_pin[slot], non_blocking=True)
-                            noise_evt[slot].record()
+                            # upload on a side stream WHILE this step's forward runs (on the compute stream the copy
+                            # would queue behind the forward and sit in front of the sampler step: ~60 us per step)
+                            copy_stream.wait_event(used_evt[slot])
+                            with torch.cuda.stream(copy_stream):
+                                noise_dev[slot].copy_(noise_pin[slot], non_blocking=True)
+                                noise_evt[slot].record()
+                            torch.cuda.current_stream().wait_event(noise_evt[slot])
                         else:
                             for _ in range(draws[i]):
                                 nz = randn_tensor(latents.shape, generator, device, latents.dtype)
                             noise_dev[slot].copy_(nz)
                         self.scheduler.fused_step(noise_pred, old_x0, have_old, t, ts_list[i - 1] if i > 0 else None,
                                                   latents, noise_dev[slot], n_cfg, self.guidance_scale, model_input)
+                        used_evt[slot].record()
                         have_old = True
                     else:
                         self.scheduler.fused_step(noise_pred, t, latents, n_cfg, self.guidance_scale, model_input)

@@ -125,3 +125,26 @@ def test_modulation_schedule_is_bit_identical(mask_on, views):
             m(hs, text, cg, torch.full((B,), 499.0, device="cuda"), return_dict=False, num_views=views, _mod_step=0)
     if mask_on:
         assert any(bool(k.any()) for _, k in ref) or True  # 10 % draws: may be all-False for a tiny batch
+
+
+def test_weight_broadcast_refreshes_parameters_that_cannot_alias_the_arena():
+    """after the arena is overwritten from outside (the NCCL weight broadcast), the zero-padded
+    action_embed.mlp.0.weight (K = 28 -> 32) must follow, or a later re-pack would silently restore the old values."""
+    from orv_b200 import dist as D
+    cfg = small_cfg()
+    src = build_model(cfg, O.synthetic_state_dict(cfg, seed=0, std=0.05))
+    dst = build_model(cfg, O.synthetic_state_dict(cfg, seed=7, std=0.05))
+    key = "action_embed.mlp.0.weight"
+    assert not torch.equal(src.state_dict()[key], dst.state_dict()[key])
+    dst.weight_arena().copy_(src.weight_arena())  # what dist.broadcast does on a non-source rank
+    D.broadcast_weights(dst, src=0)                # world size 1: no collective, but the refresh must still run
+    for k, v in src.state_dict().items():
+        assert torch.equal(dst.state_dict()[k], v), k
+    inp = O.synthetic_inputs(cfg, 1, 3, 6, 8, seed=1, n_actions=8)
+    args = (inp["hidden_states"].cuda().bfloat16(), inp["text"].cuda().bfloat16(),
+            {"actions": inp["actions"].cuda().bfloat16()}, torch.tensor([499], device="cuda"))
+    with torch.no_grad():
+        a = src(*args, return_dict=False)[0]
+        dst._invalidate()  # force a re-pack from the parameters
+        b = dst(*args, return_dict=False)[0]
+    assert torch.equal(a, b)

@@ -1,5 +1,7 @@
-"""CPU: the latent-format reader and the condition cache against the reference's read path, restated
-line by line in this file (dataset.py:655-694, 785-850, 1054-1059 for the sample; :2072-2126 for the collate)."""
+"""CPU: the latent-format reader and the condition cache against the reference's read path as restated
+in oracle/latent_oracle.py (dataset.py:655-694, 785-850, 1054-1059 for the sample; :2053-2126 for the collate), and the
+collate against tests/golden/collate_control.pt — the output of the reference's OWN CollateFunctionControl
+(oracle/make_latent_golden.py)."""
 import os
 
 import pytest
@@ -8,51 +10,31 @@ import torch
 from orv_b200.latent_store import ConditionCache, LatentStore, collate_control, sample_name
 
 
-def _write_dataset(root, names, C=32, F=5, h=6, w=8, S=7, E=16):
-    """Files as encode_dataset.py writes them (:353-363): one [C, F, h, w] moments tensor per sample and folder, plus
-    empty_prompt.pt with a batch dimension (:1073-1094)."""
-    g = torch.Generator().manual_seed(0)
+from oracle import latent_oracle as LO
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _write_dataset(root, names, **kw):
+    """Files as encode_dataset.py writes them (:353-363), from the oracle's seeded stand-ins."""
+    files = LO.synthetic_files(names, **kw)
     base = os.path.join(root, "emb", "val")
-    files = {}
-    for folder, frames in (("video_latents", F), ("image1_latents", 1), ("depth_latents", F), ("label_latents", F),
-                           ("depthGT_latents", F)):
+    for key, t in files.items():
+        if key == "empty":
+            torch.save(t, os.path.join(root, "emb", "empty_prompt.pt"))
+            continue
+        folder, n = key
         os.makedirs(os.path.join(base, folder), exist_ok=True)
-        for n in names:
-            t = torch.randn((C, frames, h, w), generator=g).to(torch.bfloat16)
-            torch.save(t, os.path.join(base, folder, f"{n}.pt"))
-            files[(folder, n)] = t
-    os.makedirs(os.path.join(base, "prompt_embeds"), exist_ok=True)
-    for n in names:
-        t = torch.randn((S, E), generator=g).to(torch.bfloat16)
-        torch.save(t, os.path.join(base, "prompt_embeds", f"{n}.pt"))
-        files[("prompt_embeds", n)] = t
-    empty = torch.randn((1, S, E), generator=g).to(torch.bfloat16)
-    torch.save(empty, os.path.join(root, "emb", "empty_prompt.pt"))
-    files["empty"] = empty
+        torch.save(t, os.path.join(base, folder, f"{n}.pt"))
     return files
 
 
-def _reference_sample(files, n, views=None, gt=False):
-    # dataset.py:673-694 (3-D VAE latents are [C, F, H, W] on disk), :814-827, :836-848, :1056-1059
-    out = {"prompt_embeds": files["empty"][0]}
-    out["latents"] = files[("video_latents", n)].permute(1, 0, 2, 3)
-    out["image"] = files[("image1_latents", n)].permute(1, 0, 2, 3)
-    views = views or [n]
-    d = "depthGT_latents" if gt else "depth_latents"
-    out["latents_depth"] = torch.stack([files[(d, v)].permute(1, 0, 2, 3) for v in views]).flatten(0, 1)
-    out["latents_label"] = torch.stack([files[("label_latents", v)].permute(1, 0, 2, 3) for v in views]).flatten(0, 1)
-    return out
+_reference_sample = LO.reference_sample
 
 
 def _reference_collate(items, dtype):
-    # dataset.py:2076-2126
-    ret = {"controls": {}}
-    ret["prompt_embeds"] = torch.stack([x["prompt_embeds"] for x in items]).to(dtype=dtype)
-    ret["latents"] = torch.stack([x["latents"] for x in items]).to(dtype=dtype).permute(0, 2, 1, 3, 4)
-    images = torch.stack([x["image"] for x in items]).to(dtype=dtype)
-    ret["images"] = images.permute(0, 2, 1, 3, 4)
-    for k in ("latents_depth", "latents_label"):
-        ret["controls"][k] = torch.stack([x[k] for x in items]).to(dtype=dtype).permute(0, 2, 1, 3, 4)
+    ret = LO.reference_collate(items, dtype)
+    ret.pop("image_width"), ret.pop("image_height")
     return ret
 
 
@@ -111,6 +93,16 @@ def test_collate_matches_reference(tmp_path):
     assert got.pop("image_width") == 64 and got.pop("image_height") == 48
     _same(got, want)
     assert got["controls"]["latents_depth"].shape == (4, 32, 5, 6, 8)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_collate_matches_the_reference_classes_own_output(dt):
+    """Product collate and oracle restatement, bit for bit against what the reference's CollateFunctionControl returned
+    for the same seeded items (tensor keys + image size)."""
+    want = torch.load(os.path.join(GOLDEN, "collate_control.pt"), weights_only=False)[str(dt).split(".")[-1]]
+    items = LO.golden_items()
+    _same(collate_control(items, dt), want)
+    _same(LO.reference_collate(items, dt), want)
 
 
 def test_condition_cache_prefetch_lru_and_values(tmp_path):
