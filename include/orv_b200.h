@@ -426,6 +426,44 @@ size_t orvb_voxelize_workspace_bytes(int32_t n, int32_t max_voxels);
  * voxelization_kernel.cu:24-129), which is also a valid outcome of its non-deterministic one. */
 int orvb_hard_voxelize(const orvb_voxelize_args* a, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * 3-D Gaussian rasteriser, forward pass (second half; replaces `_C.rasterize_gaussians` of the
+ * reference extension orv/ops/diff-gaussian-rasterization — rasterize_points.cu:35-150, ext.cpp:14-18 — as called by
+ * orv/dataset/gs_render.py:103-171: occupancy voxels rendered as Gaussians into RGB, 12 semantic channels, depth and
+ * alpha).  All pointers are device pointers, fp32; images are [C, H, W]; precomputed colours only (the caller passes
+ * `colors_precomp`, shs=None); backward is out of scope.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct orvb_gs_args {
+  int32_t p;                   /* number of Gaussians                                                            */
+  const float* means3d;        /* [p, 3]                                                                         */
+  const float* colors;         /* [p, 3]   colors_precomp                                                        */
+  const float* features;       /* [p, 12]  language_feature_precomp, 16-byte aligned; NULL = include_feature off  */
+  const float* opacities;      /* [p]                                                                            */
+  const float* scales;         /* [p, 3]   with rotations, or NULL when cov3d is given                           */
+  const float* rotations;      /* [p, 4]   quaternion (r, x, y, z), used as given (the reference does not normalise) */
+  const float* cov3d;          /* [p, 6]   precomputed upper triangle, or NULL                                   */
+  float scale_modifier;
+  const float* viewmatrix;     /* [16] as the reference passes it: world-to-camera, transposed (column-major)     */
+  const float* projmatrix;     /* [16] full projection, same convention                                          */
+  const float* background;     /* [3]                                                                            */
+  float tan_fovx, tan_fovy;
+  int32_t height, width;
+  float* out_color;            /* [3, H, W]                                                                      */
+  float* out_feature;          /* [12, H, W] or NULL                                                             */
+  float* out_depth;            /* [1, H, W]                                                                      */
+  float* out_alpha;            /* [1, H, W]                                                                      */
+  int32_t* radii;              /* [p] screen-space radius, 0 = culled                                            */
+  int32_t* num_rendered;       /* device scalar (may be NULL): number of (Gaussian, tile) instances; NEGATIVE (minus
+                                  the count) when it exceeded max_instances — the excess was dropped, call again with a
+                                  larger capacity                                                                  */
+  int32_t max_instances;       /* capacity of the binning buffers in the workspace                               */
+  void* workspace; size_t workspace_bytes;  /* orvb_gs_workspace_bytes(p, max_instances, height, width), 256-byte aligned */
+} orvb_gs_args;
+size_t orvb_gs_workspace_bytes(int32_t p, int32_t max_instances, int32_t height, int32_t width);
+/* One stream-ordered launch sequence, no host synchronisation (the reference reads the instance count back to size
+ * its buffers, rasterizer_impl.cu:276-281). */
+int orvb_gs_rasterize(const orvb_gs_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,6 +86,56 @@ def voxelization(points, voxel_size, coors_range, max_points: int = 35, max_voxe
     return voxels[:voxel_num], coors[:voxel_num], num_points_per_voxel[:voxel_num]
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# The reference's 3-D Gaussian rasteriser (orv/ops/diff-gaussian-rasterization: Inria's rasteriser plus a 12-channel
+# semantic feature, depth and alpha outputs; the occupancy -> depth / semantic-map renderer of orv/dataset/gs_render.py).
+# CUDA-only, so it is cross-compiled here with nvcc for sm_100a (glm is vendored under third_party/) and can only RUN on
+# the GPU box, where the GPU tests use it as the oracle and tools/bench_gs_render.py as the timed baseline.
+# ----------------------------------------------------------------------------------------------------------------
+GS_SRC = REF_OPS / "diff-gaussian-rasterization"
+GS_OUT = HERE / "_ref" / "diff_gaussian_rasterization"
+GS_NAME = "orv_ref_diff_gaussian_rasterization"
+_gs_mod = None
+
+
+def build_rasterizer(verbose: bool = False):
+    from torch.utils.cpp_extension import load
+    GS_OUT.mkdir(parents=True, exist_ok=True)
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0a")
+    srcs = ["cuda_rasterizer/rasterizer_impl.cu", "cuda_rasterizer/forward.cu", "cuda_rasterizer/backward.cu",
+            "rasterize_points.cu", "ext.cpp"]  # the reference's own source list (setup.py:22-27)
+    return load(GS_NAME, sources=[str(GS_SRC / s) for s in srcs],
+                extra_include_paths=[str(GS_SRC / "third_party" / "glm")],
+                # rasterizer_impl.h uses uint32_t / std::uintptr_t without <cstdint> (fine with the compilers of its day):
+                # pre-include the header instead of touching the reference source
+                extra_cuda_cflags=["-gencode", "arch=compute_100a,code=sm_100a", "--pre-include", "cstdint"],
+                build_directory=str(GS_OUT), verbose=verbose, with_cuda=True)
+
+
+def rasterizer_available() -> bool:
+    return (GS_OUT / f"{GS_NAME}.so").exists()
+
+
+def load_rasterizer():
+    """The reference extension module `_C` (`rasterize_gaussians`, ext.cpp:14-18) — prebuilt file only (GPU box)."""
+    global _gs_mod
+    if _gs_mod is not None:
+        return _gs_mod
+    import torch  # noqa: F401
+    so = GS_OUT / f"{GS_NAME}.so"
+    if not so.exists():
+        raise RuntimeError(f"{so} is missing (python -m oracle.build_ref --rasterizer, in the build container)")
+    spec = importlib.util.spec_from_file_location(GS_NAME, so)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    sys.modules[GS_NAME] = mod
+    _gs_mod = mod
+    return mod
+
+
 if __name__ == "__main__":
-    m = build(verbose="-v" in sys.argv)
+    if "--rasterizer" in sys.argv:
+        m = build_rasterizer(verbose="-v" in sys.argv)
+    else:
+        m = build(verbose="-v" in sys.argv)
     print(m.__file__)

@@ -148,6 +148,19 @@ class VoxelizeArgs(C.Structure):
     ]
 
 
+class GsArgs(C.Structure):
+    _fields_ = [
+        ("p", c_int),
+        ("means3d", c_void_p), ("colors", c_void_p), ("features", c_void_p), ("opacities", c_void_p),
+        ("scales", c_void_p), ("rotations", c_void_p), ("cov3d", c_void_p), ("scale_modifier", c_float),
+        ("viewmatrix", c_void_p), ("projmatrix", c_void_p), ("background", c_void_p),
+        ("tan_fovx", c_float), ("tan_fovy", c_float), ("height", c_int), ("width", c_int),
+        ("out_color", c_void_p), ("out_feature", c_void_p), ("out_depth", c_void_p), ("out_alpha", c_void_p),
+        ("radii", c_void_p), ("num_rendered", c_void_p), ("max_instances", c_int),
+        ("workspace", c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 # Every symbol include/orv_b200.h declares; tests check the .so exports all of them.
 EXPORTED_SYMBOLS = [
     "orvb_version", "orvb_last_error", "orvb_check_device",
@@ -159,6 +172,7 @@ EXPORTED_SYMBOLS = [
     "orvb_modulation_bytes", "orvb_modulation_schedule", "orvb_modulation_select",
     "orvb_sampler_step",
     "orvb_dynamic_voxelize", "orvb_voxelize_workspace_bytes", "orvb_hard_voxelize",
+    "orvb_gs_workspace_bytes", "orvb_gs_rasterize",
 ]
 
 _lib = None
@@ -245,6 +259,11 @@ def load() -> C.CDLL:
         lib.orvb_voxelize_workspace_bytes.restype = C.c_size_t
         lib.orvb_hard_voxelize.argtypes = [C.POINTER(VoxelizeArgs), c_void_p]
         lib.orvb_hard_voxelize.restype = c_int
+    if hasattr(lib, "orvb_gs_rasterize"):
+        lib.orvb_gs_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
+        lib.orvb_gs_workspace_bytes.restype = C.c_size_t
+        lib.orvb_gs_rasterize.argtypes = [C.POINTER(GsArgs), c_void_p]
+        lib.orvb_gs_rasterize.restype = c_int
     _lib = lib
     return lib
 

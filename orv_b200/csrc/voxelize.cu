@@ -24,19 +24,14 @@
 // No atomics decide an output value except atomicMin / atomicCAS whose results are order-independent, so the output
 // is bit-identical run to run and identical to the reference's deterministic path.
 #include "common.cuh"
+#include "sortscan.cuh"
 
 #include <math.h>
 
 namespace orvb {
 namespace {
 
-constexpr int kThreads = 256;
-constexpr unsigned kFull = 0xffffffffu;
 constexpr unsigned long long kEmptyKey = ~0ull;
-constexpr int kItems = 8;                    // elements per thread in the scan / sort tiles
-constexpr int kTile = kThreads * kItems;     // 2048
-constexpr int kRadixBits = 9;                // 17-bit keys (max_voxels = 1e5, the occupancy caller) sort in two passes
-constexpr int kBins = 1 << kRadixBits;       // 512
 
 struct VoxGeom {
   float lo[3];
@@ -127,10 +122,6 @@ __global__ void __launch_bounds__(kThreads) voxel_insert_kernel(const float* __r
 }
 
 // ---- 2. first-of-voxel flags (evaluated inside the scan kernels, never stored) ---------------------------------------
-struct LoadU32 {
-  const uint32_t* in;
-  __device__ __forceinline__ uint32_t operator()(int64_t i) const { return in[i]; }
-};
 struct LoadFirstFlag {  // 1 when point i is the first (lowest-index) point of its voxel
   const int32_t* slot_of;
   const int32_t* t_first;
@@ -139,112 +130,6 @@ struct LoadFirstFlag {  // 1 when point i is the first (lowest-index) point of i
     return (s >= 0 && __ldg(t_first + s) == static_cast<int32_t>(i)) ? 1u : 0u;
   }
 };
-
-// ---- block-wide exclusive scan of one value per thread (256 threads) ------------------------------------------------
-__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t& total) {
-  __shared__ uint32_t warp_sums[kThreads / 32 + 1];
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  uint32_t inc = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t t = __shfl_up_sync(kFull, inc, o);
-    if (lane >= o) inc += t;
-  }
-  if (lane == 31) warp_sums[warp] = inc;
-  __syncthreads();
-  if (warp == 0) {
-    const uint32_t w = (lane < kThreads / 32) ? warp_sums[lane] : 0u;
-    uint32_t winc = w;
-#pragma unroll
-    for (int o = 1; o < kThreads / 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(kFull, winc, o);
-      if (lane >= o) winc += t;
-    }
-    if (lane < kThreads / 32) warp_sums[lane] = winc - w;
-    if (lane == kThreads / 32 - 1) warp_sums[kThreads / 32] = winc;
-  }
-  __syncthreads();
-  const uint32_t res = warp_sums[warp] + inc - v;
-  total = warp_sums[kThreads / 32];
-  __syncthreads();  // warp_sums may be reused by the caller's next scan
-  return res;
-}
-
-// tile sums: sums[b] = sum of in[b*kTile .. (b+1)*kTile)
-template <class Load>
-__global__ void __launch_bounds__(kThreads) scan_reduce_kernel(Load in, int64_t n, uint32_t* __restrict__ sums) {
-  const int64_t base = static_cast<int64_t>(blockIdx.x) * kTile + static_cast<int64_t>(threadIdx.x) * kItems;
-  uint32_t s = 0;
-#pragma unroll
-  for (int k = 0; k < kItems; ++k) {
-    if (base + k < n) s += in(base + k);
-  }
-  uint32_t total;
-  block_exclusive_scan(s, total);
-  if (threadIdx.x == 0) sums[blockIdx.x] = total;
-}
-
-// exclusive scan of one tile (+ offsets[b]); in == out allowed (each thread reads its items before it writes them)
-template <class Load>
-__global__ void __launch_bounds__(kThreads) scan_tile_kernel(Load in, uint32_t* out, int64_t n,
-                                                             const uint32_t* __restrict__ offsets,
-                                                             uint32_t* __restrict__ total_out) {
-  const int64_t base = static_cast<int64_t>(blockIdx.x) * kTile + static_cast<int64_t>(threadIdx.x) * kItems;
-  uint32_t v[kItems];
-  uint32_t s = 0;
-#pragma unroll
-  for (int k = 0; k < kItems; ++k) {
-    v[k] = (base + k < n) ? in(base + k) : 0u;
-    s += v[k];
-  }
-  uint32_t total;
-  uint32_t run = block_exclusive_scan(s, total);
-  if (offsets != nullptr) run += offsets[blockIdx.x];
-#pragma unroll
-  for (int k = 0; k < kItems; ++k) {
-    if (base + k < n) out[base + k] = run;
-    run += v[k];
-  }
-  if (total_out != nullptr && threadIdx.x == 0 && gridDim.x == 1) *total_out = total;
-}
-
-inline int64_t tiles_of(int64_t n) { return (n + kTile - 1) / kTile; }
-inline size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
-
-// scratch (uint32 entries) needed by scan_u32 for n inputs
-size_t scan_scratch_entries(int64_t n) {
-  size_t e = 0;
-  while (n > kTile) {
-    n = tiles_of(n);
-    e += align256(static_cast<size_t>(n) * 4) / 4;
-  }
-  return e + 64;
-}
-
-// exclusive scan of n values produced by `in` (a LoadU32 over `out` itself is allowed: each thread reads its items
-// before it writes them); *total_out (device) = sum of all inputs
-template <class Load>
-int scan_any(Load in, uint32_t* out, int64_t n, uint32_t* scratch, uint32_t* total_out, cudaStream_t st) {
-  const int64_t nb = tiles_of(n);
-  if (nb <= 1) {
-    scan_tile_kernel<Load><<<1, kThreads, 0, st>>>(in, out, n, nullptr, total_out);
-    ORVB_CHECK_CUDA(cudaGetLastError());
-    return ORVB_OK;
-  }
-  scan_reduce_kernel<Load><<<static_cast<unsigned>(nb), kThreads, 0, st>>>(in, n, scratch);
-  ORVB_CHECK_CUDA(cudaGetLastError());
-  uint32_t* next = scratch + align256(static_cast<size_t>(nb) * 4) / 4;
-  const int rc = scan_any(LoadU32{scratch}, scratch, nb, next, total_out, st);
-  if (rc != ORVB_OK) return rc;
-  scan_tile_kernel<Load><<<static_cast<unsigned>(nb), kThreads, 0, st>>>(in, out, n, scratch, nullptr);
-  ORVB_CHECK_CUDA(cudaGetLastError());
-  return ORVB_OK;
-}
-inline int scan_u32(const uint32_t* in, uint32_t* out, int64_t n, uint32_t* scratch, uint32_t* total_out,
-                    cudaStream_t st) {
-  return scan_any(LoadU32{in}, out, n, scratch, total_out, st);
-}
 
 // ---- 3. voxel numbers -> sort keys ------------------------------------------------------------------------------------
 // order[] = exclusive scan of the first-point flags, so order[f] is the voxel number (order of first appearance) of
@@ -267,79 +152,6 @@ __global__ void __launch_bounds__(kThreads) sort_key_kernel(const int32_t* __res
     if (v < cap) k = v;
   }
   key[i] = k;
-}
-
-// ---- 4. stable LSD radix sort, kRadixBits bits per pass ----------------------------------------------------------------
-// hist[d * nblocks + b] = number of keys of tile b whose digit is d (digit-major, so one exclusive scan over the
-// whole array yields the global start of (digit d, tile b)).
-__global__ void __launch_bounds__(kThreads) radix_hist_kernel(const uint32_t* __restrict__ keys, int n, int shift,
-                                                              uint32_t* __restrict__ hist, int nblocks) {
-  __shared__ uint32_t h[kBins];
-  for (int d = threadIdx.x; d < kBins; d += kThreads) h[d] = 0;
-  __syncthreads();
-  const int64_t base = static_cast<int64_t>(blockIdx.x) * kTile;
-#pragma unroll
-  for (int k = 0; k < kItems; ++k) {
-    const int64_t idx = base + k * kThreads + threadIdx.x;
-    if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & (kBins - 1)], 1u);
-  }
-  __syncthreads();
-  for (int d = threadIdx.x; d < kBins; d += kThreads) hist[static_cast<size_t>(d) * nblocks + blockIdx.x] = h[d];
-}
-
-// Scatter of one tile.  Warp w owns the 256 consecutive elements [tile + 256 w, tile + 256 (w+1)) and walks them 32
-// at a time, so (warp, iteration, lane) order = element order: ranks by __match_any_sync peers below the lane keep
-// the sort stable.  vin == nullptr means "value = element index" (first pass).
-__global__ void __launch_bounds__(kThreads) radix_scatter_kernel(const uint32_t* __restrict__ kin,
-                                                                 const uint32_t* __restrict__ vin,
-                                                                 uint32_t* __restrict__ kout, uint32_t* __restrict__ vout,
-                                                                 int n, int shift, const uint32_t* __restrict__ offs,
-                                                                 int nblocks) {
-  __shared__ uint32_t wh[kThreads / 32][kBins];
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  for (int w = 0; w < kThreads / 32; ++w)
-    for (int d = threadIdx.x; d < kBins; d += kThreads) wh[w][d] = 0;
-  __syncthreads();
-  const int64_t wbase = static_cast<int64_t>(blockIdx.x) * kTile + warp * (32 * kItems);
-  // A: per-warp digit histogram
-  for (int it = 0; it < kItems; ++it) {
-    const int64_t idx = wbase + it * 32 + lane;
-    const bool act = idx < n;
-    const uint32_t d = act ? ((kin[idx] >> shift) & (kBins - 1)) : (kBins + lane);  // inactive lanes match nobody
-    const unsigned peers = __match_any_sync(kFull, d);
-    if (act && lane == __ffs(peers) - 1) wh[warp][d] += __popc(peers);
-    __syncwarp();
-  }
-  __syncthreads();
-  // B: per digit, turn the per-warp counts into global start positions
-  for (int d = threadIdx.x; d < kBins; d += kThreads) {
-    uint32_t run = offs[static_cast<size_t>(d) * nblocks + blockIdx.x];
-#pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) {
-      const uint32_t t = wh[w][d];
-      wh[w][d] = run;
-      run += t;
-    }
-  }
-  __syncthreads();
-  // C: stable scatter
-  for (int it = 0; it < kItems; ++it) {
-    const int64_t idx = wbase + it * 32 + lane;
-    const bool act = idx < n;
-    const uint32_t key = act ? kin[idx] : 0u;
-    const uint32_t d = act ? ((key >> shift) & (kBins - 1)) : (kBins + lane);
-    const unsigned peers = __match_any_sync(kFull, d);
-    const uint32_t start = act ? wh[warp][d] : 0u;
-    __syncwarp();  // every lane has read its start before a leader advances it
-    if (act) {
-      const uint32_t dest = start + __popc(peers & ((1u << lane) - 1u));
-      kout[dest] = key;
-      vout[dest] = (vin != nullptr) ? vin[idx] : static_cast<uint32_t>(idx);
-      if (lane == __ffs(peers) - 1) wh[warp][d] = start + __popc(peers);
-    }
-    __syncwarp();
-  }
 }
 
 // ---- 5. segments + gather ----------------------------------------------------------------------------------------------
@@ -626,11 +438,11 @@ extern "C" int orvb_hard_voxelize(const orvb_voxelize_args* a, void* stream) {
   uint32_t* vout = vb;
   for (int pass = 0; pass < w.passes; ++pass) {
     const int shift = kRadixBits * pass;
-    radix_hist_kernel<<<w.nblocks, kThreads, 0, st>>>(kin, n, shift, hist, w.nblocks);
+    radix_hist_kernel<><<<w.nblocks, kThreads, 0, st>>>(kin, n, shift, hist, w.nblocks);
     ORVB_CHECK_CUDA(cudaGetLastError());
     rc = scan_u32(hist, hist, static_cast<int64_t>(kBins) * w.nblocks, scan_scratch, nullptr, st);
     if (rc != ORVB_OK) return rc;
-    radix_scatter_kernel<<<w.nblocks, kThreads, 0, st>>>(kin, vin, kout, vout, n, shift, hist, w.nblocks);
+    radix_scatter_kernel<><<<w.nblocks, kThreads, 0, st>>>(kin, vin, kout, vout, n, shift, hist, w.nblocks);
     ORVB_CHECK_CUDA(cudaGetLastError());
     kin = kout;
     vin = vout;

@@ -19,14 +19,34 @@ def main():
     for i in range(3):
         run(40 + i)
     torch.cuda.synchronize()
+    import time
     from torch.autograd import DeviceType
     from torch.profiler import ProfilerActivity, profile
-    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    # host view of one clip without a profiler: enqueue time of the call, then the wait for the GPU to drain
+    for rep in range(2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        run(200 + rep)
+        t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        print(f"clip {rep}: pipe() returned after {1e3 * (t1 - t0):.1f} ms (host), GPU drained {1e3 * (t2 - t1):.1f} ms later, "
+              f"total {1e3 * (t2 - t0):.1f} ms")
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         run(300)
         torch.cuda.synchronize()
     evs = sorted((e.time_range.start, e.time_range.end, e.name) for e in prof.events() if e.device_type == DeviceType.CUDA)
     samp = [i for i, e in enumerate(evs) if "sampler_step_kernel" in e[2]]
     print(f"{len(evs)} device activities, {len(samp)} sampler steps")
+    first_fwd = next(i for i, e in enumerate(evs) if "patchify_kernel" in e[2])
+    print(f"clip prologue on the device: first activity -> first forward kernel {evs[first_fwd][0] - evs[0][0]:.0f} us "
+          f"({first_fwd} activities, busy {sum(e - s for s, e, _ in evs[:first_fwd]):.0f} us); denoise loop "
+          f"{evs[samp[-1]][1] - evs[first_fwd][0]:.0f} us; after the last sampler step {evs[-1][1] - evs[samp[-1]][1]:.0f} us")
+    cpu = sorted(((e.time_range.end - e.time_range.start, e.name) for e in prof.events()
+                  if e.device_type == DeviceType.CPU and e.time_range.end - e.time_range.start > 200), reverse=True)[:14]
+    print("longest host-side ops of the clip (us):")
+    for d, n in cpu:
+        print(f"  {d:9.0f}  {n[:80]}")
     busy = sum(e - s for s, e, _ in evs)
     span = evs[-1][1] - evs[0][0]
     print(f"span {span / 1e3:.2f} ms, sum of activity durations {busy / 1e3:.2f} ms")
