@@ -316,6 +316,22 @@ OUR_KERNELS = ("gemm2_bf16_kernel", "gemm_bf16_kernel", "gemm2_chain_kernel", "a
                "mv_gather_kernel", "fill_tables_kernel", "sampler_step_kernel")
 
 
+def ncu_traffic(cls: str):
+    """DRAM bytes per launch of a kernel class from the COMMITTED ncu capture (profiles/traffic.json, written by
+    tools/summarize_profiles.py) — context for `roofline.traffic`, which stays null because it cannot be measured in a
+    timed run."""
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    key = {"attention": "attention_kernel", "gemm_qkv": "gemm2_bf16_kernel<3>", "gemm_ff1": "gemm2_bf16_kernel<1>",
+           "gemm_ff2": "gemm2_bf16_kernel<2>", "gemm_out": "gemm2_bf16_kernel<2>"}.get(cls)
+    if not key or not os.path.exists(tp):
+        return None
+    for kname, ent in json.load(open(tp)).items():
+        if key in kname and ent:
+            return {"dram_bytes_per_launch": ent[0]["dram_bytes"], "us_under_ncu": ent[0]["us"], "source": ent[0]["source"],
+                    "note": "config-2 capture, serialised and cold-cache"}
+    return None
+
+
 def class_flops(model_cfg: dict, B: int, S: int, views: int, St: int, tok: int, frames_lat: int) -> dict:
     """Algorithmic FLOP per LAUNCH of the tensor-core classes (2 M N K; attention 4 S^2 D, no causal discount).
     With multiview the classes average over the temporal block's and the view block's launches."""
@@ -539,7 +555,7 @@ def run_ours(args):
                     "unit": "TFLOP/s", "frac": round(kernels[dom]["tflops"] / pk["bf16"], 4),
                     # DRAM bytes need an ncu replay and cannot be measured inside a timed run: null here; the committed
                     # capture of this kernel is profiles/r02*_attn_raw.csv (dram__bytes_read.sum + dram__bytes_write.sum)
-                    "traffic": None,
+                    "traffic": None, "traffic_ncu": ncu_traffic(dom),
                     "algorithmic_flop_per_launch": flops[dom],
                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['source']})",
                     "forward_ms_sum_of_kernels": pinfo["forward_ms_sum_of_kernels"],
