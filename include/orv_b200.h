@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ORVB_VERSION 101
+#define ORVB_VERSION 102
 
 enum {
   ORVB_OK = 0,
@@ -463,6 +463,72 @@ size_t orvb_gs_workspace_bytes(int32_t p, int32_t max_instances, int32_t height,
 /* One stream-ordered launch sequence, no host synchronisation (the reference reads the instance count back to size
  * its buffers, rasterizer_impl.cu:276-281). */
 int orvb_gs_rasterize(const orvb_gs_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 3-D VAE decode: the operators behind `AutoencoderKLCogVideoX.decode` (diffusers, called by the
+ * reference pipeline at orv/models/cogvideox_control.py:1095-1100 and :1476-1479, tiled + sliced by
+ * orv/pipeline/inference_control_to_video.py:98-99).  Activations are CHANNELS-LAST bf16 [T, H, W, C] for one sample
+ * (the reference decodes one sample at a time: slicing); the frame-batch / tile / cache orchestration is host code
+ * (orv_b200/models/autoencoder_kl_cogvideox.py).
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* Causal convolution as an implicit GEMM on tcgen05 (CogVideoXCausalConv3d with pad_mode "constant"; kt = 1 gives
+ * the per-frame Conv2d of CogVideoXUpsample3D and the 1x1x1 shortcut / spatial-norm convolutions):
+ *   out[t,h,w,n] = bias[n] + sum_{kt,kh,kw,c} X[t+kt-(KT-1), h+kh-KH/2, w+kw-KW/2, c] * W[n, ((kt*KH+kh)*KW+kw)*c_in + c]
+ *                  (+ resid[t,h,w,n])
+ * Spatial borders are zero padded; frames in front of the first one come from `cache` (the last KT-1 input frames of
+ * the previous frame batch, [KT-1, H, W, c_in]) or, when cache is NULL, repeat frame 0. */
+typedef struct orvb_conv_args {
+  const void* x;      /* bf16 [frames, height, width, c_in]                                   */
+  const void* cache;  /* bf16 [kt-1, height, width, c_in] or NULL                             */
+  const void* w;      /* bf16 [c_out, kt*kh*kw*c_in], tap-major then channel (K-major rows)   */
+  const void* bias;   /* bf16 [c_out] or NULL                                                 */
+  const void* resid;  /* bf16 [frames, height, width, c_out] or NULL; may alias out           */
+  void* out;          /* bf16 [frames, height, width, c_out] (fp32 when out_f32)              */
+  int32_t frames, height, width;
+  int32_t c_in;       /* multiple of 64 (zero-pad the channels)                               */
+  int32_t c_out;      /* multiple of 8                                                        */
+  int32_t kt, kh, kw; /* kt in 1..4; kh, kw odd, <= 7                                         */
+  int32_t out_f32;    /* tight-tolerance test mode (see orvb_gemm_args.out_f32)               */
+} orvb_conv_args;
+int orvb_conv_cl(const orvb_conv_args* args, void* stream);
+
+/* GroupNorm statistics of a channels-last tensor over ALL its pixels (one sample): stats[g] = (mean, rstd) fp32 for
+ * the `groups` groups of channels/groups consecutive channels.  Deterministic: fixed-size pixel chunks are summed in
+ * fp32, the chunk partials in fp64 in chunk order by the last block to finish.  `scratch` holds
+ * orvb_gn_scratch_bytes(pixels, groups) bytes; its first 4 bytes must be zero before the first call (the kernel
+ * leaves them zero). */
+size_t orvb_gn_scratch_bytes(int64_t pixels, int32_t groups);
+int orvb_gn_stats_cl(const void* x, int64_t pixels, int32_t channels, int32_t groups, float eps, float* stats,
+                     void* scratch, void* stream);
+
+/* CogVideoXSpatialNorm3D + SiLU, fused:  y = act( GroupNorm(x; stats, gamma, beta) * Y[src] + B[src] )  where Y / B are
+ * the 1x1x1 convolutions conv_y / conv_b of the latent `zq`, evaluated ONCE per latent pixel into `table` (a GEMM over
+ * the latent pixels) and looked up through the nearest-neighbour map of F.interpolate:
+ *   src(t,h,w) = (t_src[t] * lat_h + (h >> shift)) * lat_w + (w >> shift)
+ * (every spatial upsampling of the decoder is an exact factor 2; the temporal map — first frame kept single for odd
+ * frame counts — comes from the host as t_src). */
+typedef struct orvb_spatial_norm_args {
+  const void* x; void* y;          /* bf16 [frames, height, width, channels]; y fp32 when y_f32          */
+  int32_t frames, height, width, channels, groups;
+  const float* stats;              /* [groups, 2] from orvb_gn_stats_cl                                 */
+  const void* gamma; const void* beta; /* bf16 [channels]                                               */
+  const void* table;               /* bf16 [lat_frames*lat_h*lat_w, table_ld]                           */
+  int32_t table_ld, y_off, b_off;  /* column of conv_y / conv_b channel 0 (multiples of 8)              */
+  const int32_t* t_src;            /* DEVICE [frames] latent frame of every frame                       */
+  int32_t lat_h, lat_w, shift;
+  int32_t act;                     /* 0 none, 1 SiLU                                                    */
+  int32_t y_f32;
+} orvb_spatial_norm_args;
+int orvb_spatial_norm_cl(const orvb_spatial_norm_args* args, void* stream);
+
+/* Nearest-neighbour x2 spatial upsampling with a temporal source map (CogVideoXUpsample3D before its convolution):
+ * out[t, h, w, :] = x[t_src[t], h >> 1, w >> 1, :];  x [frames_in, height, width, c], out [frames_out, 2h, 2w, c]. */
+int orvb_upsample2x_cl(const void* x, void* out, int32_t frames_out, int32_t height, int32_t width, int32_t channels,
+                       const int32_t* t_src, void* stream);
+/* Channels-last -> planar: out[c, t, h, w] = x[t, h, w, c] for c < c_keep (x has c_ld channels per pixel). */
+int orvb_cl_to_planar(const void* x, void* out, int64_t pixels, int32_t c_ld, int32_t c_keep, void* stream);
+
 
 #ifdef __cplusplus
 }

@@ -162,6 +162,24 @@ class GsArgs(C.Structure):
 
 
 # Every symbol include/orv_b200.h declares; tests check the .so exports all of them.
+class ConvArgs(C.Structure):
+    _fields_ = [
+        ("x", c_void_p), ("cache", c_void_p), ("w", c_void_p), ("bias", c_void_p), ("resid", c_void_p), ("out", c_void_p),
+        ("frames", c_int), ("height", c_int), ("width", c_int), ("c_in", c_int), ("c_out", c_int),
+        ("kt", c_int), ("kh", c_int), ("kw", c_int), ("out_f32", c_int),
+    ]
+
+
+class SpatialNormArgs(C.Structure):
+    _fields_ = [
+        ("x", c_void_p), ("y", c_void_p),
+        ("frames", c_int), ("height", c_int), ("width", c_int), ("channels", c_int), ("groups", c_int),
+        ("stats", c_void_p), ("gamma", c_void_p), ("beta", c_void_p), ("table", c_void_p),
+        ("table_ld", c_int), ("y_off", c_int), ("b_off", c_int),
+        ("t_src", c_void_p), ("lat_h", c_int), ("lat_w", c_int), ("shift", c_int), ("act", c_int), ("y_f32", c_int),
+    ]
+
+
 EXPORTED_SYMBOLS = [
     "orvb_version", "orvb_last_error", "orvb_check_device",
     "orvb_gemm_bf16", "orvb_gemm_bf16_bn", "orvb_gemm_tile_width", "orvb_attention_bf16", "orvb_attention", "orvb_attention_set_rescale_threshold",
@@ -173,6 +191,8 @@ EXPORTED_SYMBOLS = [
     "orvb_sampler_step",
     "orvb_dynamic_voxelize", "orvb_voxelize_workspace_bytes", "orvb_hard_voxelize",
     "orvb_gs_workspace_bytes", "orvb_gs_rasterize",
+    "orvb_conv_cl", "orvb_gn_scratch_bytes", "orvb_gn_stats_cl", "orvb_spatial_norm_cl", "orvb_upsample2x_cl",
+    "orvb_cl_to_planar",
 ]
 
 _lib = None
@@ -264,6 +284,19 @@ def load() -> C.CDLL:
         lib.orvb_gs_workspace_bytes.restype = C.c_size_t
         lib.orvb_gs_rasterize.argtypes = [C.POINTER(GsArgs), c_void_p]
         lib.orvb_gs_rasterize.restype = c_int
+    if hasattr(lib, "orvb_conv_cl"):
+        lib.orvb_conv_cl.argtypes = [C.POINTER(ConvArgs), c_void_p]
+        lib.orvb_conv_cl.restype = c_int
+        lib.orvb_gn_scratch_bytes.argtypes = [C.c_int64, c_int]
+        lib.orvb_gn_scratch_bytes.restype = C.c_size_t
+        lib.orvb_gn_stats_cl.argtypes = [c_void_p, C.c_int64, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]
+        lib.orvb_gn_stats_cl.restype = c_int
+        lib.orvb_spatial_norm_cl.argtypes = [C.POINTER(SpatialNormArgs), c_void_p]
+        lib.orvb_spatial_norm_cl.restype = c_int
+        lib.orvb_upsample2x_cl.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
+        lib.orvb_upsample2x_cl.restype = c_int
+        lib.orvb_cl_to_planar.argtypes = [c_void_p, c_void_p, C.c_int64, c_int, c_int, c_void_p]
+        lib.orvb_cl_to_planar.restype = c_int
     _lib = lib
     return lib
 

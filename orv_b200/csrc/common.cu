@@ -74,6 +74,25 @@ int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t batch, uint64
   return ORVB_OK;
 }
 
+int make_tmap_4d_bf16(CUtensorMap* out, const void* base, uint64_t c, uint64_t w, uint64_t h, uint64_t t, uint32_t box_w,
+                      uint32_t box_h) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return ORVB_ECUDA;
+  ORVB_REQUIRE(c % 8 == 0 && reinterpret_cast<uintptr_t>(base) % 16 == 0, ORVB_ESHAPE,
+               "tensor map: channels must be a multiple of 8 and the base 16-byte aligned");
+  ORVB_REQUIRE(box_w >= 1 && box_h >= 1 && box_w * box_h <= 256, ORVB_ESHAPE, "tensor map: bad 4-D box");
+  cuuint64_t gdim[4] = {c, w, h, t};
+  cuuint64_t gstride[3] = {c * 2, w * c * 2, h * w * c * 2};
+  cuuint32_t box[4] = {64, box_w, box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ORVB_REQUIRE(r == CUDA_SUCCESS, ORVB_ECUDA, "cuTensorMapEncodeTiled(4d c=%llu w=%llu h=%llu t=%llu) failed: %d",
+               (unsigned long long)c, (unsigned long long)w, (unsigned long long)h, (unsigned long long)t, (int)r);
+  return ORVB_OK;
+}
+
 static int g_cc_major = -1;
 static int g_sms = 0;
 

@@ -46,6 +46,10 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t batch, uint64_t rows, uint64_t cols,
                       uint64_t ld_row, uint64_t ld_batch, uint32_t box_rows, uint32_t box_cols);
 
+// 4-D variant for channels-last activations [T, H, W, C] (C contiguous): dims (C, W, H, T), box {64, box_w, box_h, 1}.
+int make_tmap_4d_bf16(CUtensorMap* out, const void* base, uint64_t c, uint64_t w, uint64_t h, uint64_t t, uint32_t box_w,
+                      uint32_t box_h);
+
 // Kernel launch with optional programmatic dependent launch (see ptx.cuh pdl_wait): ORVB_PDL=0 disables it.
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>

@@ -1,0 +1,335 @@
+// Causal 3-D (and per-frame 2-D) convolution over channels-last bf16 activations as an IMPLICIT GEMM on the CTA-pair
+// tcgen05 mainloop of gemm.cu — the contraction of the 3-D VAE decoder (diffusers
+// AutoencoderKLCogVideoX.decode, called by the reference at orv/models/cogvideox_control.py:1095-1100, :1476-1479).
+//
+//   out[t, h, w, n] = bias[n] + sum_{kt, kh, kw, c} x[t + kt - (KT-1), h + kh - KH/2, w + kw - KW/2, c] * W[n, (kt, kh, kw, c)]
+//
+// GEMM view: M = output pixels, N = C_out, K = taps * C_in.  An M tile of 128 rows is an 8 x 16 PATCH of one frame, so
+// the A operand of one (tap, 64-channel) K step is ONE 4-D TMA box {64 c, 16 w, 8 h, 1 t} of the activation tensor at
+// the tap's offset: out-of-bounds pixels are zero-filled by the TMA unit (= the convolution's spatial zero padding),
+// the box lands in shared memory as 128 rows of 128 bytes, 128B-swizzled — exactly the K-major tile tcgen05 consumes.
+// No im2col buffer exists anywhere.  Temporal padding is causal (CogVideoXCausalConv3d, pad_mode "constant"): a tap
+// that reaches in front of the first frame reads the convolution cache (the last KT-1 input frames of the previous frame
+// batch, a second tensor map) or, without a cache, the first frame again.
+// Everything else — 6-stage ring, cta_group::2 MMAs of M = 256 (two patches per cluster), two TMEM accumulators, eight
+// epilogue warps, swizzled staging + TMA store (a {64, 16, 2, 1} box per warp and 64-column unit, clipped at the image
+// border) — is the GEMM kernel's structure (gemm.cu); the fused epilogues are the shared ones (bias, bias + residual).
+#include "common.cuh"
+#include "gemm_common.cuh"
+#include "ptx.cuh"
+
+namespace orvb {
+
+int gemm_pick_bn_pair(int m, int n, int epi);
+
+struct ConvDev {
+  int T, H, W, HB, WB;     // frames, image size, patch grid (HB = ceil(H/8), WB = ceil(W/16))
+  int KT, KH, KW, kc;      // kernel taps, K steps per tap (C_in / 64)
+  int num_patches;         // T * HB * WB
+  int has_cache;
+};
+
+constexpr int CV_PH = 8, CV_PW = 16;  // patch = 8 rows x 16 columns = 128 pixels = one M tile
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2_threads(EPI), 1)
+conv2_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_c,
+                  const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_o, const GemmDev p,
+                  const ConvDev cv, const int bn) {
+  constexpr int STAGES = G2_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* out_stage = smem + STAGES * G2_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + G2_OUT_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;  // num_m_tiles counts patch PAIRS
+  const int num_k = cv.KT * cv.KH * cv.KW * cv.kc;
+  const int half_bn = bn >> 1;
+
+  pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_x);
+    tma_prefetch_desc(&tma_b);
+    if (cv.has_cache) tma_prefetch_desc(&tma_c);
+    if (p.tma_store) tma_prefetch_desc(&tma_o);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 2 * g2_epi_warps(EPI));
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(tmem_slot, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  // patch of this CTA inside tile `m_blk`: (frame, patch row, patch column); past the end -> every load is out of
+  // bounds (zeros, but the byte count the barrier expects still arrives) and nothing is stored
+  auto patch_of = [&](int m_blk, int& t, int& h0, int& w0) -> bool {
+    const int patch = 2 * m_blk + static_cast<int>(rank);
+    const int pp = patch < cv.num_patches ? patch : 0;
+    t = pp / (cv.HB * cv.WB);
+    const int r = pp - t * (cv.HB * cv.WB);
+    h0 = (r / cv.WB) * CV_PH;
+    w0 = (r % cv.WB) * CV_PW;
+    return patch < cv.num_patches;
+  };
+
+  if (warp == 0) {
+    // ================================ TMA producer (both CTAs) ================================
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t stage_tx = 2u * static_cast<uint32_t>(G2_A_BYTES + half_bn * BK * 2);
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m_blk = tile % p.num_m_tiles;
+      const int n_blk = tile / p.num_m_tiles;
+      int t, h0, w0;
+      const bool live = patch_of(m_blk, t, h0, w0);
+      const int b_row = n_blk * bn + static_cast<int>(rank) * half_bn;
+      int tap = 0, cc = 0;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * G2_STAGE_BYTES;
+        uint8_t* sb = sa + G2_A_BYTES;
+        const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+        const int kt_i = tap / (cv.KH * cv.KW);
+        const int rem = tap - kt_i * (cv.KH * cv.KW);
+        const int kh_i = rem / cv.KW, kw_i = rem - kh_i * cv.KW;
+        int ts = t + kt_i - (cv.KT - 1);
+        const CUtensorMap* mp = &tma_x;
+        if (ts < 0) {
+          if (cv.has_cache) {
+            mp = &tma_c;
+            ts += cv.KT - 1;
+          } else {
+            ts = 0;
+          }
+        }
+        if (!live) ts = cv.T + cv.KT;  // out of bounds in either map: zero fill
+        if (elect_one()) {
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], stage_tx);
+          tma_load_4d_pair(sa, mp, leader_full, cc * BK, w0 + kw_i - (cv.KW >> 1), h0 + kh_i - (cv.KH >> 1), ts);
+          tma_load_2d_pair(sb, &tma_b, leader_full, kb * BK, b_row);
+        }
+        __syncwarp();
+        if (++cc == cv.kc) {
+          cc = 0;
+          ++tap;
+        }
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && rank == 0) {
+    // ================================ MMA issuer (leader CTA) ================================
+    const uint32_t idesc = umma_idesc_bf16(256, bn, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * G2_ACC_COLS);
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * G2_STAGE_BYTES);
+        const uint64_t a_desc = umma_desc_sw128(sa);
+        const uint64_t b_desc = umma_desc_sw128(sa + G2_A_BYTES);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_f16_ss_pair(d_tmem, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc,
+                             static_cast<uint32_t>((kb | k) != 0));
+          }
+          tc_commit_pair(&empty_bar[stage], 3);
+          if (kb == num_k - 1) tc_commit_pair(&tfull_bar[acc], 3);
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue (both CTAs) ====================================
+    constexpr int EW = g2_epi_warps(EPI);
+    constexpr int NBUF = 8 / EW;
+    const int ew = (warp - 4) & 3;         // TMEM lane quarter = patch rows 2 ew, 2 ew + 1
+    const int unit_par = (warp - 4) >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t stores = 0;
+    uint8_t* my_stage = out_stage + (warp - 4) * (NBUF * 32 * 128);
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m_blk = tile % p.num_m_tiles;
+      const int n_blk = tile / p.num_m_tiles;
+      int t, h0, w0;
+      const bool live = patch_of(m_blk, t, h0, w0);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int hh = h0 + 2 * ew + (lane >> 4), ww = w0 + (lane & 15);
+      const bool pix_ok = live && hh < cv.H && ww < cv.W;
+      const int row = pix_ok ? (t * cv.H + hh) * cv.W + ww : p.M;          // linear pixel index (row of out / resid)
+      const bool warp_ok = live && (h0 + 2 * ew) < cv.H;                    // warp-uniform: any row of mine inside?
+      const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * G2_ACC_COLS) + (static_cast<uint32_t>(ew * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < bn; c += 64) {
+        const int n0 = n_blk * bn + c;
+        if (n0 >= p.N || !warp_ok) break;  // warp-uniform
+        if (EW == 8 && ((c >> 6) & 1) != unit_par) continue;
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c), r0);
+        tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c + 32), r1);
+        tmem_ld_wait();
+        const bool staged = p.tma_store && (bn - c >= 64);
+        uint8_t* sbuf = my_stage + (stores % NBUF) * (32 * 128);
+        if (staged && stores >= NBUF) {
+          if (lane == 0) bulk_wait_group_read<NBUF - 1>();
+          __syncwarp();
+        }
+        if (row < p.M || staged) {  // (staged: rows outside the image still fill their slot; the store clips them)
+          float v[64];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] = __uint_as_float(r0[j]);
+            v[32 + j] = __uint_as_float(r1[j]);
+          }
+          int ncols = bn - c;
+          if (ncols > 64) ncols = 64;
+          if (p.N - n0 < ncols) ncols = p.N - n0;
+          if (row < p.M) {
+            epilogue_unit<EPI>(p, v, row, n0, ncols, staged ? sbuf + lane * 128 : nullptr, lane & 7);
+          }
+        }
+        if (staged) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&tma_o, sbuf, n0, w0, h0 + 2 * ew, t);
+            bulk_commit_group();
+          }
+          ++stores;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  if (warp >= 4 && lane == 0) bulk_wait_group<0>();
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+template <int EPI>
+static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tc, const CUtensorMap& tb, const CUtensorMap& to,
+                       const GemmDev& p, const ConvDev& cv, int bn, cudaStream_t stream) {
+  static bool attr_set = false;
+  auto kern = conv2_bf16_kernel<EPI>;
+  if (!attr_set) {
+    ORVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int clusters = sm_count() / 2;
+  const int grid = 2 * (tiles < clusters ? tiles : clusters);
+  ORVB_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(g2_threads(EPI)), G2_SMEM_BYTES, stream, true, tx, tc, tb, to, p, cv, bn));
+  return ORVB_OK;
+}
+
+}  // namespace orvb
+
+extern "C" int orvb_conv_cl(const orvb_conv_args* a, void* stream) {
+  using namespace orvb;
+  int rc = check_arch();
+  if (rc != ORVB_OK) return rc;
+  ORVB_REQUIRE(a != nullptr && a->x && a->w && a->out, ORVB_EINVAL, "orvb_conv_cl: null pointer");
+  ORVB_REQUIRE(a->frames > 0 && a->height > 0 && a->width > 0, ORVB_ESHAPE, "orvb_conv_cl: empty activation tensor");
+  ORVB_REQUIRE(a->c_in > 0 && a->c_in % 64 == 0, ORVB_ESHAPE,
+               "orvb_conv_cl: c_in (%d) must be a multiple of 64 (pad the channels with zeros)", a->c_in);
+  ORVB_REQUIRE(a->c_out > 0 && a->c_out % 8 == 0, ORVB_ESHAPE, "orvb_conv_cl: c_out (%d) must be a multiple of 8", a->c_out);
+  ORVB_REQUIRE(a->kt >= 1 && a->kt <= 4 && a->kh >= 1 && a->kw >= 1 && (a->kh & 1) && (a->kw & 1) && a->kh <= 7 && a->kw <= 7,
+               ORVB_ESHAPE, "orvb_conv_cl: kernel %dx%dx%d not supported (odd spatial extents <= 7, kt <= 4)", a->kt, a->kh, a->kw);
+  ORVB_REQUIRE(a->cache == nullptr || a->kt > 1, ORVB_EINVAL, "orvb_conv_cl: a cache needs a temporal kernel extent > 1");
+  const long long pixels = static_cast<long long>(a->frames) * a->height * a->width;
+  ORVB_REQUIRE(pixels < (1ll << 30), ORVB_ESHAPE, "orvb_conv_cl: too many pixels");
+  const int K = a->kt * a->kh * a->kw * a->c_in;
+  ConvDev cv;
+  cv.T = a->frames; cv.H = a->height; cv.W = a->width;
+  cv.HB = (a->height + CV_PH - 1) / CV_PH; cv.WB = (a->width + CV_PW - 1) / CV_PW;
+  cv.KT = a->kt; cv.KH = a->kh; cv.KW = a->kw; cv.kc = a->c_in / 64;
+  cv.num_patches = cv.T * cv.HB * cv.WB;
+  cv.has_cache = a->cache != nullptr ? 1 : 0;
+  const int epi = a->resid != nullptr ? ORVB_EPI_GATE_RESID : ORVB_EPI_BIAS;
+  const int num_m_tiles = (cv.num_patches + 1) / 2;
+  const int bn = gemm_pick_bn_pair(num_m_tiles * 256, a->c_out, epi);
+  CUtensorMap tx, tc, tb, to;
+  rc = make_tmap_4d_bf16(&tx, a->x, a->c_in, a->width, a->height, a->frames, CV_PW, CV_PH);
+  if (rc != ORVB_OK) return rc;
+  if (cv.has_cache) {
+    rc = make_tmap_4d_bf16(&tc, a->cache, a->c_in, a->width, a->height, a->kt - 1, CV_PW, CV_PH);
+    if (rc != ORVB_OK) return rc;
+  } else {
+    tc = tx;
+  }
+  rc = make_tmap_2d_bf16(&tb, a->w, a->c_out, K, K, bn / 2, BK);
+  if (rc != ORVB_OK) return rc;
+  const bool tma_store = !a->out_f32;
+  if (tma_store) {
+    rc = make_tmap_4d_bf16(&to, a->out, a->c_out, a->width, a->height, a->frames, CV_PW, 2);
+    if (rc != ORVB_OK) return rc;
+  } else {
+    to = tx;
+  }
+  GemmDev d;
+  memset(&d, 0, sizeof(d));
+  d.M = static_cast<int>(pixels); d.N = a->c_out; d.K = K;
+  d.out = static_cast<bf16*>(a->out); d.ldo = a->c_out;
+  d.bias = static_cast<const bf16*>(a->bias);
+  d.resid = static_cast<const bf16*>(a->resid); d.ldr = a->c_out;
+  d.num_m_tiles = num_m_tiles;
+  d.num_n_tiles = (a->c_out + bn - 1) / bn;
+  d.tma_store = tma_store ? 1 : 0;
+  d.out_f32 = a->out_f32 ? 1 : 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (epi == ORVB_EPI_GATE_RESID) return launch_conv<ORVB_EPI_GATE_RESID>(tx, tc, tb, to, d, cv, bn, st);
+  return launch_conv<ORVB_EPI_BIAS>(tx, tc, tb, to, d, cv, bn, st);
+}

@@ -183,12 +183,31 @@ class CogVideoXImageToVideoPipelineTraj:
         return cos, sin
 
     def decode_latents(self, latents: torch.Tensor) -> torch.Tensor:
+        """diffusers CogVideoXImageToVideoPipeline.decode_latents (called at reference :1478): [B, F, C, h, w] latents ->
+        [B, 3, 4(F-1)+1, 8h, 8w] frames through `vae.decode` — `orv_b200.AutoencoderKLCogVideoX` runs it on the B200
+        kernels; a config-only stand-in has no decoder and raises."""
         if self.vae is None or not hasattr(self.vae, "decode"):
-            raise RuntimeError("no VAE decoder attached: call the pipeline with output_type='latent' "
-                               "(3-D VAE decode is outside the hot path, SURVEY §8f rank 2)")
+            raise RuntimeError("no VAE decoder attached: pass vae=orv_b200.AutoencoderKLCogVideoX(...) to the pipeline "
+                               "or call it with output_type='latent'")
         latents = latents.permute(0, 2, 1, 3, 4)
         latents = 1 / self.vae_scaling_factor_image * latents
         return self.vae.decode(latents).sample
+
+    @staticmethod
+    def postprocess_video(video: torch.Tensor, output_type: str = "pil"):
+        """diffusers VideoProcessor.postprocess_video (called at reference :1479): [B, C, T, H, W] in [-1, 1] ->
+        'pt' [B, T, C, H, W] in [0, 1]; 'np' float32 [B, T, H, W, C]; 'pil' list (batch) of lists (frames) of images."""
+        if output_type not in ("pt", "np", "pil"):
+            raise ValueError(f"{output_type} does not exist. Please choose one of ['np', 'pt', 'pil']")
+        frames = (video.permute(0, 2, 1, 3, 4) / 2 + 0.5).clamp(0, 1)
+        if output_type == "pt":
+            return frames
+        arr = frames.cpu().permute(0, 1, 3, 4, 2).float().numpy()
+        if output_type == "np":
+            return arr
+        from PIL import Image
+        u8 = (arr * 255).round().astype("uint8")
+        return [[Image.fromarray(f) for f in clip] for clip in u8]
 
     # ---- reference :1115-1225 ---------------------------------------------------------------------------
     def prepare_latents(self, image: torch.Tensor, batch_size: int = 1, num_channels_latents: int = 16,
@@ -476,6 +495,7 @@ class CogVideoXImageToVideoPipelineTraj:
                                   *latents.shape[2:])
         if not output_type == "latent":
             video = self.decode_latents(latents)
+            video = self.postprocess_video(video, output_type)
         else:
             video = latents
         self.maybe_free_model_hooks()

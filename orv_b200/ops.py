@@ -159,3 +159,117 @@ def unpatchify(y: torch.Tensor, B: int, F: int, Cc: int, H: int, W: int, p: int,
     L.check(L.load().orvb_unpatchify(y.data_ptr(), out.data_ptr(), B, F, Cc, H, W, p, patch_t, L.current_stream()),
             "orvb_unpatchify")
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 3-D VAE decode operators (channels-last bf16 [T, H, W, C], one sample) — include/orv_b200.h, "3-D VAE decode"
+# ---------------------------------------------------------------------------------------------------------------
+def conv_cl(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], kernel, *, cache: Optional[torch.Tensor] = None,
+            resid: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out_f32: bool = False) -> torch.Tensor:
+    """Causal convolution (implicit GEMM).  x [T, H, W, c_in] bf16, w [c_out, kt*kh*kw*c_in] bf16 (tap-major),
+    kernel = (kt, kh, kw); cache [kt-1, H, W, c_in] = the frames in front of x (None: frame 0 repeated)."""
+    _req(x, torch.bfloat16, "x")
+    _req(w, torch.bfloat16, "w")
+    T, H, W, cin = x.shape
+    kt, kh, kw = kernel
+    cout = w.shape[0]
+    if w.shape[1] != kt * kh * kw * cin:
+        raise RuntimeError(f"conv_cl: weight [{tuple(w.shape)}] does not match {kt}x{kh}x{kw}x{cin}")
+    odt = torch.float32 if out_f32 else torch.bfloat16
+    if out is None:
+        out = torch.empty((T, H, W, cout), dtype=odt, device=x.device)
+    _req(out, odt, "out")
+    a = L.ConvArgs()
+    a.x, a.w, a.out = x.data_ptr(), w.data_ptr(), out.data_ptr()
+    if cache is not None:
+        _req(cache, torch.bfloat16, "cache")
+        if tuple(cache.shape) != (kt - 1, H, W, cin):
+            raise RuntimeError(f"conv_cl: cache {tuple(cache.shape)} must be {(kt - 1, H, W, cin)}")
+        a.cache = cache.data_ptr()
+    if bias is not None:
+        _req(bias, torch.bfloat16, "bias")
+        a.bias = bias.data_ptr()
+    if resid is not None:
+        _req(resid, torch.bfloat16, "resid")
+        a.resid = resid.data_ptr()
+    a.frames, a.height, a.width, a.c_in, a.c_out = T, H, W, cin, cout
+    a.kt, a.kh, a.kw = kt, kh, kw
+    a.out_f32 = int(out_f32)
+    L.check(L.load().orvb_conv_cl(C.byref(a), L.current_stream()), "orvb_conv_cl")
+    return out
+
+
+_gn_scratch: dict = {}
+
+
+def _gn_scratch_for(device, nbytes: int) -> torch.Tensor:
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    buf = _gn_scratch.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _gn_scratch[key] = buf
+    return buf
+
+
+def gn_stats_cl(x: torch.Tensor, groups: int, eps: float) -> torch.Tensor:
+    """(mean, rstd) fp32 [groups, 2] of a channels-last bf16 tensor [..., C] over all its pixels."""
+    _req(x, torch.bfloat16, "x")
+    Cc = x.shape[-1]
+    pixels = x.numel() // Cc
+    lib = L.load()
+    scratch = _gn_scratch_for(x.device, lib.orvb_gn_scratch_bytes(pixels, groups))
+    stats = torch.empty((groups, 2), dtype=torch.float32, device=x.device)
+    L.check(lib.orvb_gn_stats_cl(x.data_ptr(), pixels, Cc, groups, eps, stats.data_ptr(), scratch.data_ptr(),
+                                 L.current_stream()), "orvb_gn_stats_cl")
+    return stats
+
+
+def spatial_norm_cl(x: torch.Tensor, stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, table: torch.Tensor,
+                    y_off: int, b_off: int, t_src: torch.Tensor, lat_hw, shift: int, *, groups: int = 32, act: int = 1,
+                    out: Optional[torch.Tensor] = None, y_f32: bool = False) -> torch.Tensor:
+    """act(GroupNorm(x) * table[src, y_off:] + table[src, b_off:]) — see orvb_spatial_norm_args."""
+    _req(x, torch.bfloat16, "x")
+    _req(stats, torch.float32, "stats")
+    _req(gamma, torch.bfloat16, "gamma")
+    _req(beta, torch.bfloat16, "beta")
+    _req(table, torch.bfloat16, "table")
+    _req(t_src, torch.int32, "t_src")
+    T, H, W, Cc = x.shape
+    if t_src.numel() != T:
+        raise RuntimeError("spatial_norm_cl: t_src must have one entry per frame")
+    odt = torch.float32 if y_f32 else torch.bfloat16
+    if out is None:
+        out = torch.empty((T, H, W, Cc), dtype=odt, device=x.device)
+    _req(out, odt, "out")
+    a = L.SpatialNormArgs()
+    a.x, a.y = x.data_ptr(), out.data_ptr()
+    a.frames, a.height, a.width, a.channels, a.groups = T, H, W, Cc, groups
+    a.stats, a.gamma, a.beta, a.table = stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), table.data_ptr()
+    a.table_ld, a.y_off, a.b_off = table.stride(0), y_off, b_off
+    a.t_src = t_src.data_ptr()
+    a.lat_h, a.lat_w = lat_hw
+    a.shift, a.act, a.y_f32 = shift, act, int(y_f32)
+    L.check(L.load().orvb_spatial_norm_cl(C.byref(a), L.current_stream()), "orvb_spatial_norm_cl")
+    return out
+
+
+def upsample2x_cl(x: torch.Tensor, t_src: torch.Tensor) -> torch.Tensor:
+    """out[t, h, w] = x[t_src[t], h // 2, w // 2]  (channels-last bf16)."""
+    _req(x, torch.bfloat16, "x")
+    _req(t_src, torch.int32, "t_src")
+    _, H, W, Cc = x.shape
+    To = t_src.numel()
+    out = torch.empty((To, 2 * H, 2 * W, Cc), dtype=torch.bfloat16, device=x.device)
+    L.check(L.load().orvb_upsample2x_cl(x.data_ptr(), out.data_ptr(), To, H, W, Cc, t_src.data_ptr(), L.current_stream()),
+            "orvb_upsample2x_cl")
+    return out
+
+
+def cl_to_planar(x: torch.Tensor, c_keep: int) -> torch.Tensor:
+    """[T, H, W, c_ld] -> [c_keep, T, H, W]."""
+    _req(x, torch.bfloat16, "x")
+    T, H, W, cl = x.shape
+    out = torch.empty((c_keep, T, H, W), dtype=torch.bfloat16, device=x.device)
+    L.check(L.load().orvb_cl_to_planar(x.data_ptr(), out.data_ptr(), T * H * W, cl, c_keep, L.current_stream()),
+            "orvb_cl_to_planar")
+    return out

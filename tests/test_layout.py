@@ -33,7 +33,7 @@ def test_header_symbols_are_exported_by_the_library():
     lib = L.load()  # builds with nvcc if the .so is missing; loading needs no GPU
     for sym in sorted(declared):
         assert hasattr(lib, sym), f"liborv_b200.so does not export {sym}"
-    assert lib.orvb_version() == 101
+    assert lib.orvb_version() == 102
     assert isinstance(lib.orvb_last_error(), bytes)
     # ... and nothing else: every orvb_* symbol the library exports is declared in the header
     import subprocess
@@ -51,10 +51,10 @@ def test_ctypes_structs_match_header_sizes():
 #include <stdio.h>
 #include "orv_b200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(orvb_rowmap), sizeof(orvb_gemm_args), sizeof(orvb_ln_args),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(orvb_rowmap), sizeof(orvb_gemm_args), sizeof(orvb_ln_args),
          sizeof(orvb_config), sizeof(orvb_block_weights), sizeof(orvb_weights), sizeof(orvb_shape),
          sizeof(orvb_forward_args), sizeof(orvb_sampler_step_args), sizeof(orvb_attention_args),
-         sizeof(orvb_voxelize_args), sizeof(orvb_gs_args));
+         sizeof(orvb_voxelize_args), sizeof(orvb_gs_args), sizeof(orvb_conv_args), sizeof(orvb_spatial_norm_args));
   return 0;
 }'''
     with tempfile.TemporaryDirectory() as d:
@@ -64,7 +64,7 @@ int main(void) {
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     mirrors = [L.RowMap, L.GemmArgs, L.LnArgs, L.Config, L.BlockWeights, L.Weights, L.Shape, L.ForwardArgs,
-               L.SamplerStepArgs, L.AttentionArgs, L.VoxelizeArgs, L.GsArgs]
+               L.SamplerStepArgs, L.AttentionArgs, L.VoxelizeArgs, L.GsArgs, L.ConvArgs, L.SpatialNormArgs]
     assert sizes == [ctypes.sizeof(m) for m in mirrors]
 
 
