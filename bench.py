@@ -316,6 +316,23 @@ OUR_KERNELS = ("gemm2_bf16_kernel", "gemm_bf16_kernel", "gemm2_chain_kernel", "a
                "mv_gather_kernel", "fill_tables_kernel", "sampler_step_kernel")
 
 
+def init_vae_weights_(vae, seed: int):
+    """Variance-preserving random decoder weights (std 1/sqrt(fan_in); GroupNorm scales and the multiplicative conv_y
+    branch around 1) so that activations keep unit scale through the 37 norm sites, as a trained decoder's do."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    for name, p in vae.named_parameters():
+        shape = tuple(p.shape)
+        if name.endswith("norm_layer.weight"):
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif name.endswith(".bias"):
+            t = 0.05 * torch.randn(shape, generator=g) + (1.0 if "conv_y" in name else 0.0)
+        elif ".conv_y." in name:
+            t = torch.randn(shape, generator=g) * (0.3 / shape[1] ** 0.5)
+        else:
+            t = torch.randn(shape, generator=g) / (p[0].numel() ** 0.5)
+        p.data.copy_(t.to(p.dtype))
+
+
 def ncu_traffic(cls: str):
     """DRAM bytes per launch of a kernel class from the COMMITTED ncu capture (profiles/traffic.json, written by
     tools/summarize_profiles.py) — context for `roofline.traffic`, which stays null because it cannot be measured in a
@@ -442,7 +459,16 @@ def build_runner(cid: int, clips: int = 0, rank: int = 0, dev=None):
     model.action_embed.mask = False  # parity/bench runs pin the reference's stray action dropout off
     D.broadcast_weights(model, src=0)  # the single collective of the path
     sched = CogVideoXDPMScheduler(timestep_spacing="trailing")
-    pipe = CogVideoXImageToVideoPipelineTraj(None, None, default_vae_config(), model, sched)
+    # 3-D VAE decoder with the reference script's settings (inference_control_to_video.py:98-99); random
+    # variance-preserving weights.  The headline metric excludes decoding; the `decode` leg reports it.
+    from orv_b200 import AutoencoderKLCogVideoX
+    with torch.device(dev):
+        vae = AutoencoderKLCogVideoX()
+    init_vae_weights_(vae, seed=2)
+    vae = vae.to(torch.bfloat16).eval()
+    vae.enable_slicing()
+    vae.enable_tiling()
+    pipe = CogVideoXImageToVideoPipelineTraj(None, None, vae, model, sched)
     # The reference's 1.5-5B pipeline path cannot run with one view (`first_frame` is sliced with
     # size(1) of a 6-D tensor = n_views, cogvideox_control.py:1212-1214, so the image latents get one frame more than the
     # noise latents and :1413 fails).  The drop-in reproduces that by default; the bench asks for the intended padding.
@@ -466,7 +492,7 @@ def build_runner(cid: int, clips: int = 0, rank: int = 0, dev=None):
     host = {k: v.pin_memory() for k, v in host.items()}
     resident = {k: v.to(dev) for k, v in host.items()}
 
-    def run_clip(inp, seed):
+    def run_clip(inp, seed, output_type="latent"):
         gen = torch.Generator().manual_seed(seed)
         cg = {"actions": inp["actions"]}
         if c["controls"]:
@@ -477,14 +503,14 @@ def build_runner(cid: int, clips: int = 0, rank: int = 0, dev=None):
         # prompt AND prompt_embeds, as the reference programs call it (evaluation_control_to_video.py:321-322)
         return pipe(image=inp["image"], prompt_embeds=inp["text"], height=c["px"][0], width=c["px"][1], num_frames=17,
                     num_inference_steps=NUM_INFERENCE_STEPS, guidance_scale=6.0 if c["cfg_pair"] else 1.0, generator=gen,
-                    controls_or_guidances=cg, output_type="latent", return_dict=False, num_views=V, **kw)[0]
+                    controls_or_guidances=cg, output_type=output_type, return_dict=False, num_views=V, **kw)[0]
 
-    def run(seed, from_host=False):
+    def run(seed, from_host=False, output_type="latent"):
         if from_host:
-            return run_clip({k: v.to(dev, non_blocking=True) for k, v in host.items()}, seed)
-        return run_clip(resident, seed)
+            return run_clip({k: v.to(dev, non_blocking=True) for k, v in host.items()}, seed, output_type)
+        return run_clip(resident, seed, output_type)
 
-    info = dict(B=B, V=V, n_cfg=n_cfg, h=h, w=w, host_bytes=sum(v.numel() * v.element_size() for v in host.values()),
+    info = dict(B=B, V=V, n_cfg=n_cfg, h=h, w=w, vae=vae, host_bytes=sum(v.numel() * v.element_size() for v in host.values()),
                 pipe=pipe, arena_bytes=model.weight_arena().numel() * 2)
     return run, model, info
 
@@ -536,6 +562,29 @@ def run_ours(args):
     h2d = info["host_bytes"] + (NUM_INFERENCE_STEPS + 1) * lat_bytes
     d2h = lat_bytes
 
+    # ---- the same call with the 3-D VAE decode behind it (output_type="pt": frames in [0, 1], read back) ----
+    decode = None
+    try:
+        vae = info["vae"]
+
+        def full_clip(i):
+            return run(400 + i, from_host=True, output_type="pt").cpu()
+
+        vid = full_clip(0)
+        full_secs = timed(full_clip, args.steps)
+        lat = out.permute(0, 2, 1, 3, 4) / pipe.vae_scaling_factor_image
+        vae.decode(lat)
+        dec_secs = timed(lambda i: vae.decode(lat), args.steps)
+        decode = {"e2e_with_decode": {"value": world * args.steps * frames_per_step / full_secs, "unit": "frames/s",
+                                      "ms_per_step": full_secs / args.steps * 1e3,
+                                      "d2h_bytes_per_step": int(vid.numel() * vid.element_size())},
+                  "decode_ms_per_step": dec_secs / args.steps * 1e3, "decode_launches_per_step": int(vae.last_launches),
+                  "frames_shape": list(vid.shape), "tiling": True, "slicing": True,
+                  "note": "AutoencoderKLCogVideoX.decode on orvb_conv_cl / orvb_spatial_norm_cl (SURVEY 8 f2); not part of "
+                          "the headline metric, which is the denoise loop (SURVEY 8d)"}
+    except Exception as e:  # noqa: BLE001 — extra leg: never take the bench line down
+        decode = {"unavailable": repr(e)[:300]}
+
     # ---- per-kernel-class device times of one real step ----
     pk = peaks()
     mc = c["model"]
@@ -578,7 +627,7 @@ def run_ours(args):
         "gpu_launches": int(launches_per_step * args.steps),
         "tensor_frac_of_peak": round(tflop_per_step * world * args.steps / secs / (pk["bf16"] * world), 4),
         "tensor_frac_of_burst_peak": round(tflop_per_step * world * args.steps / secs / (pk["bf16_burst"] * world), 4),
-        "roofline": roofline, "kernels": kernels, "kernel_timing": pinfo, "clocks": clk,
+        "roofline": roofline, "kernels": kernels, "kernel_timing": pinfo, "clocks": clk, "decode": decode,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sec, sample, cores = cpu_reference_forward_seconds(cid, B, 3, 1, budget_s=25.0)

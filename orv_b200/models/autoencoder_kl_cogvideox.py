@@ -11,7 +11,7 @@ Arithmetic: liborv_b200.so only.  Activations live channels-last ([T, H, W, C] b
 sample by sample as well: slicing); every causal convolution is an implicit GEMM on tcgen05 (`orvb_conv_cl`: the 3x3x3
 taps are TMA boxes of the activation tensor shifted by the tap offset, zero-filled at the borders), every
 SpatialNorm3D + SiLU is one fused pass (`orvb_gn_stats_cl` + `orvb_spatial_norm_cl`) whose conv_y / conv_b branches are
-evaluated once per LATENT pixel for all 45 norm sites of a frame batch by a single GEMM and looked up through the
+evaluated once per LATENT pixel for all 37 norm sites of a frame batch by a single GEMM and looked up through the
 nearest-neighbour map, and the residual add rides in the second convolution's epilogue.  What stays in torch is layout
 plumbing on tiny tensors (latent tile -> channels-last, tile blending / concatenation of the decoded frames).
 There is no CPU or eager fallback: without the library or on a non-B200 device `decode` raises.
