@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(kThreads) scan_tile_kernel(Load in, uint32_t* 
   if (total_out != nullptr && threadIdx.x == 0 && gridDim.x == 1) *total_out = total;
 }
 
-inline int64_t tiles_of(int64_t n) { return (n + kTile - 1) / kTile; }
+__host__ __device__ inline int64_t tiles_of(int64_t n) { return (n + kTile - 1) / kTile; }
 inline size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
 // scratch (uint32 entries) needed by scan_u32 for n inputs
@@ -125,6 +125,97 @@ inline int scan_u32(const uint32_t* in, uint32_t* out, int64_t n, uint32_t* scra
   return scan_any(LoadU32{in}, out, n, scratch, total_out, st);
 }
 
+// ---- single-pass exclusive scan (decoupled look-back) ------------------------------------------------------------------
+// One launch instead of reduce + scan-of-sums + scan: a tile publishes its aggregate, then walks back over its
+// predecessors' descriptors, 32 at a time, until it meets one that already knows its inclusive prefix.  A descriptor is
+// ONE 64-bit word (flag in bits 63:62, value in the low 32), so flag and value always arrive together.  Flag 3 = not
+// ready: the descriptor array and the ticket counter are initialised by a memset with 0xFF bytes — the same memset that
+// empties the voxel hash table — and tiles are handed out by an atomic ticket in scheduling order, so every predecessor
+// of a running tile is running or done (forward progress).  The element order of the sum is fixed (integers): results
+// are bit-identical run to run.
+//   Load:  uint32_t operator()(int64_t i)                       element i
+//   Store: void operator()(int64_t i, uint32_t exclusive, uint32_t value)
+constexpr unsigned long long kDescAggregate = 1ull << 62, kDescInclusive = 2ull << 62, kDescFlagMask = 3ull << 62;
+
+//          void total(uint32_t sum)                              called once, by the last tile, with the sum of all elements
+struct StoreU32 {
+  uint32_t* out;
+  __device__ __forceinline__ void operator()(int64_t i, uint32_t exclusive, uint32_t) const { out[i] = exclusive; }
+  __device__ __forceinline__ void total(uint32_t) const {}
+};
+
+template <class Load, class Store>
+__global__ void __launch_bounds__(kThreads) scan_lookback_kernel(Load in, Store out, int64_t n,
+                                                                 unsigned long long* __restrict__ desc,
+                                                                 uint32_t* __restrict__ ticket,
+                                                                 uint32_t* __restrict__ total_out) {
+  __shared__ uint32_t s_tile, s_prefix;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u) + 1u;  // the counter starts at 0xFFFFFFFF: first ticket = 0
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const int64_t base = static_cast<int64_t>(tile) * kTile + static_cast<int64_t>(threadIdx.x) * kItems;
+  uint32_t v[kItems];
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    v[k] = (base + k < n) ? in(base + k) : 0u;
+    s += v[k];
+  }
+  uint32_t total;
+  uint32_t run = block_exclusive_scan(s, total);
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    uint32_t prefix = 0;
+    if (tile == 0) {
+      if (lane == 0) atomicExch(&desc[0], kDescInclusive | total);
+    } else {
+      if (lane == 0) atomicExch(&desc[tile], kDescAggregate | total);
+      int64_t look = static_cast<int64_t>(tile) - 1;
+      while (true) {
+        const int64_t idx = look - lane;
+        unsigned long long d = kDescInclusive;  // in front of tile 0: an inclusive prefix of zero
+        if (idx >= 0) d = *reinterpret_cast<volatile unsigned long long*>(desc + idx);
+        const unsigned notready = __ballot_sync(kFull, (d & kDescFlagMask) == kDescFlagMask);
+        const unsigned inclusive = __ballot_sync(kFull, (d & kDescFlagMask) == kDescInclusive);
+        const int first_inc = inclusive ? __ffs(inclusive) - 1 : 32;
+        const unsigned need = (first_inc >= 31) ? kFull : ((2u << first_inc) - 1u);
+        if (notready & need) continue;  // a predecessor inside the window has not published yet: poll again
+        uint32_t c = (lane <= first_inc) ? static_cast<uint32_t>(d) : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFull, c, o);
+        prefix += c;
+        if (inclusive) break;
+        look -= 32;
+      }
+      if (lane == 0) atomicExch(&desc[tile], kDescInclusive | static_cast<unsigned long long>(prefix + total));
+    }
+    if (lane == 0) {
+      s_prefix = prefix;
+      if (static_cast<int64_t>(tile) == tiles_of(n) - 1) {
+        if (total_out != nullptr) *total_out = prefix + total;
+        out.total(prefix + total);
+      }
+    }
+  }
+  __syncthreads();
+  run += s_prefix;
+#pragma unroll
+  for (int k = 0; k < kItems; ++k) {
+    if (base + k < n) out(base + k, run, v[k]);
+    run += v[k];
+  }
+}
+
+// desc: tiles_of(n) 64-bit words, ticket: one uint32 — both filled with 0xFF bytes before the launch
+template <class Load, class Store>
+int scan_lookback(Load in, Store out, int64_t n, unsigned long long* desc, uint32_t* ticket, uint32_t* total_out,
+                  cudaStream_t st) {
+  scan_lookback_kernel<Load, Store><<<static_cast<unsigned>(tiles_of(n)), kThreads, 0, st>>>(in, out, n, desc, ticket,
+                                                                                             total_out);
+  ORVB_CHECK_CUDA(cudaGetLastError());
+  return ORVB_OK;
+}
+
 // ---- 4. stable LSD radix sort, BITS bits per pass, tiles of kThreads * ITEMS elements ------------------------------------
 // hist[d * nblocks + b] = number of keys of tile b whose digit is d (digit-major, so one exclusive scan over the
 // whole array yields the global start of (digit d, tile b)).
@@ -132,8 +223,10 @@ inline int scan_u32(const uint32_t* in, uint32_t* out, int64_t n, uint32_t* scra
 // Defaults (9 bits, 8 items per thread) are the voxelizer's: 2048-element tiles keep the histogram array (512 entries
 // per tile) far smaller than the data at millions of points.  Small inputs want small tiles (more CTAs in flight: the
 // scatter is a latency chain of 2 * ITEMS match / shared-memory rounds per warp) and fewer bins.
-template <int BITS = kRadixBits, int ITEMS = kItems>
-__global__ void __launch_bounds__(kThreads) radix_hist_kernel(const uint32_t* __restrict__ keys, int n, int shift,
+// KeyFn: uint32_t operator()(int64_t i) — the key of element i (LoadU32 for a key array; the voxelizer's first pass
+// computes it from the hash table instead of materialising it).
+template <int BITS = kRadixBits, int ITEMS = kItems, class KeyFn = LoadU32>
+__global__ void __launch_bounds__(kThreads) radix_hist_kernel(KeyFn keys, int n, int shift,
                                                               uint32_t* __restrict__ hist, int nblocks,
                                                               const uint32_t* __restrict__ n_dev = nullptr) {
   constexpr int BINS = 1 << BITS;
@@ -145,7 +238,7 @@ __global__ void __launch_bounds__(kThreads) radix_hist_kernel(const uint32_t* __
 #pragma unroll
   for (int k = 0; k < ITEMS; ++k) {
     const int64_t idx = base + k * kThreads + threadIdx.x;
-    if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & (BINS - 1)], 1u);
+    if (idx < n) atomicAdd(&h[(keys(idx) >> shift) & (BINS - 1)], 1u);
   }
   __syncthreads();
   for (int d = threadIdx.x; d < BINS; d += kThreads) hist[static_cast<size_t>(d) * nblocks + blockIdx.x] = h[d];
@@ -154,8 +247,8 @@ __global__ void __launch_bounds__(kThreads) radix_hist_kernel(const uint32_t* __
 // Scatter of one tile.  Warp w owns the 32 * ITEMS consecutive elements [tile + 32 ITEMS w, tile + 32 ITEMS (w+1)) and
 // walks them 32 at a time, so (warp, iteration, lane) order = element order: ranks by __match_any_sync peers below the
 // lane keep the sort stable.  vin == nullptr means "value = element index" (first pass).
-template <int BITS = kRadixBits, int ITEMS = kItems>
-__global__ void __launch_bounds__(kThreads) radix_scatter_kernel(const uint32_t* __restrict__ kin,
+template <int BITS = kRadixBits, int ITEMS = kItems, class KeyFn = LoadU32>
+__global__ void __launch_bounds__(kThreads) radix_scatter_kernel(KeyFn kin,
                                                                  const uint32_t* __restrict__ vin,
                                                                  uint32_t* __restrict__ kout, uint32_t* __restrict__ vout,
                                                                  int n, int shift, const uint32_t* __restrict__ offs,
@@ -169,11 +262,21 @@ __global__ void __launch_bounds__(kThreads) radix_scatter_kernel(const uint32_t*
     for (int d = threadIdx.x; d < BINS; d += kThreads) wh[w][d] = 0;
   __syncthreads();
   const int64_t wbase = static_cast<int64_t>(blockIdx.x) * (kThreads * ITEMS) + warp * (32 * ITEMS);
+  // this lane's keys and values, requested together up front: with a key functor that chases pointers (the voxelizer's
+  // first pass: slot -> table) a load per phase and iteration was a chain of 2 * ITEMS dependent round trips
+  uint32_t kreg[ITEMS], vreg[ITEMS];
+#pragma unroll
+  for (int it = 0; it < ITEMS; ++it) {
+    const int64_t idx = wbase + it * 32 + lane;
+    kreg[it] = (idx < n) ? kin(idx) : 0u;
+    vreg[it] = (idx < n) ? ((vin != nullptr) ? vin[idx] : static_cast<uint32_t>(idx)) : 0u;
+  }
   // A: per-warp digit histogram
+#pragma unroll
   for (int it = 0; it < ITEMS; ++it) {
     const int64_t idx = wbase + it * 32 + lane;
     const bool act = idx < n;
-    const uint32_t d = act ? ((kin[idx] >> shift) & (BINS - 1)) : (BINS + lane);  // inactive lanes match nobody
+    const uint32_t d = act ? ((kreg[it] >> shift) & (BINS - 1)) : (BINS + lane);  // inactive lanes match nobody
     const unsigned peers = __match_any_sync(kFull, d);
     if (act && lane == __ffs(peers) - 1) wh[warp][d] += __popc(peers);
     __syncwarp();
@@ -191,10 +294,11 @@ __global__ void __launch_bounds__(kThreads) radix_scatter_kernel(const uint32_t*
   }
   __syncthreads();
   // C: stable scatter
+#pragma unroll
   for (int it = 0; it < ITEMS; ++it) {
     const int64_t idx = wbase + it * 32 + lane;
     const bool act = idx < n;
-    const uint32_t key = act ? kin[idx] : 0u;
+    const uint32_t key = kreg[it];
     const uint32_t d = act ? ((key >> shift) & (BINS - 1)) : (BINS + lane);
     const unsigned peers = __match_any_sync(kFull, d);
     const uint32_t start = act ? wh[warp][d] : 0u;
@@ -202,7 +306,7 @@ __global__ void __launch_bounds__(kThreads) radix_scatter_kernel(const uint32_t*
     if (act) {
       const uint32_t dest = start + __popc(peers & ((1u << lane) - 1u));
       kout[dest] = key;
-      vout[dest] = (vin != nullptr) ? vin[idx] : static_cast<uint32_t>(idx);
+      vout[dest] = vreg[it];
       if (lane == __ffs(peers) - 1) wh[warp][d] = start + __popc(peers);
     }
     __syncwarp();
@@ -228,11 +332,11 @@ inline int radix_sort_pairs_t(uint32_t* ka, uint32_t* va, uint32_t* kb, uint32_t
   const int passes = (bits + BITS - 1) / BITS;
   for (int pass = 0; pass < passes; ++pass) {
     const int shift = BITS * pass;
-    radix_hist_kernel<BITS, ITEMS><<<nblocks, kThreads, 0, st>>>(kin, n, shift, hist, nblocks, n_dev);
+    radix_hist_kernel<BITS, ITEMS><<<nblocks, kThreads, 0, st>>>(LoadU32{kin}, n, shift, hist, nblocks, n_dev);
     ORVB_CHECK_CUDA(cudaGetLastError());
     const int rc = scan_u32(hist, hist, static_cast<int64_t>(nblocks) << BITS, scratch, nullptr, st);
     if (rc != ORVB_OK) return rc;
-    radix_scatter_kernel<BITS, ITEMS><<<nblocks, kThreads, 0, st>>>(kin, vin, kout, vout, n, shift, hist, nblocks, n_dev);
+    radix_scatter_kernel<BITS, ITEMS><<<nblocks, kThreads, 0, st>>>(LoadU32{kin}, vin, kout, vout, n, shift, hist, nblocks, n_dev);
     ORVB_CHECK_CUDA(cudaGetLastError());
     kin = kout;
     vin = vout;

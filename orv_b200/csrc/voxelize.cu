@@ -7,16 +7,20 @@
 // numbers the voxels in a <<<1,1>>> kernel (determin_voxel_num, :134-162).  Here the same result — voxels numbered
 // in order of first appearance, points kept in index order, max_points / max_voxels caps — comes from O(N) passes:
 //
+//   0. ONE memset (0xFF bytes) empties the hash table and arms the look-back descriptors / tickets of the three scans
 //   1. voxel_insert_kernel   128-bit point loads -> (z,y,x) cell -> open-addressing hash insert of the 64-bit cell
-//                            key, atomicMin of the point index per occupied slot (= first point of the voxel)
-//   2. exclusive scan of the flags "point i is the first of its voxel" (evaluated inside the scan kernels) -> voxel
-//      numbers in first-appearance order, total voxel count
-//   3. sort_key_kernel       key[i] = voxel number of i's voxel = order[first point of the voxel] (or the drop
-//                            sentinel for invalid / over-cap voxels)
-//   4. stable LSD radix sort of (voxel number, point index), 9 bits per pass, ceil(log2(cap+1)/9) passes: points of a
-//      voxel end up contiguous and in index order, so "position in voxel" = sorted position - segment start
-//   5. segment_kernel / gather_kernel   segment bounds per voxel, feature copy of the first max_points points
-//   6. label_vote_kernel     (optional) one warp per voxel: most frequent label among the max_points slots of the
+//                            key, atomicMin of the point index per occupied slot (= first point of the voxel); the only
+//                            per-point output is the slot number (4 bytes)
+//   2. ONE single-pass (decoupled look-back) exclusive scan of the flags "point i is the first of its voxel", evaluated
+//      on the fly; the scan's store step writes the voxel number (order of first appearance, or the drop sentinel
+//      beyond max_voxels) into the table slot of every first point — no per-point order / key arrays exist
+//   3. stable LSD radix sort of (voxel number, point index), 9 bits per pass, ceil(log2(cap+1)/9) passes, each pass =
+//      histogram + single-pass scan + scatter; the first pass reads its keys through the table
+//      (key(i) = t_vox[slot_of[i]]): points of a voxel end up contiguous and in index order, so "position in voxel" =
+//      sorted position - segment start
+//   4. segment_kernel / gather_kernel   segment bounds per voxel, feature copy of the first max_points points; the
+//                            voxel coordinates are recomputed from the voxel's first point (same arithmetic as step 1)
+//   5. label_vote_kernel     (optional) one warp per voxel: most frequent label among the max_points slots of the
 //                            voxel (empty slots count as label 0, which yields to the runner-up), without ever
 //                            materialising the reference's [max_voxels, max_points, C] tensor (160 MB at its
 //                            1e5 x 100 x 4 call site) or copying it to the host.
@@ -32,6 +36,10 @@ namespace orvb {
 namespace {
 
 constexpr unsigned long long kEmptyKey = ~0ull;
+#ifndef ORVB_VOX_ITEMS
+#define ORVB_VOX_ITEMS 8
+#endif
+constexpr int kVoxItems = ORVB_VOX_ITEMS;  // elements per thread of a radix-sort tile (tile = 256 x this)
 
 struct VoxGeom {
   float lo[3];
@@ -89,21 +97,15 @@ __device__ __forceinline__ uint32_t hash_slot(unsigned long long key, int log2_s
 
 template <bool VEC4>
 __global__ void __launch_bounds__(kThreads) voxel_insert_kernel(const float* __restrict__ points, int n, int c, VoxGeom g,
-                                                                int32_t* __restrict__ cell /*[n,3] z,y,x*/,
                                                                 int32_t* __restrict__ slot_of /*[n]*/,
                                                                 unsigned long long* __restrict__ t_keys,
-                                                                int32_t* __restrict__ t_first, int log2_slots) {
+                                                                uint32_t* __restrict__ t_first, int log2_slots) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
   if (i >= n) return;
   float x, y, z;
   load_xyz<VEC4>(points, i, c, x, y, z);
   int cx, cy, cz;
-  const bool ok = voxel_cell(g, x, y, z, cx, cy, cz);
-  int32_t* o = cell + i * 3;
-  o[0] = ok ? cz : -1;
-  o[1] = ok ? cy : -1;
-  o[2] = ok ? cx : -1;
-  if (!ok) {
+  if (!voxel_cell(g, x, y, z, cx, cy, cz)) {
     slot_of[i] = -1;
     return;
   }
@@ -117,43 +119,44 @@ __global__ void __launch_bounds__(kThreads) voxel_insert_kernel(const float* __r
     if (prev == kEmptyKey || prev == key) break;
     s = (s + 1u) & mask;
   }
-  atomicMin(&t_first[s], static_cast<int32_t>(i));
+  // (measured: reading the slot first and skipping the atomics when an earlier point already holds it is SLOWER —
+  // 57.8 vs 38.1 us for 2 M points: two dependent L2 round trips in front of the atomic instead of one fire-and-forget)
+  atomicMin(&t_first[s], static_cast<uint32_t>(i));  // empty = 0xFFFFFFFF (the table memset)
   slot_of[i] = static_cast<int32_t>(s);
 }
 
-// ---- 2. first-of-voxel flags (evaluated inside the scan kernels, never stored) ---------------------------------------
+// ---- 2. first-of-voxel flags (evaluated inside the scan, never stored) and voxel numbers -----------------------------
 struct LoadFirstFlag {  // 1 when point i is the first (lowest-index) point of its voxel
   const int32_t* slot_of;
-  const int32_t* t_first;
+  const uint32_t* t_first;
   __device__ __forceinline__ uint32_t operator()(int64_t i) const {
     const int32_t s = __ldg(slot_of + i);
-    return (s >= 0 && __ldg(t_first + s) == static_cast<int32_t>(i)) ? 1u : 0u;
+    return (s >= 0 && t_first[s] == static_cast<uint32_t>(i)) ? 1u : 0u;
   }
 };
-
-// ---- 3. voxel numbers -> sort keys ------------------------------------------------------------------------------------
-// order[] = exclusive scan of the first-point flags, so order[f] is the voxel number (order of first appearance) of
-// the voxel whose first point is f.  key[i] = that number, or `cap` (sorts last) for invalid points and voxels beyond
-// max_voxels (voxelization_cpu.cpp:83: a new voxel is refused once voxel_num >= max_voxels, and so are its later
-// points).
-__global__ void __launch_bounds__(kThreads) sort_key_kernel(const int32_t* __restrict__ slot_of,
-                                                            const int32_t* __restrict__ t_first,
-                                                            const uint32_t* __restrict__ order, int n, uint32_t cap,
-                                                            uint32_t* __restrict__ key,
-                                                            const uint32_t* __restrict__ total_voxels,
-                                                            long long* __restrict__ voxel_num) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
-  if (i == 0 && voxel_num != nullptr) *voxel_num = static_cast<long long>(min(*total_voxels, cap));
-  if (i >= n) return;
-  const int32_t s = slot_of[i];
-  uint32_t k = cap;
-  if (s >= 0) {
-    const uint32_t v = order[t_first[s]];
-    if (v < cap) k = v;
+// The exclusive prefix of a first point IS its voxel's number (order of first appearance); voxels beyond max_voxels
+// get the drop sentinel `cap`, which sorts last (voxelization_cpu.cpp:83: a new voxel is refused once voxel_num >=
+// max_voxels, and so are its later points).
+struct StoreVoxelNumber {
+  const int32_t* slot_of;
+  uint32_t* t_vox;
+  uint32_t cap;
+  long long* voxel_num;  // the caller's count: min(number of voxels, max_voxels), written by the last tile
+  __device__ __forceinline__ void operator()(int64_t i, uint32_t exclusive, uint32_t flag) const {
+    if (flag) t_vox[slot_of[i]] = exclusive < cap ? exclusive : cap;
   }
-  key[i] = k;
-}
-
+  __device__ __forceinline__ void total(uint32_t sum) const { *voxel_num = static_cast<long long>(sum < cap ? sum : cap); }
+};
+// ---- 3. sort key of a point = number of its voxel (read through the table; invalid points sort last) -------------------
+struct KeyOfPoint {
+  const int32_t* slot_of;
+  const uint32_t* t_vox;
+  uint32_t cap;
+  __device__ __forceinline__ uint32_t operator()(int64_t i) const {
+    const int32_t s = __ldg(slot_of + i);
+    return s >= 0 ? t_vox[s] : cap;
+  }
+};
 // ---- 5. segments + gather ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) segment_kernel(const uint32_t* __restrict__ skey, int n, uint32_t cap,
                                                            int32_t* __restrict__ seg_start,
@@ -172,7 +175,7 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const float* __restric
                                                           const uint32_t* __restrict__ sval, uint32_t cap,
                                                           const int32_t* __restrict__ seg_start,
                                                           const int32_t* __restrict__ seg_end,
-                                                          const int32_t* __restrict__ cell, int max_points,
+                                                          VoxGeom g, int max_points,
                                                           float* __restrict__ voxels, int32_t* __restrict__ coors,
                                                           int32_t* __restrict__ num_points) {
   const int64_t p = static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x;
@@ -183,10 +186,14 @@ __global__ void __launch_bounds__(kThreads) gather_kernel(const float* __restric
   const int32_t rank = static_cast<int32_t>(p) - start;
   const uint32_t idx = sval[p];
   if (rank == 0) {
-    if (coors != nullptr) {
-      coors[3 * static_cast<size_t>(v) + 0] = cell[3 * static_cast<size_t>(idx) + 0];
-      coors[3 * static_cast<size_t>(v) + 1] = cell[3 * static_cast<size_t>(idx) + 1];
-      coors[3 * static_cast<size_t>(v) + 2] = cell[3 * static_cast<size_t>(idx) + 2];
+    if (coors != nullptr) {  // (z, y, x) of the voxel = the cell of its first point
+      float x, y, z;
+      load_xyz<VEC4>(points, idx, c, x, y, z);
+      int cx = 0, cy = 0, cz = 0;
+      voxel_cell(g, x, y, z, cx, cy, cz);
+      coors[3 * static_cast<size_t>(v) + 0] = cz;
+      coors[3 * static_cast<size_t>(v) + 1] = cy;
+      coors[3 * static_cast<size_t>(v) + 2] = cx;
     }
     if (num_points != nullptr) num_points[v] = min(seg_end[v] - start, max_points);
   }
@@ -212,9 +219,12 @@ struct Vote {
 __device__ __forceinline__ bool vote_better(const Vote& a, const Vote& b) {  // a strictly ahead of b
   return a.count > b.count || (a.count == b.count && a.count > 0 && a.value < b.value);
 }
-__device__ __forceinline__ Vote vote_warp_best(Vote v) {
+constexpr int kVoteGroup = 8;    // lanes per voxel: the occupancy caller's voxels hold ~20 points, a full warp idles
+constexpr int kVoteStage = 128;  // labels of a voxel staged in shared memory (per group); the rest re-read from L2
+
+__device__ __forceinline__ Vote vote_group_best(Vote v) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
+  for (int o = kVoteGroup / 2; o > 0; o >>= 1) {
     Vote t;
     t.count = __shfl_xor_sync(kFull, v.count, o);
     t.value = __shfl_xor_sync(kFull, v.value, o);
@@ -223,39 +233,39 @@ __device__ __forceinline__ Vote vote_warp_best(Vote v) {
   return v;
 }
 
-constexpr int kVoteStage = 128;  // labels of a voxel staged in shared memory (per warp); the rest re-read from L2
-
+// Eight lanes per voxel (four voxels per warp): the kernel is a chain of dependent loads per voxel (segment bounds ->
+// point indices -> labels -> first point), so more voxels in flight per warp is what shortens it.
 __global__ void __launch_bounds__(kThreads) label_vote_kernel(const float* __restrict__ points, int c,
                                                               const uint32_t* __restrict__ sval,
                                                               const int32_t* __restrict__ seg_start,
                                                               const int32_t* __restrict__ seg_end,
-                                                              const int32_t* __restrict__ cell, int max_points,
+                                                              VoxGeom g, int max_points,
                                                               const long long* __restrict__ voxel_num,
                                                               double* __restrict__ out) {
-  __shared__ float stage[kThreads / 32][kVoteStage];
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
+  __shared__ float stage[kThreads / kVoteGroup][kVoteStage];
+  const int gl = threadIdx.x & (kVoteGroup - 1);
+  const int grp = threadIdx.x / kVoteGroup;
   const long long nv = *voxel_num;
-  const long long v = static_cast<long long>(blockIdx.x) * (kThreads / 32) + warp;
-  if (v >= nv) return;
-  const int32_t start = seg_start[v];
-  const int kept = min(seg_end[v] - start, max_points);
+  const long long v = static_cast<long long>(blockIdx.x) * (kThreads / kVoteGroup) + grp;
+  const bool live = v < nv;  // (all lanes stay for the shuffles)
+  const int32_t start = live ? seg_start[v] : 0;
+  const int kept = live ? min(seg_end[v] - start, max_points) : 0;
   const int pad = max_points - kept;
-  float* my = stage[warp];
-  for (int e = lane; e < kept && e < kVoteStage; e += 32)
+  float* my = stage[grp];
+  for (int e = gl; e < kept && e < kVoteStage; e += kVoteGroup)
     my[e] = __ldg(points + static_cast<size_t>(sval[start + e]) * c + (c - 1));
   __syncwarp();
   auto label_at = [&](int e) -> float {
     return e < kVoteStage ? my[e] : __ldg(points + static_cast<size_t>(sval[start + e]) * c + (c - 1));
   };
   Vote best_all = {0, 0.f}, best_nz = {0, 0.f};
-  if (lane == 0 && pad > 0) {  // the empty slots: label 0
+  if (live && gl == 0 && pad > 0) {  // the empty slots: label 0
     int cnt = pad;
     for (int f = 0; f < kept; ++f) cnt += (label_at(f) == 0.f) ? 1 : 0;
     best_all.count = cnt;
     best_all.value = 0.f;
   }
-  for (int e = lane; e < kept; e += 32) {
+  for (int e = gl; e < kept; e += kVoteGroup) {
     const float le = label_at(e);
     int cnt = (le == 0.f) ? pad : 0;
     for (int f = 0; f < kept; ++f) cnt += (label_at(f) == le) ? 1 : 0;
@@ -263,15 +273,18 @@ __global__ void __launch_bounds__(kThreads) label_vote_kernel(const float* __res
     if (vote_better(cand, best_all)) best_all = cand;
     if (le != 0.f && vote_better(cand, best_nz)) best_nz = cand;
   }
-  best_all = vote_warp_best(best_all);
-  best_nz = vote_warp_best(best_nz);
-  if (lane == 0) {
+  best_all = vote_group_best(best_all);
+  best_nz = vote_group_best(best_nz);
+  if (live && gl == 0) {
     const float top = (best_all.value == 0.f && best_nz.count > 0) ? best_nz.value : best_all.value;
     const uint32_t idx = sval[start];
+    const float* pp = points + static_cast<size_t>(idx) * c;
+    int cx = 0, cy = 0, cz = 0;
+    voxel_cell(g, __ldg(pp), __ldg(pp + 1), __ldg(pp + 2), cx, cy, cz);
     double* o = out + 4 * v;
-    o[0] = static_cast<double>(cell[3 * static_cast<size_t>(idx) + 2]);
-    o[1] = static_cast<double>(cell[3 * static_cast<size_t>(idx) + 1]);
-    o[2] = static_cast<double>(cell[3 * static_cast<size_t>(idx) + 0]);
+    o[0] = static_cast<double>(cx);
+    o[1] = static_cast<double>(cy);
+    o[2] = static_cast<double>(cz);
     o[3] = static_cast<double>(top - 1.f);
   }
 }
@@ -300,8 +313,11 @@ struct VoxWorkspace {
   uint32_t cap;
   int passes;
   int nblocks;
-  size_t off_cell, off_slot, off_keys, off_first, off_flag, off_scan, off_total, off_ka, off_va, off_kb, off_vb,
-      off_hist, off_seg_start, off_seg_end, bytes;
+  // [off_keys, off_keys + init_bytes) is what the one memset (0xFF) covers: table keys, first indices, the descriptors
+  // and tickets of the three look-back scans
+  size_t off_keys, off_first, off_desc, off_ticket, init_bytes;
+  size_t desc_stride;  // 64-bit words per scan
+  size_t off_slot, off_vox, off_total, off_ka, off_va, off_kb, off_vb, off_hist, off_seg_start, off_seg_end, bytes;
 };
 
 VoxWorkspace plan_workspace(int32_t n, int32_t max_voxels) {
@@ -314,17 +330,18 @@ VoxWorkspace plan_workspace(int32_t n, int32_t max_voxels) {
   int bits = 1;
   while ((1ull << bits) <= w.cap) ++bits;  // keys take values 0..cap
   w.passes = (bits + kRadixBits - 1) / kRadixBits;
-  w.nblocks = static_cast<int>(tiles_of(static_cast<int64_t>(nn)));
+  w.nblocks = static_cast<int>((nn + static_cast<size_t>(kThreads) * kVoxItems - 1) / (static_cast<size_t>(kThreads) * kVoxItems));
   const size_t hist_entries = static_cast<size_t>(kBins) * w.nblocks;
-  const size_t scan_entries = scan_scratch_entries(static_cast<int64_t>(hist_entries > nn ? hist_entries : nn));
+  w.desc_stride = static_cast<size_t>(tiles_of(static_cast<int64_t>(hist_entries > nn ? hist_entries : nn))) + 1;
   size_t o = 0;
   auto take = [&](size_t bytes) { const size_t at = o; o += align256(bytes); return at; };
-  w.off_cell = take(nn * 12);
-  w.off_slot = take(nn * 4);
   w.off_keys = take(w.slots * 8);
   w.off_first = take(w.slots * 4);
-  w.off_flag = take(nn * 4);
-  w.off_scan = take(scan_entries * 4);
+  w.off_desc = take((1 + static_cast<size_t>(w.passes)) * w.desc_stride * 8);
+  w.off_ticket = take(256);
+  w.init_bytes = o - w.off_keys;
+  w.off_slot = take(nn * 4);
+  w.off_vox = take(w.slots * 4);
   w.off_total = take(256);
   w.off_ka = take(nn * 4);
   w.off_va = take(nn * 4);
@@ -394,12 +411,12 @@ extern "C" int orvb_hard_voxelize(const orvb_voxelize_args* a, void* stream) {
   ORVB_REQUIRE(reinterpret_cast<uintptr_t>(a->workspace) % 256 == 0, ORVB_ESHAPE,
                "hard_voxelize: workspace must be 256-byte aligned");
   char* base = static_cast<char*>(a->workspace);
-  int32_t* cell = reinterpret_cast<int32_t*>(base + w.off_cell);
   int32_t* slot_of = reinterpret_cast<int32_t*>(base + w.off_slot);
   unsigned long long* t_keys = reinterpret_cast<unsigned long long*>(base + w.off_keys);
-  int32_t* t_first = reinterpret_cast<int32_t*>(base + w.off_first);
-  uint32_t* flag = reinterpret_cast<uint32_t*>(base + w.off_flag);
-  uint32_t* scan_scratch = reinterpret_cast<uint32_t*>(base + w.off_scan);
+  uint32_t* t_first = reinterpret_cast<uint32_t*>(base + w.off_first);
+  uint32_t* t_vox = reinterpret_cast<uint32_t*>(base + w.off_vox);
+  unsigned long long* desc = reinterpret_cast<unsigned long long*>(base + w.off_desc);
+  uint32_t* ticket = reinterpret_cast<uint32_t*>(base + w.off_ticket);
   uint32_t* total = reinterpret_cast<uint32_t*>(base + w.off_total);
   uint32_t* ka = reinterpret_cast<uint32_t*>(base + w.off_ka);
   uint32_t* va = reinterpret_cast<uint32_t*>(base + w.off_va);
@@ -414,35 +431,39 @@ extern "C" int orvb_hard_voxelize(const orvb_voxelize_args* a, void* stream) {
   const bool vec4 = (a->c == 4) && (reinterpret_cast<uintptr_t>(a->points) % 16 == 0);
   const bool vec4_out = vec4 && (a->voxels == nullptr || reinterpret_cast<uintptr_t>(a->voxels) % 16 == 0);
 
-  ORVB_CHECK_CUDA(cudaMemsetAsync(t_keys, 0xff, w.slots * 8, st));
-  ORVB_CHECK_CUDA(cudaMemsetAsync(t_first, 0x7f, w.slots * 4, st));
+  // empty table (key = all ones, first index = 0xFFFFFFFF) + armed scan descriptors / tickets: one memset
+  ORVB_CHECK_CUDA(cudaMemsetAsync(t_keys, 0xff, w.init_bytes, st));
   if (vec4)
-    voxel_insert_kernel<true><<<blocks, kThreads, 0, st>>>(a->points, n, a->c, g, cell, slot_of, t_keys, t_first,
-                                                          w.log2_slots);
+    voxel_insert_kernel<true><<<blocks, kThreads, 0, st>>>(a->points, n, a->c, g, slot_of, t_keys, t_first, w.log2_slots);
   else
-    voxel_insert_kernel<false><<<blocks, kThreads, 0, st>>>(a->points, n, a->c, g, cell, slot_of, t_keys, t_first,
-                                                           w.log2_slots);
+    voxel_insert_kernel<false><<<blocks, kThreads, 0, st>>>(a->points, n, a->c, g, slot_of, t_keys, t_first, w.log2_slots);
   ORVB_CHECK_CUDA(cudaGetLastError());
-  // order[i] = number of voxels whose first point precedes i (flags evaluated on the fly, never stored)
-  uint32_t* order = flag;
-  rc = scan_any(LoadFirstFlag{slot_of, t_first}, order, n, scan_scratch, total, st);
+  // voxel numbers (order of first appearance) into the table, voxel count
+  rc = scan_lookback(LoadFirstFlag{slot_of, t_first},
+                     StoreVoxelNumber{slot_of, t_vox, w.cap, reinterpret_cast<long long*>(a->voxel_num)}, n, desc, ticket,
+                     total, st);
   if (rc != ORVB_OK) return rc;
-  sort_key_kernel<<<blocks, kThreads, 0, st>>>(slot_of, t_first, order, n, w.cap, ka, total,
-                                              reinterpret_cast<long long*>(a->voxel_num));
-  ORVB_CHECK_CUDA(cudaGetLastError());
 
-  // stable LSD radix sort of (voxel number, point index)
-  const uint32_t* kin = ka;
+  // stable LSD radix sort of (voxel number, point index); the first pass reads its keys through the table
+  const uint32_t* kin = nullptr;
   const uint32_t* vin = nullptr;  // identity
   uint32_t* kout = kb;
   uint32_t* vout = vb;
+  const KeyOfPoint key0{slot_of, t_vox, w.cap};
+  const int64_t hist_entries = static_cast<int64_t>(kBins) * w.nblocks;
   for (int pass = 0; pass < w.passes; ++pass) {
     const int shift = kRadixBits * pass;
-    radix_hist_kernel<><<<w.nblocks, kThreads, 0, st>>>(kin, n, shift, hist, w.nblocks);
+    if (pass == 0) radix_hist_kernel<kRadixBits, kVoxItems, KeyOfPoint><<<w.nblocks, kThreads, 0, st>>>(key0, n, shift, hist, w.nblocks);
+    else radix_hist_kernel<kRadixBits, kVoxItems><<<w.nblocks, kThreads, 0, st>>>(LoadU32{kin}, n, shift, hist, w.nblocks);
     ORVB_CHECK_CUDA(cudaGetLastError());
-    rc = scan_u32(hist, hist, static_cast<int64_t>(kBins) * w.nblocks, scan_scratch, nullptr, st);
+    rc = scan_lookback(LoadU32{hist}, StoreU32{hist}, hist_entries, desc + (1 + pass) * w.desc_stride, ticket + 1 + pass,
+                       nullptr, st);
     if (rc != ORVB_OK) return rc;
-    radix_scatter_kernel<><<<w.nblocks, kThreads, 0, st>>>(kin, vin, kout, vout, n, shift, hist, w.nblocks);
+    if (pass == 0)
+      radix_scatter_kernel<kRadixBits, kVoxItems, KeyOfPoint><<<w.nblocks, kThreads, 0, st>>>(key0, vin, kout, vout, n, shift, hist,
+                                                                                         w.nblocks);
+    else
+      radix_scatter_kernel<kRadixBits, kVoxItems><<<w.nblocks, kThreads, 0, st>>>(LoadU32{kin}, vin, kout, vout, n, shift, hist, w.nblocks);
     ORVB_CHECK_CUDA(cudaGetLastError());
     kin = kout;
     vin = vout;
@@ -456,17 +477,17 @@ extern "C" int orvb_hard_voxelize(const orvb_voxelize_args* a, void* stream) {
   ORVB_CHECK_CUDA(cudaGetLastError());
   if (a->voxels != nullptr || a->coors != nullptr || a->num_points_per_voxel != nullptr) {
     if (vec4_out)
-      gather_kernel<true><<<blocks, kThreads, 0, st>>>(a->points, n, a->c, skey, sval, w.cap, seg_start, seg_end, cell,
+      gather_kernel<true><<<blocks, kThreads, 0, st>>>(a->points, n, a->c, skey, sval, w.cap, seg_start, seg_end, g,
                                                       a->max_points, a->voxels, a->coors, a->num_points_per_voxel);
     else
-      gather_kernel<false><<<blocks, kThreads, 0, st>>>(a->points, n, a->c, skey, sval, w.cap, seg_start, seg_end, cell,
+      gather_kernel<false><<<blocks, kThreads, 0, st>>>(a->points, n, a->c, skey, sval, w.cap, seg_start, seg_end, g,
                                                        a->max_points, a->voxels, a->coors, a->num_points_per_voxel);
     ORVB_CHECK_CUDA(cudaGetLastError());
   }
   if (a->voxel_labels != nullptr) {
-    const unsigned vblocks = (w.cap + kThreads / 32 - 1) / (kThreads / 32);
+    const unsigned vblocks = (w.cap + kThreads / kVoteGroup - 1) / (kThreads / kVoteGroup);
     if (vblocks > 0) {
-      label_vote_kernel<<<vblocks, kThreads, 0, st>>>(a->points, a->c, sval, seg_start, seg_end, cell, a->max_points,
+      label_vote_kernel<<<vblocks, kThreads, 0, st>>>(a->points, a->c, sval, seg_start, seg_end, g, a->max_points,
                                                      reinterpret_cast<const long long*>(a->voxel_num),
                                                      a->voxel_labels);
       ORVB_CHECK_CUDA(cudaGetLastError());
