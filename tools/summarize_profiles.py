@@ -45,7 +45,7 @@ if os.path.exists(lp):
         f.write(f"\ntotal {tot/1e3:.1f} us over {len(rows)} launches\n")
 
 traffic = {}
-for name in ("attn", "gemm", "pointwise"):
+for name in ("attn", "gemm", "pointwise", "conv"):
     rp = os.path.join(src, f"{tag}_{name}.ncu-rep")
     if not os.path.exists(rp):
         continue
