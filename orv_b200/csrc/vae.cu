@@ -30,6 +30,8 @@ gn_stats_kernel(const uint4* __restrict__ x, long long pixels, int C, int groups
   __shared__ float s_sum[VAE_THREADS * 8];
   __shared__ float s_sq[VAE_THREADS * 8];
   __shared__ bool s_last;
+  pdl_launch_dependents();
+  pdl_wait();  // x comes from the previous kernel of the chain (programmatic dependent launch)
   const int vp = C >> 3;
   const int lanes = VAE_THREADS / vp;
   const int tid = threadIdx.x;
@@ -41,7 +43,25 @@ gn_stats_kernel(const uint4* __restrict__ x, long long pixels, int C, int groups
     const long long p0 = static_cast<long long>(blockIdx.x) * chunk;
     long long p1 = p0 + chunk;
     if (p1 > pixels) p1 = pixels;
-    for (long long p = p0 + lane; p < p1; p += lanes) {
+    // four pixels per trip: the loads are issued together (one 16-byte load in flight per thread left the kernel at
+    // 3.0 TB/s); the accumulation order per channel stays pixel order, so the result does not change
+    long long p = p0 + lane;
+    for (; p + 3LL * lanes < p1; p += 4LL * lanes) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = __ldg(x + (p + static_cast<long long>(k) * lanes) * vp + v);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float f[8];
+        unpack8(u[k], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a[j] += f[j];
+          q[j] = fmaf(f[j], f[j], q[j]);
+        }
+      }
+    }
+    for (; p < p1; p += lanes) {
       float f[8];
       unpack8(__ldg(x + p * vp + v), f);
 #pragma unroll
@@ -82,7 +102,20 @@ gn_stats_kernel(const uint4* __restrict__ x, long long pixels, int C, int groups
   const double n = static_cast<double>(pixels) * gs;
   for (int g = warp; g < groups; g += VAE_THREADS / 32) {
     double s = 0.0, t = 0.0;
-    for (int c = wl; c < nchunks; c += 32) {
+    int c = wl;
+    // eight partials requested per trip: one dependent L2 round trip per partial made this fold (19 per lane for the
+    // decoder's largest tensors, four groups per warp) as long as the streaming pass itself
+    for (; c + 7 * 32 < nchunks; c += 8 * 32) {
+      GnPartial pp[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) pp[k] = __ldcg(partial + static_cast<size_t>(c + k * 32) * groups + g);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        s += pp[k].x;
+        t += pp[k].y;
+      }
+    }
+    for (; c < nchunks; c += 32) {
       const GnPartial pp = __ldcg(partial + static_cast<size_t>(c) * groups + g);
       s += pp.x;
       t += pp.y;
@@ -127,6 +160,8 @@ struct SnDev {
 
 __global__ void __launch_bounds__(VAE_THREADS) spatial_norm_kernel(const SnDev p) {
   extern __shared__ float s_ab[];  // [2][C]: a = rstd * gamma, b = beta - mean * a
+  pdl_launch_dependents();
+  pdl_wait();  // stats / x come from the previous kernels of the chain
   const int C = p.C;
   const int gs = C / p.groups;
   for (int c = threadIdx.x; c < C; c += VAE_THREADS) {
@@ -140,35 +175,70 @@ __global__ void __launch_bounds__(VAE_THREADS) spatial_norm_kernel(const SnDev p
   const long long total = p.pixels * vp;
   const long long stride = static_cast<long long>(gridDim.x) * VAE_THREADS;
   const int hw = p.H * p.W;
-  for (long long i = static_cast<long long>(blockIdx.x) * VAE_THREADS + threadIdx.x; i < total; i += stride) {
-    const long long pix = i / vp;
-    const int c0 = static_cast<int>(i - pix * vp) * 8;
-    const int t = static_cast<int>(pix / hw);
-    const int r = static_cast<int>(pix - static_cast<long long>(t) * hw);
-    const int h = r / p.W, w = r - h * p.W;
-    const size_t src = (static_cast<size_t>(__ldg(p.t_src + t)) * p.lat_h + (h >> p.shift)) * p.lat_w + (w >> p.shift);
-    const bf16* trow = p.table + src * p.table_ld;
-    float f[8], yy[8], bb[8];
-    unpack8(__ldg(p.x + i), f);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(trow + p.y_off + c0)), yy);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(trow + p.b_off + c0)), bb);
-    float o[8];
+  // The grid stride is a multiple of vp whenever vp divides the block size (C = 64 .. 512 and every power of two), so a
+  // thread keeps ONE channel chunk for the whole loop: its eight (a, b) pairs live in registers, and the pixel index
+  // advances by a constant.  Two vectors per trip: six independent 16-byte loads in flight per thread.
+  const unsigned uvp = static_cast<unsigned>(vp);
+  const bool fixed_chunk = (VAE_THREADS % vp) == 0;
+  const unsigned first = blockIdx.x * VAE_THREADS + threadIdx.x;
+  float ra[8], rb[8];
+  if (fixed_chunk) {
+    const int c0 = static_cast<int>(first % uvp) * 8;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float nrm = fmaf(f[j], s_ab[c0 + j], s_ab[C + c0 + j]);
-      float v = fmaf(nrm, yy[j], bb[j]);
-      if (p.act == 1) v = v / (1.0f + __expf(-v));
-      o[j] = v;
+      ra[j] = s_ab[c0 + j];
+      rb[j] = s_ab[C + c0 + j];
     }
-    if (p.y_f32) {
-      float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.y) + i * 8);
-      op[0] = make_float4(o[0], o[1], o[2], o[3]);
-      op[1] = make_float4(o[4], o[5], o[6], o[7]);
-    } else {
-      uint4 u;
-      u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]);
-      u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
-      reinterpret_cast<uint4*>(p.y)[i] = u;
+  }
+  for (long long i0 = first; i0 < total; i0 += 2 * stride) {
+    long long idx[2] = {i0, i0 + stride};
+    uint4 ux[2], uy[2], ub[2];
+    int c0s[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const long long i = idx[k] < total ? idx[k] : i0;
+      // 32-bit index arithmetic (the host checks pixels * C / 8 < 2^31): 64-bit divisions cost ~100 instructions each
+      const unsigned iu = static_cast<unsigned>(i);
+      const unsigned pix = iu / uvp;
+      const int c0 = static_cast<int>(iu - pix * uvp) * 8;
+      const unsigned t = pix / static_cast<unsigned>(hw);
+      const unsigned r = pix - t * static_cast<unsigned>(hw);
+      const unsigned h = r / static_cast<unsigned>(p.W), w = r - h * static_cast<unsigned>(p.W);
+      const size_t src = (static_cast<size_t>(__ldg(p.t_src + t)) * p.lat_h + (h >> p.shift)) * p.lat_w + (w >> p.shift);
+      const bf16* trow = p.table + src * p.table_ld;
+      c0s[k] = c0;
+      ux[k] = __ldg(p.x + i);
+      uy[k] = __ldg(reinterpret_cast<const uint4*>(trow + p.y_off + c0));
+      ub[k] = __ldg(reinterpret_cast<const uint4*>(trow + p.b_off + c0));
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (idx[k] >= total) break;
+      const long long i = idx[k];
+      const int c0 = c0s[k];
+      float f[8], yy[8], bb[8], o[8];
+      unpack8(ux[k], f);
+      unpack8(uy[k], yy);
+      unpack8(ub[k], bb);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float a = fixed_chunk ? ra[j] : s_ab[c0 + j];
+        const float b = fixed_chunk ? rb[j] : s_ab[C + c0 + j];
+        const float nrm = fmaf(f[j], a, b);
+        float v = fmaf(nrm, yy[j], bb[j]);
+        if (p.act == 1) v = __fdividef(v, 1.0f + __expf(-v));  // SiLU: MUFU.EX2 + MUFU.RCP (2 ulp), no division routine
+        o[j] = v;
+      }
+      if (p.y_f32) {
+        float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.y) + i * 8);
+        op[0] = make_float4(o[0], o[1], o[2], o[3]);
+        op[1] = make_float4(o[4], o[5], o[6], o[7]);
+      } else {
+        uint4 u;
+        u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]);
+        u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
+        reinterpret_cast<uint4*>(p.y)[i] = u;
+      }
     }
   }
 }
@@ -176,15 +246,18 @@ __global__ void __launch_bounds__(VAE_THREADS) spatial_norm_kernel(const SnDev p
 __global__ void __launch_bounds__(VAE_THREADS)
 upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int frames_out, int H, int W, int vp,
                   const int* __restrict__ t_src) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int H2 = 2 * H, W2 = 2 * W;
   const long long total = static_cast<long long>(frames_out) * H2 * W2 * vp;
   const long long stride = static_cast<long long>(gridDim.x) * VAE_THREADS;
   for (long long i = static_cast<long long>(blockIdx.x) * VAE_THREADS + threadIdx.x; i < total; i += stride) {
-    const long long pix = i / vp;
-    const int v = static_cast<int>(i - pix * vp);
-    const int t = static_cast<int>(pix / (H2 * W2));
-    const int r = static_cast<int>(pix - static_cast<long long>(t) * (H2 * W2));
-    const int h = r / W2, w = r - h * W2;
+    const unsigned iu = static_cast<unsigned>(i);  // (the host checks total < 2^31)
+    const unsigned pix = iu / static_cast<unsigned>(vp);
+    const unsigned v = iu - pix * static_cast<unsigned>(vp);
+    const unsigned t = pix / static_cast<unsigned>(H2 * W2);
+    const unsigned r = pix - t * static_cast<unsigned>(H2 * W2);
+    const unsigned h = r / static_cast<unsigned>(W2), w = r - h * static_cast<unsigned>(W2);
     const size_t src = (static_cast<size_t>(__ldg(t_src + t)) * H + (h >> 1)) * W + (w >> 1);
     out[i] = __ldg(x + src * vp + v);
   }
@@ -192,6 +265,8 @@ upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int fram
 
 __global__ void __launch_bounds__(VAE_THREADS)
 cl_to_planar_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, long long pixels, int c_ld, int c_keep) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long stride = static_cast<long long>(gridDim.x) * VAE_THREADS;
   for (long long p = static_cast<long long>(blockIdx.x) * VAE_THREADS + threadIdx.x; p < pixels; p += stride) {
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + p * c_ld));
@@ -231,10 +306,11 @@ extern "C" int orvb_gn_stats_cl(const void* x, int64_t pixels, int32_t channels,
                "orvb_gn_stats_cl: channels (%d) must be a multiple of 8 (<= 2048) and of groups (%d)", channels, groups);
   const int chunk = gn_chunk(pixels);
   const int nchunks = static_cast<int>((pixels + chunk - 1) / chunk);
-  gn_stats_kernel<<<nchunks, VAE_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint4*>(x), pixels, channels, groups, chunk, nchunks, eps,
-      reinterpret_cast<GnPartial*>(static_cast<uint8_t*>(scratch) + 256), static_cast<unsigned int*>(scratch), stats);
-  ORVB_CHECK_CUDA(cudaGetLastError());
+  ORVB_CHECK_CUDA(launch_kernel(gn_stats_kernel, dim3(nchunks), dim3(VAE_THREADS), 0, static_cast<cudaStream_t>(stream), true,
+                                static_cast<const uint4*>(x), static_cast<long long>(pixels), static_cast<int>(channels),
+                                static_cast<int>(groups), chunk, nchunks, eps,
+                                reinterpret_cast<GnPartial*>(static_cast<uint8_t*>(scratch) + 256),
+                                static_cast<unsigned int*>(scratch), stats));
   return ORVB_OK;
 }
 
@@ -267,8 +343,9 @@ extern "C" int orvb_spatial_norm_cl(const orvb_spatial_norm_args* a, void* strea
   d.t_src = a->t_src; d.lat_h = a->lat_h; d.lat_w = a->lat_w; d.shift = a->shift;
   d.act = a->act; d.y_f32 = a->y_f32;
   const long long items = d.pixels * (d.C >> 3);
-  spatial_norm_kernel<<<grid_for(items), VAE_THREADS, 2 * d.C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(d);
-  ORVB_CHECK_CUDA(cudaGetLastError());
+  ORVB_REQUIRE(items < (1ll << 31), ORVB_ESHAPE, "orvb_spatial_norm_cl: tensor too large (%lld 16-byte vectors)", items);
+  ORVB_CHECK_CUDA(launch_kernel(spatial_norm_kernel, dim3(grid_for(items)), dim3(VAE_THREADS), 2 * d.C * sizeof(float),
+                                static_cast<cudaStream_t>(stream), true, d));
   return ORVB_OK;
 }
 
@@ -281,9 +358,11 @@ extern "C" int orvb_upsample2x_cl(const void* x, void* out, int32_t frames_out, 
   ORVB_REQUIRE(frames_out > 0 && height > 0 && width > 0 && channels > 0 && channels % 8 == 0, ORVB_ESHAPE,
                "orvb_upsample2x_cl: bad shape (channels must be a multiple of 8)");
   const long long items = static_cast<long long>(frames_out) * 4 * height * width * (channels >> 3);
-  upsample2x_kernel<<<grid_for(items), VAE_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint4*>(x), static_cast<uint4*>(out), frames_out, height, width, channels >> 3, t_src);
-  ORVB_CHECK_CUDA(cudaGetLastError());
+  ORVB_REQUIRE(items < (1ll << 31), ORVB_ESHAPE, "orvb_upsample2x_cl: tensor too large (%lld 16-byte vectors)", items);
+  ORVB_CHECK_CUDA(launch_kernel(upsample2x_kernel, dim3(grid_for(items)), dim3(VAE_THREADS), 0,
+                                static_cast<cudaStream_t>(stream), true, static_cast<const uint4*>(x),
+                                static_cast<uint4*>(out), static_cast<int>(frames_out), static_cast<int>(height),
+                                static_cast<int>(width), static_cast<int>(channels >> 3), static_cast<const int*>(t_src)));
   return ORVB_OK;
 }
 
@@ -294,8 +373,8 @@ extern "C" int orvb_cl_to_planar(const void* x, void* out, int64_t pixels, int32
   ORVB_REQUIRE(x && out, ORVB_EINVAL, "orvb_cl_to_planar: null pointer");
   ORVB_REQUIRE(pixels > 0 && c_ld >= 8 && c_ld % 8 == 0 && c_keep >= 1 && c_keep <= 8, ORVB_ESHAPE,
                "orvb_cl_to_planar: c_ld must be a multiple of 8 and 1 <= c_keep <= 8");
-  cl_to_planar_kernel<<<grid_for(pixels), VAE_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const bf16*>(x), static_cast<bf16*>(out), pixels, c_ld, c_keep);
-  ORVB_CHECK_CUDA(cudaGetLastError());
+  ORVB_CHECK_CUDA(launch_kernel(cl_to_planar_kernel, dim3(grid_for(pixels)), dim3(VAE_THREADS), 0,
+                                static_cast<cudaStream_t>(stream), true, static_cast<const bf16*>(x), static_cast<bf16*>(out),
+                                static_cast<long long>(pixels), static_cast<int>(c_ld), static_cast<int>(c_keep)));
   return ORVB_OK;
 }
