@@ -579,6 +579,9 @@ def run_ours(args):
                                       "ms_per_step": full_secs / args.steps * 1e3,
                                       "d2h_bytes_per_step": int(vid.numel() * vid.element_size())},
                   "decode_ms_per_step": dec_secs / args.steps * 1e3, "decode_launches_per_step": int(vae.last_launches),
+                  "decode_conv_tflop_per_step": round(lat.shape[0] * vae.decode_conv_flops(*lat.shape[2:]) / 1e12, 3),
+                  "decode_tensor_frac_of_peak": round(lat.shape[0] * vae.decode_conv_flops(*lat.shape[2:]) / 1e12
+                                                      / (dec_secs / args.steps) / peaks()["bf16"], 4),
                   "frames_shape": list(vid.shape), "tiling": True, "slicing": True,
                   "note": "AutoencoderKLCogVideoX.decode on orvb_conv_cl / orvb_spatial_norm_cl (SURVEY 8 f2); not part of "
                           "the headline metric, which is the denoise loop (SURVEY 8d)"}

@@ -434,6 +434,39 @@ class AutoencoderKLCogVideoX(nn.Module):
             result_rows.append(torch.cat(result_row, dim=3))
         return torch.cat(result_rows, dim=2)
 
+    def decode_conv_flops(self, frames: int, h: int, w: int) -> float:
+        """Algorithmic FLOP (2 * pixels * taps * c_in * c_out) of the convolutions of one sample's decode, tile overlap
+        included — it is work the reference's algorithm prescribes.  Used by the benches for the tensor-pipe fraction."""
+        c = self.config
+        rev = tuple(reversed(c.block_out_channels))
+        if self.use_tiling and (w > self.tile_latent_min_width or h > self.tile_latent_min_height):
+            oh = int(self.tile_latent_min_height * (1 - self.tile_overlap_factor_height))
+            ow = int(self.tile_latent_min_width * (1 - self.tile_overlap_factor_width))
+            tiles = [(min(self.tile_latent_min_height, h - i), min(self.tile_latent_min_width, w - j))
+                     for i in range(0, h, oh) for j in range(0, w, ow)]
+        else:
+            tiles = [(h, w)]
+        compress_level = int(np.log2(c.temporal_compression_ratio))
+
+        def res(ci, co):
+            return 27 * ci * co + 27 * co * co + (ci * co if ci != co else 0)
+
+        total = 0.0
+        for th, tw in tiles:
+            for s, e in frame_batches(frames, self.num_latent_frames_batch_size):
+                t, H, W = e - s, th, tw
+                total += 2.0 * t * H * W * (27 * c.latent_channels * rev[0] + 2 * res(rev[0], rev[0]))
+                cout = rev[0]
+                for b, ch in enumerate(rev):
+                    cin, cout = cout, ch
+                    total += 2.0 * t * H * W * (res(cin, cout) + c.layers_per_block * res(cout, cout))
+                    if b != len(rev) - 1:
+                        t = len(upsample_frame_map(t, b < compress_level))
+                        H, W = 2 * H, 2 * W
+                        total += 2.0 * t * H * W * 9 * cout * cout
+                total += 2.0 * t * H * W * 27 * cout * c.out_channels
+        return total
+
     def _decode_sample(self, z: torch.Tensor) -> torch.Tensor:
         _, _, h, w = z.shape
         if self.use_tiling and (w > self.tile_latent_min_width or h > self.tile_latent_min_height):

@@ -22,37 +22,7 @@ import torch  # noqa: E402
 
 
 def conv_flops(vae, T, h, w) -> float:
-    """Algorithmic FLOP of the convolutions of a tiled decode (tile overlap included: it is work the reference's
-    algorithm prescribes)."""
-    from orv_b200.models.autoencoder_kl_cogvideox import frame_batches, upsample_frame_map
-    c = vae.config
-    rev = tuple(reversed(c.block_out_channels))
-    tiles = []
-    if vae.use_tiling and (w > vae.tile_latent_min_width or h > vae.tile_latent_min_height):
-        oh = int(vae.tile_latent_min_height * (1 - vae.tile_overlap_factor_height))
-        ow = int(vae.tile_latent_min_width * (1 - vae.tile_overlap_factor_width))
-        for i in range(0, h, oh):
-            for j in range(0, w, ow):
-                tiles.append((min(vae.tile_latent_min_height, h - i), min(vae.tile_latent_min_width, w - j)))
-    else:
-        tiles.append((h, w))
-    total = 0.0
-    for th, tw in tiles:
-        for s, e in frame_batches(T, vae.num_latent_frames_batch_size):
-            t, H, W = e - s, th, tw
-            total += 2.0 * t * H * W * 27 * c.latent_channels * rev[0]
-            cout = rev[0]
-            per_res = lambda ci, co: 27 * ci * co + 27 * co * co + (ci * co if ci != co else 0)  # noqa: E731
-            total += 2 * 2.0 * t * H * W * per_res(rev[0], rev[0])
-            for b, ch in enumerate(rev):
-                cin, cout = cout, ch
-                total += 2.0 * t * H * W * (per_res(cin, cout) + c.layers_per_block * per_res(cout, cout))
-                if b != len(rev) - 1:
-                    t = len(upsample_frame_map(t, b < 2))
-                    H, W = 2 * H, 2 * W
-                    total += 2.0 * t * H * W * 9 * cout * cout
-            total += 2.0 * t * H * W * 27 * cout * c.out_channels
-    return total
+    return vae.decode_conv_flops(T, h, w)
 
 
 def main():
