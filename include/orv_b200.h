@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ORVB_VERSION 102
+#define ORVB_VERSION 103
 
 enum {
   ORVB_OK = 0,
@@ -490,8 +490,15 @@ typedef struct orvb_conv_args {
   int32_t c_out;      /* multiple of 8                                                        */
   int32_t kt, kh, kw; /* kt in 1..4; kh, kw odd, <= 7                                         */
   int32_t out_f32;    /* tight-tolerance test mode (see orvb_gemm_args.out_f32)               */
+  /* Optional: GroupNorm statistics of the OUTPUT (as stored, i.e. rounded to bf16) accumulated in the epilogue, so the
+   * SpatialNorm3D that follows needs no extra pass over the tensor: gn_stats[g] = (mean, rstd) fp32 for gn_groups
+   * (<= 32) groups of c_out / gn_groups (a power of two in 2..64) consecutive channels; c_out % 64 == 0.  gn_scratch:
+   * orvb_conv_gn_scratch_bytes() bytes, 16-byte aligned.  Deterministic (fixed tile schedule, fp64 fold in a fixed
+   * order).  NULL = off. */
+  float* gn_stats; void* gn_scratch; int32_t gn_groups; float gn_eps;
 } orvb_conv_args;
 int orvb_conv_cl(const orvb_conv_args* args, void* stream);
+size_t orvb_conv_gn_scratch_bytes(void);
 
 /* GroupNorm statistics of a channels-last tensor over ALL its pixels (one sample): stats[g] = (mean, rstd) fp32 for
  * the `groups` groups of channels/groups consecutive channels.  Deterministic: fixed-size pixel chunks are summed in

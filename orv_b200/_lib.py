@@ -167,6 +167,7 @@ class ConvArgs(C.Structure):
         ("x", c_void_p), ("cache", c_void_p), ("w", c_void_p), ("bias", c_void_p), ("resid", c_void_p), ("out", c_void_p),
         ("frames", c_int), ("height", c_int), ("width", c_int), ("c_in", c_int), ("c_out", c_int),
         ("kt", c_int), ("kh", c_int), ("kw", c_int), ("out_f32", c_int),
+        ("gn_stats", c_void_p), ("gn_scratch", c_void_p), ("gn_groups", c_int), ("gn_eps", c_float),
     ]
 
 
@@ -191,7 +192,7 @@ EXPORTED_SYMBOLS = [
     "orvb_sampler_step",
     "orvb_dynamic_voxelize", "orvb_voxelize_workspace_bytes", "orvb_hard_voxelize",
     "orvb_gs_workspace_bytes", "orvb_gs_rasterize",
-    "orvb_conv_cl", "orvb_gn_scratch_bytes", "orvb_gn_stats_cl", "orvb_spatial_norm_cl", "orvb_upsample2x_cl",
+    "orvb_conv_cl", "orvb_conv_gn_scratch_bytes", "orvb_gn_scratch_bytes", "orvb_gn_stats_cl", "orvb_spatial_norm_cl", "orvb_upsample2x_cl",
     "orvb_cl_to_planar",
 ]
 
@@ -287,6 +288,8 @@ def load() -> C.CDLL:
     if hasattr(lib, "orvb_conv_cl"):
         lib.orvb_conv_cl.argtypes = [C.POINTER(ConvArgs), c_void_p]
         lib.orvb_conv_cl.restype = c_int
+        lib.orvb_conv_gn_scratch_bytes.argtypes = []
+        lib.orvb_conv_gn_scratch_bytes.restype = C.c_size_t
         lib.orvb_gn_scratch_bytes.argtypes = [C.c_int64, c_int]
         lib.orvb_gn_scratch_bytes.restype = C.c_size_t
         lib.orvb_gn_stats_cl.argtypes = [c_void_p, C.c_int64, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]

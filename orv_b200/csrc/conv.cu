@@ -27,9 +27,47 @@ struct ConvDev {
   int KT, KH, KW, kc;      // kernel taps, K steps per tap (C_in / 64)
   int num_patches;         // T * HB * WB
   int has_cache;
+  // GroupNorm statistics of the OUTPUT, accumulated in the epilogue (gn_gs_log2 < 0: off): channels per group = 2^gs_log2,
+  // gn_part[cta * 32 + group] = (sum, sum of squares) over the pixels that CTA stored
+  int gn_gs_log2;
+  double2* gn_part;
 };
 
 constexpr int CV_PH = 8, CV_PW = 16;  // patch = 8 rows x 16 columns = 128 pixels = one M tile
+
+__device__ __forceinline__ float cv_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// Sum and sum of squares of one 64-column unit, per group of GS channels, over the warp's 32 pixels — of the values AS
+// STORED (rounded to bf16: the next operator normalises the bf16 tensor).  Lane g keeps group g's running totals in
+// fp64; which tiles a warp sees and in which order is fixed by the static tile schedule, so the result is deterministic.
+template <int GS>
+__device__ __forceinline__ void cv_gn_unit(const float (&v)[64], bool valid, int n0, int ncols, int lane, double& acc_s,
+                                           double& acc_q) {
+  constexpr int G = 64 / GS;
+  const int g0 = n0 / GS;
+#pragma unroll
+  for (int k = 0; k < G; ++k) {
+    if (k * GS >= ncols) break;  // (warp-uniform) the narrower last unit of a tile: its tail belongs to the next tile
+    float s = 0.f, q = 0.f;
+    if (valid) {
+#pragma unroll
+      for (int c = 0; c < GS; ++c) {
+        const float r = __bfloat162float(__float2bfloat16(v[k * GS + c]));
+        s += r;
+        q = fmaf(r, r, q);
+      }
+    }
+    s = cv_warp_sum(s);
+    q = cv_warp_sum(q);
+    if (lane == g0 + k) {
+      acc_s += static_cast<double>(s);
+      acc_q += static_cast<double>(q);
+    }
+  }
+}
 
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2_threads(EPI), 1)
@@ -188,6 +226,7 @@ conv2_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t stores = 0;
+    double gn_s = 0.0, gn_q = 0.0;  // lane g: group g of the output's GroupNorm (cv.gn_part)
     uint8_t* my_stage = out_stage + (warp - 4) * (NBUF * 32 * 128);
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m_blk = tile % p.num_m_tiles;
@@ -216,8 +255,8 @@ conv2_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
           if (lane == 0) bulk_wait_group_read<NBUF - 1>();
           __syncwarp();
         }
+        float v[64];
         if (row < p.M || staged) {  // (staged: rows outside the image still fill their slot; the store clips them)
-          float v[64];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             v[j] = __uint_as_float(r0[j]);
@@ -228,6 +267,20 @@ conv2_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
           if (p.N - n0 < ncols) ncols = p.N - n0;
           if (row < p.M) {
             epilogue_unit<EPI>(p, v, row, n0, ncols, staged ? sbuf + lane * 128 : nullptr, lane & 7);
+          }
+        }
+        if (cv.gn_gs_log2 >= 0) {  // warp-uniform: statistics of the values just stored, for the next GroupNorm
+          const bool valid = row < p.M;
+          int nc = bn - c;
+          if (nc > 64) nc = 64;
+          if (p.N - n0 < nc) nc = p.N - n0;
+          switch (cv.gn_gs_log2) {
+            case 1: cv_gn_unit<2>(v, valid, n0, nc, lane, gn_s, gn_q); break;
+            case 2: cv_gn_unit<4>(v, valid, n0, nc, lane, gn_s, gn_q); break;
+            case 3: cv_gn_unit<8>(v, valid, n0, nc, lane, gn_s, gn_q); break;
+            case 4: cv_gn_unit<16>(v, valid, n0, nc, lane, gn_s, gn_q); break;
+            case 5: cv_gn_unit<32>(v, valid, n0, nc, lane, gn_s, gn_q); break;
+            default: cv_gn_unit<64>(v, valid, n0, nc, lane, gn_s, gn_q); break;
           }
         }
         if (staged) {
@@ -248,6 +301,25 @@ conv2_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
         acc_phase ^= 1;
       }
     }
+    if (cv.gn_part != nullptr) {
+      // one partial per CTA: the eight epilogue warps meet in the output staging area (every TMA store that read it has
+      // finished) and warp 4 adds them up in warp order
+      if (lane == 0) bulk_wait_group_read<0>();
+      __syncwarp();
+      named_bar_sync(1, 8 * 32);  // nobody stages output any more (a warp without units would otherwise get here early)
+      double2* sh = reinterpret_cast<double2*>(out_stage);
+      sh[(warp - 4) * 32 + lane] = make_double2(gn_s, gn_q);
+      named_bar_sync(1, 8 * 32);
+      if (warp == 4) {
+        double s = 0.0, q = 0.0;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) {
+          s += sh[w8 * 32 + lane].x;
+          q += sh[w8 * 32 + lane].y;
+        }
+        cv.gn_part[static_cast<size_t>(blockIdx.x) * 32 + lane] = make_double2(s, q);
+      }
+    }
   }
 
   if (warp >= 4 && lane == 0) bulk_wait_group<0>();
@@ -259,9 +331,48 @@ conv2_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
   }
 }
 
+// Folds the per-warp partials of the convolution's epilogue into (mean, rstd) per group: fp64, fixed order (lanes stride
+// over the partials, xor tree), one block.
+__global__ void __launch_bounds__(1024) conv_gn_finalize_kernel(const double2* __restrict__ part, int nparts, int groups,
+                                                                double count, float eps, float* __restrict__ stats) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;  // one warp per group
+  if (g >= groups) return;
+  double s = 0.0, q = 0.0;
+  int i = lane;
+  for (; i + 3 * 32 < nparts; i += 4 * 32) {  // four partials requested per trip
+    double2 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = part[static_cast<size_t>(i + k * 32) * 32 + g];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      s += v[k].x;
+      q += v[k].y;
+    }
+  }
+  for (; i < nparts; i += 32) {
+    const double2 v = part[static_cast<size_t>(i) * 32 + g];
+    s += v.x;
+    q += v.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane == 0) {
+    const double mean = s / count;
+    double var = q / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[2 * g] = static_cast<float>(mean);
+    stats[2 * g + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+}
+
 template <int EPI>
 static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tc, const CUtensorMap& tb, const CUtensorMap& to,
-                       const GemmDev& p, const ConvDev& cv, int bn, cudaStream_t stream) {
+                       const GemmDev& p, const ConvDev& cv, int bn, cudaStream_t stream, int* grid_out) {
   static bool attr_set = false;
   auto kern = conv2_bf16_kernel<EPI>;
   if (!attr_set) {
@@ -272,6 +383,7 @@ static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tc, const CUten
   const int clusters = sm_count() / 2;
   const int grid = 2 * (tiles < clusters ? tiles : clusters);
   ORVB_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(g2_threads(EPI)), G2_SMEM_BYTES, stream, true, tx, tc, tb, to, p, cv, bn));
+  if (grid_out != nullptr) *grid_out = grid;
   return ORVB_OK;
 }
 
@@ -330,6 +442,35 @@ extern "C" int orvb_conv_cl(const orvb_conv_args* a, void* stream) {
   d.tma_store = tma_store ? 1 : 0;
   d.out_f32 = a->out_f32 ? 1 : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (epi == ORVB_EPI_GATE_RESID) return launch_conv<ORVB_EPI_GATE_RESID>(tx, tc, tb, to, d, cv, bn, st);
-  return launch_conv<ORVB_EPI_BIAS>(tx, tc, tb, to, d, cv, bn, st);
+  cv.gn_gs_log2 = -1;
+  cv.gn_part = nullptr;
+  if (a->gn_stats != nullptr) {
+    const int gs = a->gn_groups > 0 ? a->c_out / a->gn_groups : 0;
+    ORVB_REQUIRE(a->gn_groups > 0 && a->gn_groups <= 32 && gs * a->gn_groups == a->c_out && gs >= 2 && gs <= 64 &&
+                     (gs & (gs - 1)) == 0 && a->c_out % 64 == 0,
+                 ORVB_ESHAPE, "orvb_conv_cl: fused GroupNorm statistics need c_out %% 64 == 0, <= 32 groups of 2..64 "
+                 "(power of two) channels; got c_out %d, %d groups", a->c_out, a->gn_groups);
+    ORVB_REQUIRE(a->gn_scratch != nullptr && reinterpret_cast<uintptr_t>(a->gn_scratch) % 16 == 0, ORVB_EINVAL,
+                 "orvb_conv_cl: gn_scratch (orvb_conv_gn_scratch_bytes(), 16-byte aligned) is required with gn_stats");
+    ORVB_REQUIRE(!a->out_f32, ORVB_EINVAL, "orvb_conv_cl: gn_stats describes the bf16 output (not available with out_f32)");
+    int l2 = 0;
+    while ((1 << l2) < gs) ++l2;
+    cv.gn_gs_log2 = l2;
+    cv.gn_part = static_cast<double2*>(a->gn_scratch);
+  }
+  int grid = 0;
+  rc = (epi == ORVB_EPI_GATE_RESID) ? launch_conv<ORVB_EPI_GATE_RESID>(tx, tc, tb, to, d, cv, bn, st, &grid)
+                                    : launch_conv<ORVB_EPI_BIAS>(tx, tc, tb, to, d, cv, bn, st, &grid);
+  if (rc != ORVB_OK) return rc;
+  if (a->gn_stats != nullptr) {
+    const double count = static_cast<double>(pixels) * (a->c_out / a->gn_groups);
+    ORVB_CHECK_CUDA(launch_kernel(conv_gn_finalize_kernel, dim3(1), dim3(1024), 0, st, true,
+                                  static_cast<const double2*>(a->gn_scratch), grid, static_cast<int>(a->gn_groups), count,
+                                  a->gn_eps, a->gn_stats));
+  }
+  return ORVB_OK;
+}
+
+extern "C" size_t orvb_conv_gn_scratch_bytes(void) {
+  return static_cast<size_t>(orvb::sm_count() > 0 ? orvb::sm_count() : 160) * 32 * sizeof(double2);
 }

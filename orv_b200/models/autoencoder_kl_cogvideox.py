@@ -9,8 +9,9 @@ reference (`encode_dataset.py`, SURVEY §2 out of scope) and is not built: `enco
 
 Arithmetic: liborv_b200.so only.  Activations live channels-last ([T, H, W, C] bf16, one sample — the reference decodes
 sample by sample as well: slicing); every causal convolution is an implicit GEMM on tcgen05 (`orvb_conv_cl`: the 3x3x3
-taps are TMA boxes of the activation tensor shifted by the tap offset, zero-filled at the borders), every
-SpatialNorm3D + SiLU is one fused pass (`orvb_gn_stats_cl` + `orvb_spatial_norm_cl`) whose conv_y / conv_b branches are
+taps are TMA boxes of the activation tensor shifted by the tap offset, zero-filled at the borders; its epilogue also
+accumulates the GroupNorm statistics of its output), every SpatialNorm3D + SiLU is one fused pass
+(`orvb_spatial_norm_cl`; `orvb_gn_stats_cl` only where no convolution produced the tensor) whose conv_y / conv_b branches are
 evaluated once per LATENT pixel for all 37 norm sites of a frame batch by a single GEMM and looked up through the
 nearest-neighbour map, and the residual add rides in the second convolution's epilogue.  What stays in torch is layout
 plumbing on tiny tensors (latent tile -> channels-last, tile blending / concatenation of the decoded frames).
@@ -313,12 +314,16 @@ class AutoencoderKLCogVideoX(nn.Module):
     # ------------------------------------------------------------------------------------------------------
     # decoder (one tile of one sample, one frame batch)
     # ------------------------------------------------------------------------------------------------------
-    def _conv(self, P, name, x, cache: dict, resid=None):
+    def _conv(self, P, name, x, cache: dict, resid=None, stats: bool = False):
+        """One convolution; stats=True also returns the GroupNorm statistics of its output (accumulated in the epilogue:
+        the SpatialNorm3D that follows needs no pass of its own over the tensor)."""
         w, b, ker = P["conv"][name]
         kt = ker[0]
         prev = cache.get(name) if kt > 1 else None
-        y = ops.conv_cl(x, w, b, ker, cache=prev, resid=resid)
-        self.last_launches += 1
+        fuse = stats and os.environ.get("ORVB_VAE_FUSE_GN", "1") != "0" and w.shape[0] % 64 == 0 and (w.shape[0] // self.config.norm_num_groups) in (2, 4, 8, 16, 32, 64) \
+            and self.config.norm_num_groups <= 32
+        y = ops.conv_cl(x, w, b, ker, cache=prev, resid=resid, gn=(self.config.norm_num_groups, 1e-6) if fuse else None)
+        self.last_launches += 2 if fuse else 1
         if kt > 1:
             # CogVideoXCausalConv3d: the cache is the last kt-1 frames of [context | x]
             if x.shape[0] >= kt - 1:
@@ -326,16 +331,20 @@ class AutoencoderKLCogVideoX(nn.Module):
             else:
                 ctx = prev if prev is not None else x[:1].expand(kt - 1, *x.shape[1:])
                 cache[name] = torch.cat([ctx, x], 0)[-(kt - 1):].contiguous()
+        if stats:
+            return y if fuse else (y, None)
         return y
 
-    def _norm_act(self, P, name, x, table, t_lat, lat_hw, act=1):
+    def _norm_act(self, P, name, x, table, t_lat, lat_hw, act=1, stats=None):
         ent = P["norm"][name]
         g = self.config.norm_num_groups
-        stats = ops.gn_stats_cl(x, g, 1e-6)
+        if stats is None:
+            stats = ops.gn_stats_cl(x, g, 1e-6)
+            self.last_launches += 1
         T, H = x.shape[0], x.shape[1]
         shift = int(round(math.log2(H / lat_hw[0]))) if H >= lat_hw[0] else 0
         t_src = self._map(spatial_norm_frame_map(T, t_lat))
-        self.last_launches += 2
+        self.last_launches += 1
         return ops.spatial_norm_cl(x, stats, ent["gamma"], ent["beta"], table, ent["y_off"], ent["b_off"], t_src, lat_hw,
                                    shift, groups=g, act=act)
 
@@ -349,30 +358,35 @@ class AutoencoderKLCogVideoX(nn.Module):
         table = ops.gemm(z64.view(-1, 64), P["table_w"], P["table_b"])
         self.last_launches += 1
         lat = (h, w)
-        x = self._conv(P, "decoder.conv_in", z64, cache)
+        x, xs = self._conv(P, "decoder.conv_in", z64, cache, stats=True)
         rev = tuple(reversed(c.block_out_channels))
         compress_level = int(np.log2(c.temporal_compression_ratio))
 
-        def resnet(name, cin, cout, x):
-            hdn = self._norm_act(P, f"{name}.norm1", x, table, Tb, lat)
-            hdn = self._conv(P, f"{name}.conv1", hdn, cache)
-            hdn = self._norm_act(P, f"{name}.norm2", hdn, table, Tb, lat)
+        def resnet(name, cin, cout, x, xs, want_stats=True):
+            hdn = self._norm_act(P, f"{name}.norm1", x, table, Tb, lat, stats=xs)
+            hdn, hs = self._conv(P, f"{name}.conv1", hdn, cache, stats=True)
+            hdn = self._norm_act(P, f"{name}.norm2", hdn, table, Tb, lat, stats=hs)
             if cin != cout:
                 x = self._conv(P, f"{name}.conv_shortcut", x, cache)
-            return self._conv(P, f"{name}.conv2", hdn, cache, resid=x)
+            if want_stats:
+                return self._conv(P, f"{name}.conv2", hdn, cache, resid=x, stats=True)
+            return self._conv(P, f"{name}.conv2", hdn, cache, resid=x), None
 
         for i in range(2):
-            x = resnet(f"decoder.mid_block.resnets.{i}", rev[0], rev[0], x)
+            x, xs = resnet(f"decoder.mid_block.resnets.{i}", rev[0], rev[0], x, xs)
         cout = rev[0]
         for b, ch in enumerate(rev):
             cin, cout = cout, ch
+            last_block = b == len(rev) - 1
             for i in range(c.layers_per_block + 1):
-                x = resnet(f"decoder.up_blocks.{b}.resnets.{i}", cin if i == 0 else cout, cout, x)
-            if b != len(rev) - 1:
+                # the last resnet of a block feeds the upsampler, which has no norm: no statistics needed there
+                need = last_block or i < c.layers_per_block
+                x, xs = resnet(f"decoder.up_blocks.{b}.resnets.{i}", cin if i == 0 else cout, cout, x, xs, want_stats=need)
+            if not last_block:
                 x = ops.upsample2x_cl(x, self._map(upsample_frame_map(x.shape[0], b < compress_level)))
                 self.last_launches += 1
-                x = self._conv(P, f"decoder.up_blocks.{b}.upsamplers.0", x, cache)
-        x = self._norm_act(P, "decoder.norm_out", x, table, Tb, lat)
+                x, xs = self._conv(P, f"decoder.up_blocks.{b}.upsamplers.0", x, cache, stats=True)
+        x = self._norm_act(P, "decoder.norm_out", x, table, Tb, lat, stats=xs)
         x = self._conv(P, "decoder.conv_out", x, cache)
         self.last_launches += 1
         return ops.cl_to_planar(x, c.out_channels)

@@ -164,10 +164,16 @@ def unpatchify(y: torch.Tensor, B: int, F: int, Cc: int, H: int, W: int, p: int,
 # ---------------------------------------------------------------------------------------------------------------
 # 3-D VAE decode operators (channels-last bf16 [T, H, W, C], one sample) — include/orv_b200.h, "3-D VAE decode"
 # ---------------------------------------------------------------------------------------------------------------
+_conv_gn_scratch: dict = {}
+
+
 def conv_cl(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], kernel, *, cache: Optional[torch.Tensor] = None,
-            resid: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out_f32: bool = False) -> torch.Tensor:
+            resid: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out_f32: bool = False,
+            gn: Optional[tuple] = None):
     """Causal convolution (implicit GEMM).  x [T, H, W, c_in] bf16, w [c_out, kt*kh*kw*c_in] bf16 (tap-major),
-    kernel = (kt, kh, kw); cache [kt-1, H, W, c_in] = the frames in front of x (None: frame 0 repeated)."""
+    kernel = (kt, kh, kw); cache [kt-1, H, W, c_in] = the frames in front of x (None: frame 0 repeated).
+    gn = (groups, eps): also returns the GroupNorm statistics [groups, 2] of the output, accumulated in the epilogue
+    (result = (out, stats))."""
     _req(x, torch.bfloat16, "x")
     _req(w, torch.bfloat16, "w")
     T, H, W, cin = x.shape
@@ -195,8 +201,19 @@ def conv_cl(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], kern
     a.frames, a.height, a.width, a.c_in, a.c_out = T, H, W, cin, cout
     a.kt, a.kh, a.kw = kt, kh, kw
     a.out_f32 = int(out_f32)
-    L.check(L.load().orvb_conv_cl(C.byref(a), L.current_stream()), "orvb_conv_cl")
-    return out
+    lib = L.load()
+    stats = None
+    if gn is not None:
+        key = (x.device, torch.cuda.current_stream().cuda_stream)
+        scratch = _conv_gn_scratch.get(key)
+        if scratch is None:
+            scratch = torch.empty(lib.orvb_conv_gn_scratch_bytes() + 16, dtype=torch.uint8, device=x.device)
+            _conv_gn_scratch[key] = scratch
+        stats = torch.empty((gn[0], 2), dtype=torch.float32, device=x.device)
+        a.gn_stats, a.gn_scratch = stats.data_ptr(), (scratch.data_ptr() + 15) // 16 * 16
+        a.gn_groups, a.gn_eps = int(gn[0]), float(gn[1])
+    L.check(lib.orvb_conv_cl(C.byref(a), L.current_stream()), "orvb_conv_cl")
+    return out if gn is None else (out, stats)
 
 
 _gn_scratch: dict = {}

@@ -87,6 +87,29 @@ def test_conv_cl_f32(ops, T, H, W, cin, cout, ker, cache, resid):
     assert torch.equal(out16, out.bfloat16())
 
 
+@pytest.mark.parametrize("T,H,W,cin,cout,resid", [(3, 13, 21, 64, 128, False), (2, 30, 45, 128, 256, True),
+                                                  (5, 60, 90, 64, 512, True), (1, 9, 17, 64, 64, False)])
+def test_conv_cl_fused_groupnorm_stats(ops, T, H, W, cin, cout, resid):
+    """Statistics accumulated in the convolution's epilogue = statistics of the tensor it stored (what orvb_gn_stats_cl
+    computes from that tensor), deterministic, and the output itself is unchanged by asking for them."""
+    torch.manual_seed(cout + T)
+    x = _bf(T, H, W, cin, k=0.5)
+    w = _bf(cout, cin, 3, 3, 3, k=(27 * cin) ** -0.5)
+    b = _bf(cout, k=0.3) + 0.2
+    r = _bf(T, H, W, cout) if resid else None
+    plain = ops.conv_cl(x, _pack_w(w), b, (3, 3, 3), resid=r)
+    out, st = ops.conv_cl(x, _pack_w(w), b, (3, 3, 3), resid=r, gn=(32, 1e-6))
+    assert torch.equal(out, plain)
+    want = ops.gn_stats_cl(out, 32, 1e-6)
+    _close(st[:, 0], want[:, 0], 1e-5, 1e-6)
+    _close(st[:, 1], want[:, 1], 1e-5, 1e-6)
+    xd = out.double().reshape(-1, 32, cout // 32)
+    _close(st[:, 0], xd.mean(dim=(0, 2)), 1e-5, 1e-6)
+    _close(st[:, 1], (xd.var(dim=(0, 2), unbiased=False) + 1e-6).rsqrt(), 1e-5, 1e-6)
+    out2, st2 = ops.conv_cl(x, _pack_w(w), b, (3, 3, 3), resid=r, gn=(32, 1e-6))
+    assert torch.equal(st, st2) and torch.equal(out, out2)
+
+
 def test_conv_cl_resid_in_place(ops):
     """conv2 of a resnet block writes over its residual input."""
     torch.manual_seed(3)
