@@ -14,6 +14,8 @@
 // Everything else — 6-stage ring, cta_group::2 MMAs of M = 256 (two patches per cluster), two TMEM accumulators, eight
 // epilogue warps, swizzled staging + TMA store (a {64, 16, 2, 1} box per warp and 64-column unit, clipped at the image
 // border) — is the GEMM kernel's structure (gemm.cu); the fused epilogues are the shared ones (bias, bias + residual).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "gemm_common.cuh"
 #include "ptx.cuh"
@@ -34,6 +36,20 @@ struct ConvDev {
 };
 
 constexpr int CV_PH = 8, CV_PW = 16;  // patch = 8 rows x 16 columns = 128 pixels = one M tile
+
+// "Halo" variant for 3 x 3 spatial taps and C_out <= 128.  With N = 128 a K step of the plain kernel moves 24 KB of fills
+// + 24 KB of operand reads through a CTA's shared memory in the 256 clk its MMAs take = 192 B/clk against the 128 B/clk
+// the SM has: those layers (42 % of the decoder's FLOPs) ran at 65 % of the tensor peak.  Here the M tile is a 16 x 8
+// patch (16 image rows of 8 pixels = 16 eight-row core groups of 1024 bytes), and ONE TMA box of 18 rows x 8 pixels per
+// (temporal tap, 64-channel chunk, horizontal tap) serves the three vertical taps: the A operand of vertical tap dh is
+// the same shared-memory tile read from row dh on — a descriptor start address moved by dh x 1024 bytes, which keeps the
+// 128-byte swizzle phase, so nothing but the standard descriptor is needed.  A fills drop from 16 to 6 KB per tap.
+constexpr int CH_PH = 16, CH_PW = 8;
+constexpr int CH_STAGES = 4;
+constexpr int CH_A_BYTES = (CH_PH + 2) * CH_PW * 128;      // 18 KB: rows h0 - 1 .. h0 + 16 of the patch's 8 columns
+constexpr int CH_B_SLOT = 64 * 128;                        // 8 KB: this CTA's <= 64 weight rows of one tap
+constexpr int CH_STAGE_BYTES = CH_A_BYTES + 3 * CH_B_SLOT;  // 42 KB
+constexpr int CH_SMEM_BYTES = CH_STAGES * CH_STAGE_BYTES + G2_OUT_STAGE_BYTES + 1024 + 256;
 
 __device__ __forceinline__ float cv_warp_sum(float v) {
 #pragma unroll
@@ -69,15 +85,17 @@ __device__ __forceinline__ void cv_gn_unit(const float (&v)[64], bool valid, int
   }
 }
 
-template <int EPI>
+template <int EPI, bool HALO>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2_threads(EPI), 1)
 conv2_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_c,
                   const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_o, const GemmDev p,
                   const ConvDev cv, const int bn) {
-  constexpr int STAGES = G2_STAGES;
+  constexpr int STAGES = HALO ? CH_STAGES : G2_STAGES;
+  constexpr int STAGE_BYTES = HALO ? CH_STAGE_BYTES : G2_STAGE_BYTES;
+  constexpr int PH = HALO ? CH_PH : CV_PH, PW = HALO ? CH_PW : CV_PW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* out_stage = smem + STAGES * G2_STAGE_BYTES;
+  uint8_t* out_stage = smem + STAGES * STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + G2_OUT_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
@@ -90,7 +108,8 @@ conv2_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;  // num_m_tiles counts patch PAIRS
-  const int num_k = cv.KT * cv.KH * cv.KW * cv.kc;
+  // K steps per tile: one per (tap, channel chunk); the halo variant handles the three vertical taps of a step together
+  const int num_k = HALO ? cv.KT * cv.KW * cv.kc : cv.KT * cv.KH * cv.KW * cv.kc;
   const int half_bn = bn >> 1;
 
   pdl_launch_dependents();
@@ -128,8 +147,8 @@ conv2_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
     const int pp = patch < cv.num_patches ? patch : 0;
     t = pp / (cv.HB * cv.WB);
     const int r = pp - t * (cv.HB * cv.WB);
-    h0 = (r / cv.WB) * CV_PH;
-    w0 = (r % cv.WB) * CV_PW;
+    h0 = (r / cv.WB) * PH;
+    w0 = (r % cv.WB) * PW;
     return patch < cv.num_patches;
   };
 
@@ -137,17 +156,61 @@ conv2_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
     // ================================ TMA producer (both CTAs) ================================
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t stage_tx = 2u * static_cast<uint32_t>(G2_A_BYTES + half_bn * BK * 2);
+    const uint32_t stage_tx = HALO ? 2u * static_cast<uint32_t>(CH_A_BYTES + 3 * half_bn * BK * 2)
+                                   : 2u * static_cast<uint32_t>(G2_A_BYTES + half_bn * BK * 2);
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m_blk = tile % p.num_m_tiles;
       const int n_blk = tile / p.num_m_tiles;
       int t, h0, w0;
       const bool live = patch_of(m_blk, t, h0, w0);
       const int b_row = n_blk * bn + static_cast<int>(rank) * half_bn;
+      if (HALO) {
+        // step order: temporal tap, channel chunk, horizontal tap; the three vertical taps share the step's A tile
+        int kt_i = 0, cc = 0, kw_i = 0;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + CH_A_BYTES;
+          const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          int ts = t + kt_i - (cv.KT - 1);
+          const CUtensorMap* mp = &tma_x;
+          if (ts < 0) {
+            if (cv.has_cache) {
+              mp = &tma_c;
+              ts += cv.KT - 1;
+            } else {
+              ts = 0;
+            }
+          }
+          if (!live) ts = cv.T + cv.KT;  // out of bounds in either map: zero fill
+          if (elect_one()) {
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], stage_tx);
+            tma_load_4d_pair(sa, mp, leader_full, cc * BK, w0 + kw_i - 1, h0 - 1, ts);
+#pragma unroll
+            for (int kh_i = 0; kh_i < 3; ++kh_i) {
+              const int tap = (kt_i * 3 + kh_i) * 3 + kw_i;
+              tma_load_2d_pair(sb + kh_i * CH_B_SLOT, &tma_b, leader_full, (tap * cv.kc + cc) * BK, b_row);
+            }
+          }
+          __syncwarp();
+          if (++kw_i == 3) {
+            kw_i = 0;
+            if (++cc == cv.kc) {
+              cc = 0;
+              ++kt_i;
+            }
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        continue;
+      }
       int tap = 0, cc = 0;
       for (int kb = 0; kb < num_k; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * G2_STAGE_BYTES;
+        uint8_t* sa = smem + stage * STAGE_BYTES;
         uint8_t* sb = sa + G2_A_BYTES;
         const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
         const int kt_i = tap / (cv.KH * cv.KW);
@@ -194,17 +257,35 @@ conv2_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
       for (int kb = 0; kb < num_k; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * G2_STAGE_BYTES);
-        const uint64_t a_desc = umma_desc_sw128(sa);
-        const uint64_t b_desc = umma_desc_sw128(sa + G2_A_BYTES);
-        if (elect_one()) {
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        if (HALO) {
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            umma_f16_ss_pair(d_tmem, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc,
-                             static_cast<uint32_t>((kb | k) != 0));
+            for (int kh_i = 0; kh_i < 3; ++kh_i) {
+              // vertical tap kh_i: the patch's rows start kh_i image rows (= kh_i x 1024 bytes) into the haloed tile
+              const uint64_t a_desc = umma_desc_sw128(sa + kh_i * (CH_PW * 128));
+              const uint64_t b_desc = umma_desc_sw128(sa + CH_A_BYTES + kh_i * CH_B_SLOT);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                umma_f16_ss_pair(d_tmem, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc,
+                                 static_cast<uint32_t>((kb | kh_i | k) != 0));
+              }
+            }
+            tc_commit_pair(&empty_bar[stage], 3);
+            if (kb == num_k - 1) tc_commit_pair(&tfull_bar[acc], 3);
           }
-          tc_commit_pair(&empty_bar[stage], 3);
-          if (kb == num_k - 1) tc_commit_pair(&tfull_bar[acc], 3);
+        } else {
+          const uint64_t a_desc = umma_desc_sw128(sa);
+          const uint64_t b_desc = umma_desc_sw128(sa + G2_A_BYTES);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              umma_f16_ss_pair(d_tmem, a_desc + static_cast<uint64_t>(k * 2), b_desc + static_cast<uint64_t>(k * 2), idesc,
+                               static_cast<uint32_t>((kb | k) != 0));
+            }
+            tc_commit_pair(&empty_bar[stage], 3);
+            if (kb == num_k - 1) tc_commit_pair(&tfull_bar[acc], 3);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -221,7 +302,7 @@ conv2_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
     // ================================ epilogue (both CTAs) ====================================
     constexpr int EW = g2_epi_warps(EPI);
     constexpr int NBUF = 8 / EW;
-    const int ew = (warp - 4) & 3;         // TMEM lane quarter = patch rows 2 ew, 2 ew + 1
+    const int ew = (warp - 4) & 3;         // TMEM lane quarter = patch rows 2 ew, 2 ew + 1 (halo variant: 4 ew .. 4 ew + 3)
     const int unit_par = (warp - 4) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -235,10 +316,11 @@ conv2_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
       const bool live = patch_of(m_blk, t, h0, w0);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int hh = h0 + 2 * ew + (lane >> 4), ww = w0 + (lane & 15);
+      const int hq = h0 + (HALO ? 4 : 2) * ew;                              // first image row of this lane quarter
+      const int hh = hq + (HALO ? (lane >> 3) : (lane >> 4)), ww = w0 + (HALO ? (lane & 7) : (lane & 15));
       const bool pix_ok = live && hh < cv.H && ww < cv.W;
       const int row = pix_ok ? (t * cv.H + hh) * cv.W + ww : p.M;          // linear pixel index (row of out / resid)
-      const bool warp_ok = live && (h0 + 2 * ew) < cv.H;                    // warp-uniform: any row of mine inside?
+      const bool warp_ok = live && hq < cv.H;                               // warp-uniform: any row of mine inside?
       const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * G2_ACC_COLS) + (static_cast<uint32_t>(ew * 32) << 16);
 #pragma unroll 1
       for (int c = 0; c < bn; c += 64) {
@@ -287,7 +369,7 @@ conv2_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_4d(&tma_o, sbuf, n0, w0, h0 + 2 * ew, t);
+            tma_store_4d(&tma_o, sbuf, n0, w0, hq, t);
             bulk_commit_group();
           }
           ++stores;
@@ -370,19 +452,20 @@ __global__ void __launch_bounds__(1024) conv_gn_finalize_kernel(const double2* _
   }
 }
 
-template <int EPI>
+template <int EPI, bool HALO>
 static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tc, const CUtensorMap& tb, const CUtensorMap& to,
                        const GemmDev& p, const ConvDev& cv, int bn, cudaStream_t stream, int* grid_out) {
   static bool attr_set = false;
-  auto kern = conv2_bf16_kernel<EPI>;
+  auto kern = conv2_bf16_kernel<EPI, HALO>;
+  constexpr int SMEM = HALO ? CH_SMEM_BYTES : G2_SMEM_BYTES;
   if (!attr_set) {
-    ORVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+    ORVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int clusters = sm_count() / 2;
   const int grid = 2 * (tiles < clusters ? tiles : clusters);
-  ORVB_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(g2_threads(EPI)), G2_SMEM_BYTES, stream, true, tx, tc, tb, to, p, cv, bn));
+  ORVB_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(g2_threads(EPI)), SMEM, stream, true, tx, tc, tb, to, p, cv, bn));
   if (grid_out != nullptr) *grid_out = grid;
   return ORVB_OK;
 }
@@ -404,20 +487,32 @@ extern "C" int orvb_conv_cl(const orvb_conv_args* a, void* stream) {
   const long long pixels = static_cast<long long>(a->frames) * a->height * a->width;
   ORVB_REQUIRE(pixels < (1ll << 30), ORVB_ESHAPE, "orvb_conv_cl: too many pixels");
   const int K = a->kt * a->kh * a->kw * a->c_in;
+  // 3 x 3 spatial taps and a narrow output: the halo variant (one activation tile per horizontal tap serves the three
+  // vertical taps; see CH_* above).  ORVB_CONV_HALO=0 keeps the plain kernel (A/B measurements).
+  static int halo_env = -1;
+  if (halo_env < 0) {
+    const char* e = getenv("ORVB_CONV_HALO");
+    halo_env = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  const bool halo = halo_env && a->kh == 3 && a->kw == 3 && a->c_out <= 128;
+  const int ph = halo ? CH_PH : CV_PH, pw = halo ? CH_PW : CV_PW;
   ConvDev cv;
   cv.T = a->frames; cv.H = a->height; cv.W = a->width;
-  cv.HB = (a->height + CV_PH - 1) / CV_PH; cv.WB = (a->width + CV_PW - 1) / CV_PW;
+  cv.HB = (a->height + ph - 1) / ph; cv.WB = (a->width + pw - 1) / pw;
   cv.KT = a->kt; cv.KH = a->kh; cv.KW = a->kw; cv.kc = a->c_in / 64;
   cv.num_patches = cv.T * cv.HB * cv.WB;
   cv.has_cache = a->cache != nullptr ? 1 : 0;
   const int epi = a->resid != nullptr ? ORVB_EPI_GATE_RESID : ORVB_EPI_BIAS;
   const int num_m_tiles = (cv.num_patches + 1) / 2;
-  const int bn = gemm_pick_bn_pair(num_m_tiles * 256, a->c_out, epi);
+  int bn = gemm_pick_bn_pair(num_m_tiles * 256, a->c_out, epi);
+  if (halo && bn > 128) bn = 128;
   CUtensorMap tx, tc, tb, to;
-  rc = make_tmap_4d_bf16(&tx, a->x, a->c_in, a->width, a->height, a->frames, CV_PW, CV_PH);
+  // activation boxes: the patch itself, or (halo) the patch's 8 columns with one row of halo above and below
+  const int bw = halo ? CH_PW : CV_PW, bh = halo ? CH_PH + 2 : CV_PH;
+  rc = make_tmap_4d_bf16(&tx, a->x, a->c_in, a->width, a->height, a->frames, bw, bh);
   if (rc != ORVB_OK) return rc;
   if (cv.has_cache) {
-    rc = make_tmap_4d_bf16(&tc, a->cache, a->c_in, a->width, a->height, a->kt - 1, CV_PW, CV_PH);
+    rc = make_tmap_4d_bf16(&tc, a->cache, a->c_in, a->width, a->height, a->kt - 1, bw, bh);
     if (rc != ORVB_OK) return rc;
   } else {
     tc = tx;
@@ -426,7 +521,8 @@ extern "C" int orvb_conv_cl(const orvb_conv_args* a, void* stream) {
   if (rc != ORVB_OK) return rc;
   const bool tma_store = !a->out_f32;
   if (tma_store) {
-    rc = make_tmap_4d_bf16(&to, a->out, a->c_out, a->width, a->height, a->frames, CV_PW, 2);
+    // one epilogue warp stores 32 pixels: 2 rows of 16 (plain) or 4 rows of 8 (halo)
+    rc = make_tmap_4d_bf16(&to, a->out, a->c_out, a->width, a->height, a->frames, pw, halo ? 4 : 2);
     if (rc != ORVB_OK) return rc;
   } else {
     to = tx;
@@ -459,8 +555,12 @@ extern "C" int orvb_conv_cl(const orvb_conv_args* a, void* stream) {
     cv.gn_part = static_cast<double2*>(a->gn_scratch);
   }
   int grid = 0;
-  rc = (epi == ORVB_EPI_GATE_RESID) ? launch_conv<ORVB_EPI_GATE_RESID>(tx, tc, tb, to, d, cv, bn, st, &grid)
-                                    : launch_conv<ORVB_EPI_BIAS>(tx, tc, tb, to, d, cv, bn, st, &grid);
+  if (halo)
+    rc = (epi == ORVB_EPI_GATE_RESID) ? launch_conv<ORVB_EPI_GATE_RESID, true>(tx, tc, tb, to, d, cv, bn, st, &grid)
+                                      : launch_conv<ORVB_EPI_BIAS, true>(tx, tc, tb, to, d, cv, bn, st, &grid);
+  else
+    rc = (epi == ORVB_EPI_GATE_RESID) ? launch_conv<ORVB_EPI_GATE_RESID, false>(tx, tc, tb, to, d, cv, bn, st, &grid)
+                                      : launch_conv<ORVB_EPI_BIAS, false>(tx, tc, tb, to, d, cv, bn, st, &grid);
   if (rc != ORVB_OK) return rc;
   if (a->gn_stats != nullptr) {
     const double count = static_cast<double>(pixels) * (a->c_out / a->gn_groups);
