@@ -46,6 +46,6 @@ print(" | ".join(res), "| checksum", float(o1.float().abs().sum()))
 '''
 for lib in sys.argv[1:]:
     env = dict(os.environ, ORVB_LIB_PATH=lib, ORVB_NO_BUILD="1")
-    for rep in range(2):
+    for rep in range(1 if os.environ.get("NCU_ONCE") else 2):
         r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True, timeout=300)
         print(f"{os.path.basename(lib)}: {r.stdout.strip() or r.stderr.strip()[-400:]}", flush=True)
