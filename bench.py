@@ -543,6 +543,7 @@ def run_ours(args):
     frames_per_step = B * c["frames"]
     tflop_per_step = NUM_INFERENCE_STEPS * c["tflop"] * B
     # ---- device-resident throughput ----
+    out = run(41)  # (always at least one untimed call: graph capture, allocations; also the shape of the result)
     for i in range(args.warmup):
         out = run(42 + i)
     with ClockSampler(local_rank) as clocks:
