@@ -55,6 +55,29 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return ORVB_OK;
 }
 
+// Unswizzled [box_rows x box_cols] boxes (rows packed at box_cols * 2 bytes in shared memory): the narrow last column
+// unit of a GEMM tile whose width is not a multiple of 64.
+int make_tmap_2d_bf16_plain(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                            uint32_t box_rows, uint32_t box_cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return ORVB_ECUDA;
+  ORVB_REQUIRE(box_cols >= 8 && box_cols % 8 == 0 && box_cols <= 128, ORVB_ESHAPE,
+               "tensor map: plain box needs a multiple of 8 columns (got %u)", box_cols);
+  ORVB_REQUIRE(box_rows >= 1 && box_rows <= 256, ORVB_ESHAPE, "tensor map: box rows %u out of range", box_rows);
+  ORVB_REQUIRE((ld * 2) % 16 == 0 && reinterpret_cast<uintptr_t>(base) % 16 == 0, ORVB_ESHAPE,
+               "tensor map: base and row pitch must be 16-byte aligned");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ORVB_REQUIRE(r == CUDA_SUCCESS, ORVB_ECUDA, "cuTensorMapEncodeTiled(2d plain rows=%llu cols=%llu ld=%llu) failed: %d",
+               (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, (int)r);
+  return ORVB_OK;
+}
+
 int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t batch, uint64_t rows, uint64_t cols,
                       uint64_t ld_row, uint64_t ld_batch, uint32_t box_rows, uint32_t box_cols) {
   EncodeTiledFn fn = get_encode_fn();

@@ -43,6 +43,8 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
                       uint32_t box_rows, uint32_t box_cols);
 
 // 3-D variant: [batch, rows, cols] with explicit element strides for rows and batch.
+int make_tmap_2d_bf16_plain(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                            uint32_t box_rows, uint32_t box_cols);
 int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t batch, uint64_t rows, uint64_t cols,
                       uint64_t ld_row, uint64_t ld_batch, uint32_t box_rows, uint32_t box_cols);
 

@@ -348,7 +348,7 @@ conv2_bf16_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_consta
           if (ncols > 64) ncols = 64;
           if (p.N - n0 < ncols) ncols = p.N - n0;
           if (row < p.M) {
-            epilogue_unit<EPI>(p, v, row, n0, ncols, staged ? sbuf + lane * 128 : nullptr, lane & 7);
+            epilogue_unit<EPI, false>(p, v, row, n0, ncols, staged ? sbuf + lane * 128 : nullptr, lane & 7);
           }
         }
         if (cv.gn_gs_log2 >= 0) {  // warp-uniform: statistics of the values just stored, for the next GroupNorm

@@ -217,18 +217,27 @@ __device__ long long* g_gemm_dbg = nullptr;
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2_threads(EPI), 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                  const __grid_constant__ CUtensorMap tma_o, const GemmDev p, const int bn) {
+                  const __grid_constant__ CUtensorMap tma_o, const __grid_constant__ CUtensorMap tma_t, const GemmDev p,
+                  const int bn) {
   constexpr int STAGES = G2_STAGES;
   extern __shared__ uint8_t smem_raw[];
   // Both CTAs of the pair must use identical offsets (the MMA applies the leader's descriptors to the peer's shared
   // memory), which holds because the dynamic shared window starts at the same shared::cta address in every CTA.
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* out_stage = smem + STAGES * G2_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + G2_OUT_STAGE_BYTES);
+  // Plan (host: g2_plan): [stages][output staging][fast epilogue: gate / bias rows][barriers]; a stage holds 16 KB of A
+  // and this CTA's half of B (the full 16 KB unless the host shrank it to make room for the fast epilogue's buffers).
+  // (pointer arithmetic on the __shared__ array, not an integer round trip: the compiler keeps the address space and
+  //  emits LDS / STS instead of generic loads and stores for the epilogue's staging traffic)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int stage_bytes = p.stage_bytes;
+  uint8_t* out_stage = smem + STAGES * stage_bytes;
+  const bool fast_resid = (EPI == ORVB_EPI_GATE_RESID) && p.fast_resid != 0;
+  uint8_t* gstage = out_stage + p.out_stage_bytes;  // fast epilogue only: 4 * units slots of G2_GS_SLOT bytes
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(gstage + (fast_resid ? 4 * ((bn + 63) >> 6) * G2_GS_SLOT : 0));
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* rbar = tempty_bar + 2;  // [8 epilogue warps][2 units]: residual tile landed (fast epilogue)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -245,6 +254,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     if (p.tma_store) tma_prefetch_desc(&tma_o);
+    if (fast_resid && (bn & 63)) tma_prefetch_desc(&tma_t);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -255,6 +265,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       mbar_init(&tfull_bar[i], 1);   // multicast tcgen05.commit
       mbar_init(&tempty_bar[i], 2 * g2_epi_warps(EPI));  // epilogue warps x 2 CTAs (leader's copy is waited on)
     }
+    for (int i = 0; i < 16; ++i) mbar_init(&rbar[i], 1);  // the issuing lane's arrive.expect_tx
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -281,7 +292,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       const int b_row = n_blk * bn + static_cast<int>(rank) * half_bn;
       for (int kb = 0; kb < num_k; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * G2_STAGE_BYTES;
+        uint8_t* sa = smem + stage * stage_bytes;
         uint8_t* sb = sa + G2_A_BYTES;
         const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
         if (elect_one()) {
@@ -313,7 +324,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (tile == cluster_id && kb == 0) G2_STAMP(5);  // first operands landed
-        const uint32_t sa = smem_u32(smem + stage * G2_STAGE_BYTES);
+        const uint32_t sa = smem_u32(smem + stage * stage_bytes);
         const uint64_t a_desc = umma_desc_sw128(sa);
         const uint64_t b_desc = umma_desc_sw128(sa + G2_A_BYTES);
         if (elect_one()) {
@@ -348,6 +359,177 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     uint32_t acc_phase = 0;
     uint32_t stores = 0;  // TMA stores issued by this warp (staging buffer = stores % NBUF)
     uint8_t* my_stage = out_stage + (warp - 4) * (NBUF * 32 * 128);
+    if (fast_resid) {
+      // ---- gated residual written in place (out == resid), everything but the accumulator fetched ahead ----------
+      // The generic path below reads, per thread and AFTER the accumulator has landed, 128 bytes of its own residual
+      // row and 256 bytes of a gate row from global memory: with 64 accumulator registers live the compiler can keep
+      // only a few of those loads in flight, and the unit takes ~6 k clocks, all of it exposed behind the last tile of a
+      // cluster (profiles/r02a_gemm_timeline.log).  Here every 64-column unit of the tile has its own staging tile:
+      // BEFORE waiting for the accumulator the warp's elected lane fetches the [32 x 64] residual tile into it with one
+      // TMA load (same tensor map and swizzle as the output store) and the warp copies the (at most two distinct) gate
+      // rows and the bias of the unit into shared memory.  After the accumulator wait a thread only touches TMEM and
+      // shared memory: out = resid + gate * (acc + bias) is formed in place in the staging tile and written back with
+      // the usual TMA store.  A narrower last unit (tile width not a multiple of 64) goes through a second,
+      // unswizzled tensor map whose box is exactly that wide, so it never touches the neighbouring tile's columns.
+      const int U = (bn + 63) >> 6;
+      const int tail = bn & 63;
+      uint64_t* my_rbar = rbar + (warp - 4) * 2;
+      uint32_t rphase = 0;       // bit i: parity of my_rbar[i]
+      bool stores_out = false;   // this warp has TMA stores whose source reads may still be in flight
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_blk = tile % p.num_m_tiles;
+        const int n_blk = tile / p.num_m_tiles;
+        const int row0 = m_blk * 256 + static_cast<int>(rank) * BM + ew * 32;
+        const int row = row0 + lane;
+        const bool rows_ok = row0 < p.M;  // warp-uniform
+        const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * G2_ACC_COLS) + (static_cast<uint32_t>(ew * 32) << 16);
+        // gate row of this thread's output row; the rows of a warp normally share one or two of them
+        const float* gpl = nullptr;
+        if (p.gate != nullptr && row < p.M) {
+          int sq;
+          int g = row_group(p.rm, row, &sq);
+          if (p.grp_off != nullptr) g += *p.grp_off;
+          const int is_text = (p.rm.seq_len > 0) ? (sq < p.rm.text_len) : 0;
+          gpl = p.gate + static_cast<size_t>(g) * p.gate_ld + (is_text ? p.gate_text_off : p.gate_video_off);
+        }
+        int lv = p.M - 1 - row0;
+        lv = lv > 31 ? 31 : (lv < 0 ? 0 : lv);
+        const float* gA = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(gpl), 0));
+        const float* gB = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(gpl), lv));
+        const bool gate_staged = __all_sync(0xffffffffu, row >= p.M || gpl == gA || gpl == gB);
+        const int gsel = (gpl == gA) ? 0 : 64;
+        if (rows_ok) {
+          if (stores_out) {
+            if (lane == 0) bulk_wait_group_read<0>();  // last tile's stores have read my staging tiles
+            stores_out = false;
+          }
+#pragma unroll 1
+          for (int i = 0; i < 2; ++i) {
+            const int u = unit_par + 2 * i;
+            const int n0 = n_blk * bn + u * 64;
+            if (u >= U || n0 >= p.N) break;  // warp-uniform
+            const bool is_tail = tail != 0 && u == U - 1;
+            uint8_t* buf = out_stage + (ew * U + u) * 4096;
+            if (lane == 0) {
+              mbar_expect_tx(&my_rbar[i], is_tail ? static_cast<uint32_t>(32 * tail * 2) : 4096u);
+              tma_load_2d(buf, is_tail ? &tma_t : &tma_o, &my_rbar[i], n0, row0);
+            }
+            float* gs = reinterpret_cast<float*>(gstage + (ew * U + u) * G2_GS_SLOT);
+            const int cc = n0 + 2 * lane;
+            float2 a2 = make_float2(1.f, 1.f), b2 = make_float2(1.f, 1.f);
+            uint32_t bb = 0;
+            if (cc < p.N) {
+              if (p.gate != nullptr && gate_staged) {
+                a2 = *reinterpret_cast<const float2*>(gA + cc);
+                b2 = *reinterpret_cast<const float2*>(gB + cc);
+              }
+              if (p.bias != nullptr) bb = *reinterpret_cast<const uint32_t*>(p.bias + cc);
+            }
+            reinterpret_cast<float2*>(gs)[lane] = a2;
+            reinterpret_cast<float2*>(gs + 64)[lane] = b2;
+            reinterpret_cast<float2*>(gs + 128)[lane] = make_float2(bf16_lo(bb), bf16_hi(bb));
+          }
+          __syncwarp();
+        }
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        if (warp == 4) {
+          if (tile == cluster_id) G2_STAMP(8);
+          G2_STAMP(10);
+        }
+        if (rows_ok) {
+#pragma unroll 1
+          for (int i = 0; i < 2; ++i) {
+            const int u = unit_par + 2 * i;
+            const int c = u * 64;
+            const int n0 = n_blk * bn + c;
+            if (u >= U || n0 >= p.N) break;  // warp-uniform
+            const bool is_tail = tail != 0 && u == U - 1;
+            uint8_t* buf = out_stage + (ew * U + u) * 4096;
+            const float* gs = reinterpret_cast<const float*>(gstage + (ew * U + u) * G2_GS_SLOT);
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c), r0);
+            tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c + 32), r1);  // may run past bn: still inside the buffer
+            // while the accumulator columns are on their way: this thread's residual row out of the staging tile
+            mbar_wait(&my_rbar[i], (rphase >> i) & 1u);
+            rphase ^= 1u << i;
+            int nchunk = is_tail ? (tail >> 3) : 8;                    // 16-byte pieces of a row
+            if (((p.N - n0) >> 3) < nchunk) nchunk = (p.N - n0) >> 3;  // columns past N: clipped by the store anyway
+            if (row >= p.M) nchunk = 0;
+            uint8_t* rowp = buf + lane * (is_tail ? tail * 2 : 128);
+            uint4 rr[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (j < nchunk) rr[j] = *reinterpret_cast<const uint4*>(rowp + (is_tail ? (j << 4) : ((j ^ (lane & 7)) << 4)));
+            }
+            tmem_ld_wait();
+            {
+              const float* bsrc = gs + 128;
+              const bool has_bias = p.bias != nullptr;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (j < nchunk) {
+                  float4 g0, g1;
+                  if (gate_staged) {  // warp-uniform
+                    g0 = *reinterpret_cast<const float4*>(gs + gsel + j * 8);
+                    g1 = *reinterpret_cast<const float4*>(gs + gsel + j * 8 + 4);
+                  } else {  // three or more gate rows inside 32 output rows (tiny test shapes): straight from global
+                    g0 = *reinterpret_cast<const float4*>(gpl + n0 + j * 8);
+                    g1 = *reinterpret_cast<const float4*>(gpl + n0 + j * 8 + 4);
+                  }
+                  // packed fp32 pairs (FADD2 / FFMA2: the same round-to-nearest results as the scalar fadd / fma of
+                  // the generic epilogue, half the issue slots)
+                  f32x2 x0 = pk2(__uint_as_float(j < 4 ? r0[(j * 8 + 0) & 31] : r1[(j * 8 + 0) & 31]),
+                                 __uint_as_float(j < 4 ? r0[(j * 8 + 1) & 31] : r1[(j * 8 + 1) & 31]));
+                  f32x2 x1 = pk2(__uint_as_float(j < 4 ? r0[(j * 8 + 2) & 31] : r1[(j * 8 + 2) & 31]),
+                                 __uint_as_float(j < 4 ? r0[(j * 8 + 3) & 31] : r1[(j * 8 + 3) & 31]));
+                  f32x2 x2 = pk2(__uint_as_float(j < 4 ? r0[(j * 8 + 4) & 31] : r1[(j * 8 + 4) & 31]),
+                                 __uint_as_float(j < 4 ? r0[(j * 8 + 5) & 31] : r1[(j * 8 + 5) & 31]));
+                  f32x2 x3 = pk2(__uint_as_float(j < 4 ? r0[(j * 8 + 6) & 31] : r1[(j * 8 + 6) & 31]),
+                                 __uint_as_float(j < 4 ? r0[(j * 8 + 7) & 31] : r1[(j * 8 + 7) & 31]));
+                  if (has_bias) {
+                    const float4 b0 = *reinterpret_cast<const float4*>(bsrc + j * 8);
+                    const float4 b1 = *reinterpret_cast<const float4*>(bsrc + j * 8 + 4);
+                    x0 = add2p(x0, pk2(b0.x, b0.y)); x1 = add2p(x1, pk2(b0.z, b0.w));
+                    x2 = add2p(x2, pk2(b1.x, b1.y)); x3 = add2p(x3, pk2(b1.z, b1.w));
+                  }
+                  x0 = fma2p(x0, pk2(g0.x, g0.y), pk2(bf16_lo(rr[j].x), bf16_hi(rr[j].x)));
+                  x1 = fma2p(x1, pk2(g0.z, g0.w), pk2(bf16_lo(rr[j].y), bf16_hi(rr[j].y)));
+                  x2 = fma2p(x2, pk2(g1.x, g1.y), pk2(bf16_lo(rr[j].z), bf16_hi(rr[j].z)));
+                  x3 = fma2p(x3, pk2(g1.z, g1.w), pk2(bf16_lo(rr[j].w), bf16_hi(rr[j].w)));
+                  float lo, hi;
+                  uint4 o;
+                  upk2(x0, lo, hi); o.x = pack_bf16(lo, hi);
+                  upk2(x1, lo, hi); o.y = pack_bf16(lo, hi);
+                  upk2(x2, lo, hi); o.z = pack_bf16(lo, hi);
+                  upk2(x3, lo, hi); o.w = pack_bf16(lo, hi);
+                  sts128_nobarrier(rowp + (is_tail ? (j << 4) : ((j ^ (lane & 7)) << 4)), o);
+                }
+              }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(is_tail ? &tma_t : &tma_o, buf, n0, row0);
+              bulk_commit_group();
+            }
+            stores_out = true;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+        if (warp == 4) {
+          if (tile == cluster_id) G2_STAMP(9);
+          G2_STAMP(11);
+          G2_STAMP_VALUE(14, (tile - cluster_id) / num_clusters + 1);
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    } else
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m_blk = tile % p.num_m_tiles;
       const int n_blk = tile / p.num_m_tiles;
@@ -416,7 +598,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   }
 
   // ---- teardown: nobody may exit (or free TMEM) while the peer can still touch this CTA's memory ----
-  if (warp >= 4 && lane == 0) bulk_wait_group<0>();  // staged output tiles fully written
+  // (the staged output tiles must have been READ out of shared memory before the CTA may go away; the writes
+  //  themselves complete like any other store before the grid counts as finished)
+  if (warp >= 4 && lane == 0) bulk_wait_group_read<0>();
   if (warp == 4) G2_STAMP(12);  // this warp's output stores complete
   tc_fence_before();
   cluster_sync_all();
@@ -447,29 +631,37 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmD
   return ORVB_OK;
 }
 
+// Shared-memory bytes of a CTA-pair launch with this plan (mirrors the pointer arithmetic at the top of the kernel).
+static int g2_smem_bytes(const GemmDev& p, int bn) {
+  const int gs = p.fast_resid ? 4 * ((bn + 63) / 64) * G2_GS_SLOT : 0;
+  return 1024 + G2_STAGES * p.stage_bytes + p.out_stage_bytes + gs + G2_BAR_BYTES;
+}
+
 template <int EPI>
-static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmDev& p, int bn,
-                        cudaStream_t stream) {
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tt,
+                        const GemmDev& p, int bn, cudaStream_t stream) {
   static bool attr_set = false;
   auto kern = gemm2_bf16_kernel<EPI>;
   if (!attr_set) {
-    ORVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+    ORVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_MAX));
     attr_set = true;
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int clusters = sm_count() / 2;
   const int grid = 2 * (tiles < clusters ? tiles : clusters);
-  ORVB_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(g2_threads(EPI)), G2_SMEM_BYTES, stream, true, ta, tb, to, p, bn));
+  const int smem = g2_smem_bytes(p, bn);
+  ORVB_REQUIRE(smem <= G2_SMEM_MAX, ORVB_EINVAL, "gemm: shared-memory plan of %d bytes does not fit", smem);
+  ORVB_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(g2_threads(EPI)), smem, stream, true, ta, tb, to, tt, p, bn));
   return ORVB_OK;
 }
 
-static int launch_gemm2_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmDev& p,
-                            int bn, cudaStream_t stream) {
+static int launch_gemm2_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
+                            const CUtensorMap& tt, const GemmDev& p, int bn, cudaStream_t stream) {
   switch (epi) {
-    case ORVB_EPI_BIAS: return launch_gemm2<ORVB_EPI_BIAS>(ta, tb, to, p, bn, stream);
-    case ORVB_EPI_GELU: return launch_gemm2<ORVB_EPI_GELU>(ta, tb, to, p, bn, stream);
-    case ORVB_EPI_GATE_RESID: return launch_gemm2<ORVB_EPI_GATE_RESID>(ta, tb, to, p, bn, stream);
-    case ORVB_EPI_QKV: return launch_gemm2<ORVB_EPI_QKV>(ta, tb, to, p, bn, stream);
+    case ORVB_EPI_BIAS: return launch_gemm2<ORVB_EPI_BIAS>(ta, tb, to, tt, p, bn, stream);
+    case ORVB_EPI_GELU: return launch_gemm2<ORVB_EPI_GELU>(ta, tb, to, tt, p, bn, stream);
+    case ORVB_EPI_GATE_RESID: return launch_gemm2<ORVB_EPI_GATE_RESID>(ta, tb, to, tt, p, bn, stream);
+    case ORVB_EPI_QKV: return launch_gemm2<ORVB_EPI_QKV>(ta, tb, to, tt, p, bn, stream);
   }
   set_error("orvb_gemm_bf16: unknown epilogue %d", epi);
   return ORVB_EINVAL;
@@ -486,6 +678,11 @@ static int launch_gemm_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb
   }
   set_error("orvb_gemm_bf16: unknown epilogue %d", epi);
   return ORVB_EINVAL;
+}
+
+static bool fast_resid_enabled() {
+  const char* e = getenv("ORVB_GEMM_FAST_RESID");  // read per call: the tests switch it inside one process
+  return !(e != nullptr && e[0] == '0');
 }
 
 // Picks the N tile that minimises (waves x tile cost) on this GPU for a persistent 1-CTA/SM launch.
@@ -537,9 +734,9 @@ int gemm_pick_bn_pair(int m, int n, int epi) {
 }
 
 // bn > 0: 1-CTA kernel with that N tile; bn < 0: CTA-pair kernel with N tile -bn.
-int gemm_launch_prepared(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmDev& p, int bn,
-                         int epi, cudaStream_t stream) {
-  if (bn < 0) return launch_gemm2_epi(epi, ta, tb, to, p, -bn, stream);
+int gemm_launch_prepared(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tt,
+                         const GemmDev& p, int bn, int epi, cudaStream_t stream) {
+  if (bn < 0) return launch_gemm2_epi(epi, ta, tb, to, tt, p, -bn, stream);
   switch (bn) {
     case 256: return launch_gemm_epi<256>(epi, ta, tb, p, stream);
     case 192: return launch_gemm_epi<192>(epi, ta, tb, p, stream);
@@ -550,8 +747,8 @@ int gemm_launch_prepared(const CUtensorMap& ta, const CUtensorMap& tb, const CUt
   return ORVB_EINVAL;
 }
 
-int gemm_prepare(const orvb_gemm_args* a, int bn_override, CUtensorMap* ta, CUtensorMap* tb, CUtensorMap* to, GemmDev* p,
-                 int* bn_out) {
+int gemm_prepare(const orvb_gemm_args* a, int bn_override, CUtensorMap* ta, CUtensorMap* tb, CUtensorMap* to, CUtensorMap* tt,
+                 GemmDev* p, int* bn_out) {
   ORVB_REQUIRE(a != nullptr && a->a && a->w && a->out, ORVB_EINVAL, "orvb_gemm_bf16: null pointer");
   ORVB_REQUIRE(a->m > 0 && a->n > 0 && a->k > 0, ORVB_ESHAPE, "orvb_gemm_bf16: empty problem m=%d n=%d k=%d", a->m,
                a->n, a->k);
@@ -596,6 +793,30 @@ int gemm_prepare(const orvb_gemm_args* a, int bn_override, CUtensorMap* ta, CUte
     *to = *ta;  // unused placeholder
   }
   GemmDev d;
+  d.stage_bytes = G2_STAGE_BYTES;
+  d.out_stage_bytes = G2_OUT_STAGE_BYTES;
+  d.fast_resid = 0;
+  *tt = *to;  // (placeholder unless the fast epilogue needs a tail map)
+  // Gated residual written in place over its own residual (attn-out / FF2 of every block): the epilogue that prefetches
+  // the residual tiles by TMA.  One staging tile per 64-column unit of the CTA's half tile -> needs the room a narrower
+  // B stage leaves (tile widths up to 192).  ORVB_GEMM_FAST_RESID=0 keeps the generic epilogue (A/B, bit-identical).
+  if (pair && tma_store && a->epilogue == ORVB_EPI_GATE_RESID && a->resid == a->out && a->ldr == a->ldo &&
+      a->resid_mod == 0 && fast_resid_enabled()) {
+    const int w = -bn, units = (w + 63) / 64, tail = w % 64;
+    GemmDev f = d;
+    f.stage_bytes = G2_A_BYTES + (((w / 2) * BK * 2 + 1023) & ~1023);
+    f.out_stage_bytes = 4 * units * 4096;
+    f.fast_resid = 1;
+    if (units <= 3 && g2_smem_bytes(f, w) <= G2_SMEM_MAX) {
+      d.stage_bytes = f.stage_bytes;
+      d.out_stage_bytes = f.out_stage_bytes;
+      d.fast_resid = 1;
+      if (tail != 0) {
+        rc = make_tmap_2d_bf16_plain(tt, a->out, a->m, a->n, a->ldo, 32, tail);
+        if (rc != ORVB_OK) return rc;
+      }
+    }
+  }
   d.tma_store = tma_store ? 1 : 0;
   d.out_f32 = a->out_f32 ? 1 : 0;
   d.grp_off = a->group_offset;
@@ -621,12 +842,12 @@ int gemm_prepare(const orvb_gemm_args* a, int bn_override, CUtensorMap* ta, CUte
 }
 
 int gemm_run(const orvb_gemm_args* a, cudaStream_t stream) {
-  CUtensorMap ta, tb, to;
+  CUtensorMap ta, tb, to, tt;
   GemmDev p;
   int bn;
-  int rc = gemm_prepare(a, 0, &ta, &tb, &to, &p, &bn);
+  int rc = gemm_prepare(a, 0, &ta, &tb, &to, &tt, &p, &bn);
   if (rc != ORVB_OK) return rc;
-  return gemm_launch_prepared(ta, tb, to, p, bn, a->epilogue, stream);
+  return gemm_launch_prepared(ta, tb, to, tt, p, bn, a->epilogue, stream);
 }
 
 
@@ -636,12 +857,12 @@ extern "C" int orvb_gemm_bf16(const orvb_gemm_args* args, void* stream) {
   using namespace orvb;
   int rc = check_arch();
   if (rc != ORVB_OK) return rc;
-  CUtensorMap ta, tb, to;
+  CUtensorMap ta, tb, to, tt;
   GemmDev p;
   int bn;
-  rc = gemm_prepare(args, 0, &ta, &tb, &to, &p, &bn);
+  rc = gemm_prepare(args, 0, &ta, &tb, &to, &tt, &p, &bn);
   if (rc != ORVB_OK) return rc;
-  return gemm_launch_prepared(ta, tb, to, p, bn, args->epilogue, static_cast<cudaStream_t>(stream));
+  return gemm_launch_prepared(ta, tb, to, tt, p, bn, args->epilogue, static_cast<cudaStream_t>(stream));
 }
 
 // Test hook: same as orvb_gemm_bf16 with a forced tile: bn in {64,128,192,256} = 1-CTA kernel, -bn (multiple of 16,
@@ -650,12 +871,12 @@ extern "C" int orvb_gemm_bf16_bn(const orvb_gemm_args* args, int bn, void* strea
   using namespace orvb;
   int rc = check_arch();
   if (rc != ORVB_OK) return rc;
-  CUtensorMap ta, tb, to;
+  CUtensorMap ta, tb, to, tt;
   GemmDev p;
   int bn_used;
-  rc = gemm_prepare(args, bn, &ta, &tb, &to, &p, &bn_used);
+  rc = gemm_prepare(args, bn, &ta, &tb, &to, &tt, &p, &bn_used);
   if (rc != ORVB_OK) return rc;
-  return gemm_launch_prepared(ta, tb, to, p, bn_used, args->epilogue, static_cast<cudaStream_t>(stream));
+  return gemm_launch_prepared(ta, tb, to, tt, p, bn_used, args->epilogue, static_cast<cudaStream_t>(stream));
 }
 
 #ifdef ORVB_GEMM_TIMELINE

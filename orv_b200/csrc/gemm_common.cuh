@@ -26,6 +26,10 @@ struct GemmDev {
   int tma_store;  // pair kernel: stage full 64-column units in shared memory and write them with TMA
   int out_f32;    // test mode: `out` is fp32, written before the bf16 rounding (direct stores only)
   const int* grp_off;  // optional device scalar added to the modulation-group index (schedule slice of this step)
+  // ---- CTA-pair kernel shared-memory plan (gemm.cu; the convolution kernel has its own fixed plan) ----
+  int stage_bytes;      // bytes per operand pipeline stage (A 16 KB + this CTA's half of B, rounded up to 1 KB)
+  int out_stage_bytes;  // output staging area behind the stages
+  int fast_resid;       // gated-residual epilogue with the residual tile prefetched by TMA (see gemm2_bf16_kernel)
 };
 
 constexpr int BM = 128;
@@ -55,7 +59,8 @@ __device__ __forceinline__ int row_group(const orvb_rowmap& rm, int row, int* s_
 }
 
 // Epilogue over one 64-column unit held by one thread (one output row).
-template <int EPI>
+// GATED = false compiles the gate operand out (the convolution kernel never has one and needs the registers).
+template <int EPI, bool GATED = true>
 __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float (&v)[64], int row, int n0, int ncols,
                                               uint8_t* stage_row = nullptr, int sw = 0) {
   // ---- bias --------------------------------------------------------------------------------------
@@ -137,20 +142,17 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float (&v)[64], 
   }
 
   if (EPI == ORVB_EPI_GATE_RESID) {
-    if (p.gate != nullptr) {
+    // out = resid + gate * (acc + bias): ONE fused multiply-add per element when both operands are present (the
+    // TMA-prefetched epilogue of the CTA-pair kernel forms the same fma, so the two paths agree bit for bit).
+    const float* gp = nullptr;
+    if (GATED && p.gate != nullptr) {
       int s;
       int g = row_group(p.rm, out_row, &s);  // modulation group of the DESTINATION row
       if (p.grp_off != nullptr) g += *p.grp_off;
       int is_text = (p.rm.seq_len > 0) ? (s < p.rm.text_len) : 0;
-      const float* gp = p.gate + static_cast<size_t>(g) * p.gate_ld + (is_text ? p.gate_text_off : p.gate_video_off) + n0;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if (j * 4 < ncols) {
-          float4 g4 = *reinterpret_cast<const float4*>(gp + j * 4);
-          v[j * 4 + 0] *= g4.x; v[j * 4 + 1] *= g4.y; v[j * 4 + 2] *= g4.z; v[j * 4 + 3] *= g4.w;
-        }
-      }
+      gp = p.gate + static_cast<size_t>(g) * p.gate_ld + (is_text ? p.gate_text_off : p.gate_video_off) + n0;
     }
+    const bf16* rp = nullptr;
     if (p.resid != nullptr) {
       size_t rrow;
       if (p.resid_mod > 0) {
@@ -160,15 +162,48 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float (&v)[64], 
       } else {
         rrow = static_cast<size_t>(out_row);
       }
-      const bf16* rp = p.resid + rrow * p.ldr + n0;
+      rp = p.resid + rrow * p.ldr + n0;
+    }
+    if (gp != nullptr && rp != nullptr) {
+      // half a row of residual first (four independent 16-byte loads in flight together), then gate pieces + fma
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint4 rr[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if ((h * 4 + q) * 8 < ncols) rr[q] = *reinterpret_cast<const uint4*>(rp + (h * 4 + q) * 8);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int j = h * 4 + q;
+          if (j * 8 < ncols) {
+            const float4 g0 = *reinterpret_cast<const float4*>(gp + j * 8);
+            const float4 g1 = *reinterpret_cast<const float4*>(gp + j * 8 + 4);
+            v[j * 8 + 0] = __fmaf_rn(v[j * 8 + 0], g0.x, bf16_lo(rr[q].x)); v[j * 8 + 1] = __fmaf_rn(v[j * 8 + 1], g0.y, bf16_hi(rr[q].x));
+            v[j * 8 + 2] = __fmaf_rn(v[j * 8 + 2], g0.z, bf16_lo(rr[q].y)); v[j * 8 + 3] = __fmaf_rn(v[j * 8 + 3], g0.w, bf16_hi(rr[q].y));
+            v[j * 8 + 4] = __fmaf_rn(v[j * 8 + 4], g1.x, bf16_lo(rr[q].z)); v[j * 8 + 5] = __fmaf_rn(v[j * 8 + 5], g1.y, bf16_hi(rr[q].z));
+            v[j * 8 + 6] = __fmaf_rn(v[j * 8 + 6], g1.z, bf16_lo(rr[q].w)); v[j * 8 + 7] = __fmaf_rn(v[j * 8 + 7], g1.w, bf16_hi(rr[q].w));
+          }
+        }
+      }
+    } else if (gp != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (j * 4 < ncols) {
+          float4 g4 = *reinterpret_cast<const float4*>(gp + j * 4);
+          v[j * 4 + 0] = __fmul_rn(v[j * 4 + 0], g4.x); v[j * 4 + 1] = __fmul_rn(v[j * 4 + 1], g4.y);
+          v[j * 4 + 2] = __fmul_rn(v[j * 4 + 2], g4.z); v[j * 4 + 3] = __fmul_rn(v[j * 4 + 3], g4.w);
+        }
+      }
+    } else if (rp != nullptr) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         if (j * 8 < ncols) {
           uint4 rr = *reinterpret_cast<const uint4*>(rp + j * 8);
-          v[j * 8 + 0] += bf16_lo(rr.x); v[j * 8 + 1] += bf16_hi(rr.x);
-          v[j * 8 + 2] += bf16_lo(rr.y); v[j * 8 + 3] += bf16_hi(rr.y);
-          v[j * 8 + 4] += bf16_lo(rr.z); v[j * 8 + 5] += bf16_hi(rr.z);
-          v[j * 8 + 6] += bf16_lo(rr.w); v[j * 8 + 7] += bf16_hi(rr.w);
+          v[j * 8 + 0] = __fadd_rn(v[j * 8 + 0], bf16_lo(rr.x)); v[j * 8 + 1] = __fadd_rn(v[j * 8 + 1], bf16_hi(rr.x));
+          v[j * 8 + 2] = __fadd_rn(v[j * 8 + 2], bf16_lo(rr.y)); v[j * 8 + 3] = __fadd_rn(v[j * 8 + 3], bf16_hi(rr.y));
+          v[j * 8 + 4] = __fadd_rn(v[j * 8 + 4], bf16_lo(rr.z)); v[j * 8 + 5] = __fadd_rn(v[j * 8 + 5], bf16_hi(rr.z));
+          v[j * 8 + 6] = __fadd_rn(v[j * 8 + 6], bf16_lo(rr.w)); v[j * 8 + 7] = __fadd_rn(v[j * 8 + 7], bf16_hi(rr.w));
         }
       }
     }
@@ -218,7 +253,10 @@ constexpr int G2_A_BYTES = BM * BK * 2;           // 16 KB: this CTA's 128 rows 
 constexpr int G2_B_BYTES = 128 * BK * 2;          // up to 16 KB: this CTA's BN/2 rows of B
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
 constexpr int G2_OUT_STAGE_BYTES = 8 * 32 * 128;  // 32 KB of [32 x 64] bf16 output staging tiles, split over the epilogue warps
-constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + G2_OUT_STAGE_BYTES + 1024 + 256;
+constexpr int G2_BAR_BYTES = 512;                 // mbarriers + the TMEM slot
+constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + G2_OUT_STAGE_BYTES + 1024 + G2_BAR_BYTES;
+constexpr int G2_SMEM_MAX = 232448;               // 227 KB: the most a CTA can own
+constexpr int G2_GS_SLOT = 768;                   // fast gated-residual epilogue, per 64-column unit: gate rows A | B, bias (64 fp32 each)
 constexpr int G2_ACC_COLS = 256;                  // TMEM columns per accumulator buffer (2 buffers = 512)
 
 // Epilogue warps per CTA: eight — warps e and e + 4 share a TMEM lane quarter and take alternate 64-column units, which

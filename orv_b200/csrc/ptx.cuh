@@ -85,6 +85,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// 16-byte shared-memory store WITHOUT a compiler memory barrier: later shared-memory loads of OTHER addresses may be
+// scheduled above it (an unrolled read-modify-write over distinct slots; a plain C++ store would serialise the slots,
+// since the compiler cannot prove them distinct).  Volatile: ordered against the other volatile asm (fences, TMA).
+__device__ __forceinline__ void sts128_nobarrier(void* smem_dst, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(smem_dst)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+
 // generic-proxy writes to smem -> visible to the async proxy (TMA / UMMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

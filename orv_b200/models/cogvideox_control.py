@@ -26,6 +26,16 @@ from .components import ActionEmbed, ActionRecon, Transformer3DModelTrajOutput
 from .embeddings import sincos_pos_embed_3d
 
 
+
+def _host_scalar(x) -> float:
+    """First element of `x` as a Python float.  The pipeline tags the device tensor it builds with the value it filled it
+    with (`_orvb_host_value`), so reading it back does not synchronise the stream in front of every clip."""
+    if torch.is_tensor(x):
+        v = getattr(x, "_orvb_host_value", None)
+        return float(v) if v is not None else float(x.reshape(-1)[0].item())
+    return float(x)
+
+
 class FrozenConfig(dict):
     """dict with attribute access, like diffusers' FrozenDict (`model.config.patch_size_t`, `dict(model.config)`)."""
 
@@ -397,7 +407,7 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
         if self.ofs_embedding is not None:
             if ofs is None:
                 raise RuntimeError("this model has an ofs embedding; pass `ofs`")
-            ofs_val = float(ofs.reshape(-1)[0].item()) if torch.is_tensor(ofs) else float(ofs)
+            ofs_val = _host_scalar(ofs)
         shape = L.Shape(batch=B, views=V, frames=Fr, height=H, width=W, text_len=text_len, action_frames=action_frames)
         lib = L.load()
         nbytes = lib.orvb_modulation_bytes(self._handle, C.byref(shape), steps)
@@ -802,7 +812,7 @@ class CogVideoXTransformer3DModelTraj(nn.Module):
         if self.ofs_embedding is not None and sched is None:  # (a scheduled step consumed ofs when the tables were built;
             if ofs is None:                                   #  reading it here would cost a device sync per step)
                 raise RuntimeError("this model has an ofs embedding; pass `ofs`")
-            ofs_val = float(ofs.reshape(-1)[0].item()) if torch.is_tensor(ofs) else float(ofs)
+            ofs_val = _host_scalar(ofs)
 
         shape = L.Shape(batch=B, views=V, frames=Fr, height=H, width=W, text_len=St, action_frames=action_frames)
         lib = L.load()

@@ -78,7 +78,10 @@ def get_3d_rotary_pos_embed(embed_dim: int, crops_coords, grid_size: Tuple[int, 
 
     cos, sin = combine(tc, hc, wc), combine(ts, hs, ws)
     if device is not None:
-        cos, sin = cos.to(device), sin.to(device)
+        if torch.device(device).type == "cuda":  # pinned + non-blocking: a pageable upload would synchronise the stream
+            cos, sin = cos.pin_memory().to(device, non_blocking=True), sin.pin_memory().to(device, non_blocking=True)
+        else:
+            cos, sin = cos.to(device), sin.to(device)
     return cos, sin
 
 

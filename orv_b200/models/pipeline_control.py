@@ -353,11 +353,13 @@ class CogVideoXImageToVideoPipelineTraj:
         image_rotary_emb = (self._prepare_rotary_positional_embeddings(height, width, latents.size(1), device)
                             if tcfg.use_rotary_positional_embeddings else None)
         ofs_emb = None if tcfg.ofs_embed_dim is None else latents.new_full((1,), fill_value=2.0)
+        if ofs_emb is not None:
+            ofs_emb._orvb_host_value = 2.0  # read by the transformer instead of a device -> host copy
 
         # ---- denoising loop (:1402-1473), with the per-step tensor math fused on the device ----
         is_dpm = isinstance(self.scheduler, CogVideoXDPMScheduler)
         fused = latents.is_cuda and latents.dtype == torch.bfloat16 and callback_on_step_end is None
-        ts_list = timesteps.tolist()
+        ts_list = list(getattr(self.scheduler, "timesteps_host", None) or timesteps.tolist())
         n_cfg = 2 if do_cfg else 1
         draws = noise_dev = noise_pin = noise_evt = None
         if is_dpm and fused:

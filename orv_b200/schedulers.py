@@ -14,6 +14,8 @@ from types import SimpleNamespace
 from typing import List, Optional, Tuple
 
 import numpy as np
+import os
+
 import torch
 
 from . import _lib as L
@@ -88,7 +90,12 @@ class _CogVideoXSchedulerBase:
             ts = np.round(np.arange(c.num_train_timesteps, 0, -ratio)).astype(np.int64) - 1
         else:
             raise ValueError(f"{c.timestep_spacing} is not supported.")
-        self.timesteps = torch.from_numpy(ts).to(device)
+        self.timesteps_host = [int(t) for t in ts]  # the sampler loop reads these: no device -> host copy (= stream sync)
+        t_cpu = torch.from_numpy(ts)
+        if device is not None and torch.device(device).type == "cuda" and os.environ.get("ORVB_PINNED_UPLOADS", "1") != "0":
+            self.timesteps = t_cpu.pin_memory().to(device, non_blocking=True)
+        else:
+            self.timesteps = t_cpu.to(device)
 
     # ---- float64 scalars -------------------------------------------------------------------------------
     def _alphas(self, timestep: int):
@@ -184,7 +191,7 @@ class CogVideoXDPMScheduler(_CogVideoXSchedulerBase):
     def noise_draws(self, num_steps: int) -> List[int]:
         """How many `randn_tensor` calls diffusers' step makes at each loop index: one always, a second one on
         the second-order branch (the first draw is then discarded) — needed to keep the generator stream aligned."""
-        ts = self.timesteps.tolist()
+        ts = getattr(self, "timesteps_host", None) or self.timesteps.tolist()
         out = []
         for i, t in enumerate(ts):
             prev = t - self.config.num_train_timesteps // self.num_inference_steps
@@ -224,6 +231,11 @@ def _randn(shape, generator, device, dtype):
         generator = generator[0]
     gen_dev = generator.device.type if generator is not None else torch.device(device).type
     if gen_dev == "cpu" and torch.device(device).type != "cpu":
+        # Same CPU draw; the upload goes through PINNED memory and does not block.  A pageable cudaMemcpyAsync
+        # synchronises the stream before it starts, i.e. the host would wait here for everything still queued — the tail of
+        # the previous clip — and the GPU would then idle through the rest of this clip's host prologue.
+        if torch.device(device).type == "cuda" and os.environ.get("ORVB_PINNED_UPLOADS", "1") != "0":
+            return torch.randn(shape, generator=generator, device="cpu", dtype=dtype, pin_memory=True).to(device, non_blocking=True)
         return torch.randn(shape, generator=generator, device="cpu", dtype=dtype).to(device)
     return torch.randn(shape, generator=generator, device=device, dtype=dtype)
 

@@ -29,11 +29,13 @@ NAMES = ["entry", "prologue", "pdl_wait", "tma_first", "tma_last", "ops_landed",
          "epi_first", "acc_last", "epi_last", "stores", "teardown"]
 
 
-def run(name, M, N, K, epilogue=L.EPI_BIAS, **kw):
+def run(name, M, N, K, epilogue=L.EPI_BIAS, inplace=False, **kw):
     a = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
     w = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
     b = torch.randn(N, device=dev).bfloat16()
-    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    # inplace: written over its own residual, as the forward does (-> the TMA-prefetched epilogue unless
+    # ORVB_GEMM_FAST_RESID=0)
+    out = kw["resid"] if inplace else torch.empty(M, N, device=dev, dtype=torch.bfloat16)
     call = lambda: ops.gemm(a, w, b, epilogue=epilogue, out=out, **kw)  # noqa: E731
     for _ in range(3):
         call()
@@ -59,7 +61,7 @@ def run(name, M, N, K, epilogue=L.EPI_BIAS, **kw):
             t0 = int(row[0])
             if t0 == 0:
                 continue
-            rel = {n: (int(row[i]) - t0 if int(row[i]) > 0 else None) for i, n in enumerate(NAMES)}
+            rel = {n: (int(row[i]) - t0 if int(row[i]) > 0 else None) for i, n in enumerate(NAMES) if n}
             print(f"  {cname} CTA {r} ({int(row[14])} tiles), clk from entry: "
                   + "  ".join(f"{n}={v}" for n, v in rel.items() if v is not None))
     return us
@@ -70,6 +72,11 @@ resid = (torch.randn(M, D, device=dev)).bfloat16()
 gate = torch.randn(6, 6 * D, device=dev)
 rm = ops.rowmap(seq_len=M, text_len=226, tokens_per_group=600, groups_per_batch=6)
 run("attn-out (gate*x + residual)", M, D, D, L.EPI_GATE_RESID, resid=resid, gate=gate, gate_text_off=0, gate_video_off=0, rm=rm)
+gate_s = gate * 0.01  # (in place the residual stream is accumulated over the timing loop: keep it bounded)
+run("attn-out IN PLACE (gate*x + residual)", M, D, D, L.EPI_GATE_RESID, inplace=True, resid=resid.clone(), gate=gate_s,
+    gate_text_off=0, gate_video_off=0, rm=rm)
+run("FF2 IN PLACE (gate*x + residual)", M, D, 4 * D, L.EPI_GATE_RESID, inplace=True, resid=resid.clone(), gate=gate_s,
+    gate_text_off=0, gate_video_off=0, rm=rm)
 run("FF1 (GELU)", M, 4 * D, D, L.EPI_GELU)
 run("FF2 (gate*x + residual)", M, D, 4 * D, L.EPI_GATE_RESID, resid=resid, gate=gate, gate_text_off=0, gate_video_off=0, rm=rm)
 run("QKV-shaped (bias only)", M, 3 * D, D, L.EPI_BIAS)
