@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ORVB_VERSION 103
+#define ORVB_VERSION 104
 
 enum {
   ORVB_OK = 0,
@@ -111,6 +111,10 @@ typedef struct orvb_gemm_args {
   /* Optional DEVICE scalar added to every modulation-group index (the row of `gate`) — lets one captured launch
    * sequence walk through the per-step slices of a modulation schedule (orvb_forward_args.schedule).  NULL = 0. */
   const int32_t* group_offset;
+  /* k_wrap > 0: W has only k_wrap columns and is walked cyclically along K (column kk of the contraction reads
+   * W[:, kk % k_wrap]); k % k_wrap == 0, k_wrap % 64 == 0.  With A = [hi | lo] (an fp32 operand split into two bf16
+   * halves, k = 2 * k_wrap) the product is the fp32-accurate A_fp32 @ W^T — the AdaLN table build uses this. */
+  int32_t k_wrap;
 } orvb_gemm_args;
 
 /* tcgen05 / TMA GEMM.  Requirements: k % 8 == 0, n % 8 == 0, lda/ldw/ldo % 8 == 0, 16-byte aligned bases. */

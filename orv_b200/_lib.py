@@ -44,6 +44,7 @@ class GemmArgs(C.Structure):
         ("rope_cos", c_void_p), ("rope_sin", c_void_p),
         ("out_f32", c_int),
         ("group_offset", c_void_p),
+        ("k_wrap", c_int),
     ]
 
 

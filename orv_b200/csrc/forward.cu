@@ -85,6 +85,7 @@ static int make_geometry(const orvb_config& c, const orvb_shape& s, Geometry* g)
 struct Workspace {
   bf16 *x, *xn, *qkv, *att, *ffh, *patches, *ctrl, *yout, *qkv_mv, *att_mv, *tmp_mv;
   float *tsin, *t1, *temb, *osin, *o1, *oemb, *act_in, *act_h, *act_emb, *emb, *mod;
+  bf16* emb_hl;  // [groups, 2T]: the conditioning rows split into bf16 halves [hi | lo], A operand of the table GEMMs
   bf16* ab;
   SkinnyJob* jobs;   // [3 * layers] device table of the batched AdaLN linears (points into `mod`)
   AbSite* ab_sites;  // [3 * layers + 1] device table of the A/B folds (points into `mod` / `ab`)
@@ -115,6 +116,7 @@ static void carve_modulation(const orvb_config& c, const Geometry& g, Take&& tak
   ws->act_h = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * fa * c.action_hidden * 4));
   ws->act_emb = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * fa * g.T * 4));
   ws->emb = reinterpret_cast<float*>(take(static_cast<size_t>(g.B) * g.G * g.T * 4));
+  ws->emb_hl = reinterpret_cast<bf16*>(take(static_cast<size_t>(g.B) * g.G * g.T * 2 * 2));
   ws->mod = reinterpret_cast<float*>(take(static_cast<size_t>(g.sites) * g.B * g.G * mod_width(c) * D * 4));
   ws->ab = reinterpret_cast<bf16*>(take(static_cast<size_t>(g.sites) * g.B * g.G * 4 * D * 2));
   ws->jobs = reinterpret_cast<SkinnyJob*>(take(sizeof(SkinnyJob) * 3 * c.layers));
@@ -192,7 +194,8 @@ __global__ void actions_to_f32_kernel(const bf16* __restrict__ a, float* __restr
 // Reference: cogvideox_control.py:121-130 (LayerNormZero), :166-170 (AdaLayerNorm), components.py:66-69 (mask).
 __global__ void build_emb_kernel(const float* __restrict__ temb, const float* __restrict__ oemb,
                                  const float* __restrict__ act_emb, const uint8_t* __restrict__ mask,
-                                 const bf16* __restrict__ mask_embed, float* __restrict__ emb, int B, int G, int T) {
+                                 const bf16* __restrict__ mask_embed, float* __restrict__ emb,
+                                 bf16* __restrict__ emb_hl, int B, int G, int T) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * G * T) return;
   const int c = idx % T;
@@ -205,7 +208,13 @@ __global__ void build_emb_kernel(const float* __restrict__ temb, const float* __
     else a = act_emb[(static_cast<size_t>(b) * (G - 1) + (g - 1)) * T + c];
     v += a;
   }
-  emb[idx] = silu(v);
+  const float e = silu(v);
+  emb[idx] = e;
+  // e = hi + lo + O(2^-17 e) with both halves bf16: [hi | lo] @ [W | W]^T on the tensor cores is e @ W^T to fp32 accuracy
+  const bf16 hi = __float2bfloat16(e);
+  const size_t row = static_cast<size_t>(idx / T);
+  emb_hl[row * 2 * T + c] = hi;
+  emb_hl[row * 2 * T + T + c] = __float2bfloat16(e - __bfloat162float(hi));
 }
 
 // ctrl[r, col_off + c] += x[video row r, c]   (hidden_states.repeat(1,1,keys) + controls, :853-855)
@@ -305,6 +314,12 @@ __global__ void fill_tables_kernel(const orvb_block_weights* __restrict__ blocks
   }
 }
 
+// ORVB_MOD_TABLES_TC=0 keeps the CUDA-core table build (A/B; fp32 activations instead of the [hi | lo] bf16 split).
+static bool mod_tables_on_tensor_cores() {
+  const char* e = getenv("ORVB_MOD_TABLES_TC");
+  return !(e != nullptr && e[0] == '0');
+}
+
 static int build_modulation(orvb_model* m, const Geometry& g, const ModIn& in, const Workspace& ws, cudaStream_t st) {
   const orvb_config& c = m->cfg;
   const orvb_weights& w = m->w;
@@ -357,7 +372,7 @@ static int build_modulation(orvb_model* m, const Geometry& g, const ModIn& in, c
   {
     const int n = g.B * g.G * T;
     build_emb_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws.temb, oemb, ws.act_emb, a->action_mask,
-                                                      static_cast<const bf16*>(w.act_mask_embed), ws.emb, g.B, g.G, T);
+                                                      static_cast<const bf16*>(w.act_mask_embed), ws.emb, ws.emb_hl, g.B, g.G, T);
     ORVB_CHECK_CUDA(cudaGetLastError());
     note_launch(m);
   }
@@ -374,13 +389,38 @@ static int build_modulation(orvb_model* m, const Geometry& g, const ModIn& in, c
     ORVB_CHECK_CUDA(cudaGetLastError());
     note_launch(m);
   }
-  ORVB_TRY(skinny_linear_launch(ws.emb, SkinnyJob{nullptr, nullptr, nullptr}, ws.jobs,
-                                2 * c.layers + (c.multiview ? c.layers : 0), g.B * g.G, mw * D, T, 0, st));
   float* mod_out = ws.mod + static_cast<size_t>(2 * c.layers) * site_stride;  // norm_out table, row pitch 2D
-  {
+  const int rows = g.B * g.G;
+  if (T % 64 == 0 && mod_tables_on_tensor_cores()) {
+    // One tcgen05 GEMM per site: [rows, 2T] x [n, T (walked twice)]^T -> fp32 [rows, n] + bias.  The CUDA-core kernel
+    // below streams every weight once per 8 rows; for the 300 rows of a 50-step schedule that is 38 passes and 7 ms per
+    // clip, the GEMMs take < 1 ms.  The same kernels run for the 6 rows of a single forward (same K order in the
+    // single-CTA and the CTA-pair kernel), so a scheduled step and a stand-alone forward see the same table bits.
+    auto site_gemm = [&](const void* lw, const void* lb, float* out, int n) -> int {
+      orvb_gemm_args ga = gemm_base(ws.emb_hl, lw, lb, out, rows, n, 2 * T, 2 * T, n, ORVB_EPI_BIAS);
+      ga.ldw = T;
+      ga.k_wrap = T;
+      ga.out_f32 = 1;
+      return gemm_run(&ga, st);
+    };
+    for (int l = 0; l < c.layers; ++l) {
+      const orvb_block_weights& bw = m->blocks[l];
+      ORVB_TRY(site_gemm(bw.norm1_lin_w, bw.norm1_lin_b, ws.mod + static_cast<size_t>(2 * l) * site_stride, mw * D));
+      ORVB_TRY(site_gemm(bw.norm2_lin_w, bw.norm2_lin_b, ws.mod + static_cast<size_t>(2 * l + 1) * site_stride, mw * D));
+    }
+    if (c.multiview) {
+      for (int l = 0; l < c.layers; ++l) {
+        const orvb_block_weights& bw = m->mv_blocks[l];
+        ORVB_TRY(site_gemm(bw.norm1_lin_w, bw.norm1_lin_b, ws.mod + static_cast<size_t>(2 * c.layers + 1 + l) * site_stride, mw * D));
+      }
+    }
+    ORVB_TRY(site_gemm(w.norm_out_lin_w, w.norm_out_lin_b, mod_out, 2 * D));
+  } else {
+    ORVB_TRY(skinny_linear_launch(ws.emb, SkinnyJob{nullptr, nullptr, nullptr}, ws.jobs,
+                                  2 * c.layers + (c.multiview ? c.layers : 0), rows, mw * D, T, 0, st));
     // norm_out.linear is [2D, T]; written with pitch 2D into its slot
     ORVB_TRY(skinny_linear_launch(ws.emb, SkinnyJob{static_cast<const bf16*>(w.norm_out_lin_w), static_cast<const bf16*>(w.norm_out_lin_b), mod_out},
-                                  nullptr, 1, g.B * g.G, 2 * D, T, 0, st));
+                                  nullptr, 1, rows, 2 * D, T, 0, st));
   }
   // fold LayerNorm affine + (shift, scale) of every site into bf16 A/B tables for the LN kernels
   ORVB_TRY(ab_combine_launch(ws.ab_sites, g.sites, g.B * g.G, D, st));

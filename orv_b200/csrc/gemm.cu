@@ -81,7 +81,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         if (elect_one()) {
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
-          tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+          tma_load_2d(sb, &tma_b, &full_bar[stage], p.k_wrap > 0 ? (kb * BK) % p.k_wrap : kb * BK, n_blk * BN);
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -298,7 +298,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         if (elect_one()) {
           if (rank == 0) mbar_expect_tx(&full_bar[stage], stage_tx);
           tma_load_2d_pair(sa, &tma_a, leader_full, kb * BK, a_row);
-          tma_load_2d_pair(sb, &tma_b, leader_full, kb * BK, b_row);
+          tma_load_2d_pair(sb, &tma_b, leader_full, p.k_wrap > 0 ? (kb * BK) % p.k_wrap : kb * BK, b_row);
         }
         __syncwarp();
         if (tile == cluster_id && kb == 0) G2_STAMP(3);  // first stage requested
@@ -782,7 +782,9 @@ int gemm_prepare(const orvb_gemm_args* a, int bn_override, CUtensorMap* ta, CUte
   }
   int rc = make_tmap_2d_bf16(ta, a->a, a->m, a->k, a->lda, BM, BK);
   if (rc != ORVB_OK) return rc;
-  rc = make_tmap_2d_bf16(tb, a->w, a->n, a->k, a->ldw, pair ? (-bn) / 2 : bn, BK);
+  ORVB_REQUIRE(a->k_wrap == 0 || (a->k_wrap > 0 && a->k_wrap % BK == 0 && a->k % a->k_wrap == 0), ORVB_ESHAPE,
+               "orvb_gemm_bf16: k_wrap %d must be a multiple of %d dividing k = %d", a->k_wrap, BK, a->k);
+  rc = make_tmap_2d_bf16(tb, a->w, a->n, a->k_wrap > 0 ? a->k_wrap : a->k, a->ldw, pair ? (-bn) / 2 : bn, BK);
   if (rc != ORVB_OK) return rc;
   // Output through TMA (pair kernel, rows written in place): [32 rows x 64 cols] boxes of the [M, N] output
   const bool tma_store = pair && a->src_rows == 0 && a->mv_tokens == 0 && !a->out_f32;
@@ -793,6 +795,7 @@ int gemm_prepare(const orvb_gemm_args* a, int bn_override, CUtensorMap* ta, CUte
     *to = *ta;  // unused placeholder
   }
   GemmDev d;
+  d.k_wrap = a->k_wrap;
   d.stage_bytes = G2_STAGE_BYTES;
   d.out_stage_bytes = G2_OUT_STAGE_BYTES;
   d.fast_resid = 0;

@@ -30,6 +30,7 @@ struct GemmDev {
   int stage_bytes;      // bytes per operand pipeline stage (A 16 KB + this CTA's half of B, rounded up to 1 KB)
   int out_stage_bytes;  // output staging area behind the stages
   int fast_resid;       // gated-residual epilogue with the residual tile prefetched by TMA (see gemm2_bf16_kernel)
+  int k_wrap;           // > 0: W has k_wrap columns, walked cyclically along K (orvb_gemm_args.k_wrap)
 };
 
 constexpr int BM = 128;

@@ -31,14 +31,14 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
          row_remap=(0, 0, 0), resid: Optional[torch.Tensor] = None, resid_mod: int = 0, resid_views: int = 1,
          resid_view_stride: int = 0, gate: Optional[torch.Tensor] = None, gate_text_off: int = 0,
          gate_video_off: int = 0, rm: Optional[L.RowMap] = None, qk_dim: int = 0, q_norm=None, k_norm=None,
-         qk_eps: float = 1e-6, rope=None, bn: int = 0, launch: bool = True, out_f32: bool = False):
+         qk_eps: float = 1e-6, rope=None, bn: int = 0, launch: bool = True, out_f32: bool = False, k_wrap: int = 0):
     """out = epilogue(a @ w.T)  — a [M,K] bf16, w [N,K] bf16 (nn.Linear layout).  `launch=False` only fills and
     returns `(GemmArgs, out)`."""
     _req(a, torch.bfloat16, "a")
     _req(w, torch.bfloat16, "w")
     M, K = a.shape
     N = w.shape[0]
-    assert w.shape[1] == K
+    assert w.shape[1] == (k_wrap or K)  # k_wrap: W [N, k_wrap] is walked cyclically along K (orvb_gemm_args.k_wrap)
     odt = torch.float32 if out_f32 else torch.bfloat16  # out_f32: tight-tolerance test mode (fp32 before the rounding)
     if out is None:
         rows = M if row_remap[0] == 0 else (M // row_remap[0]) * row_remap[1]
@@ -46,6 +46,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     _req(out, odt, "out")
     args = L.GemmArgs()
     args.out_f32 = int(out_f32)
+    args.k_wrap = int(k_wrap)
     args.a, args.w = a.data_ptr(), w.data_ptr()
     args.out = out.data_ptr() + out_col_offset * out.element_size()
     args.bias = L.ptr(bias)

@@ -206,3 +206,26 @@ def test_ln_modulate_f32(ops, use_ab):
         ref = (xhat * w.double() + b.double()) * (1 + scale) + shift
         out = ops.ln_modulate(x, w, b, 1e-5, mod=mod, text_off=3 * D, video_off=0, rm=rm, out_f32=True)
     _close(out, ref)
+
+
+@pytest.mark.parametrize("rows", [6, 300])
+def test_gemm_k_wrap_hi_lo_split_is_fp32_accurate(ops, rows):
+    """The AdaLN table build (orv_b200/csrc/forward.cu build_modulation; reference cogvideox_control.py:121-130 linear of
+    silu(emb)): an fp32 activation split into bf16 halves [hi | lo] against W walked twice along K (k_wrap) must equal
+    the fp32 product x @ W^T + b at the north-star tolerance (rtol 1e-3 / atol 1e-4; observed ~1e-6), and the 6 rows of
+    a stand-alone forward (single-CTA kernel) must carry the same bits as the same rows inside a 300-row schedule
+    (CTA-pair kernel)."""
+    torch.manual_seed(rows)
+    T, N = 512, 1920
+    x = torch.nn.functional.silu(torch.randn(300, T, device=DEV) * 2.0)
+    w = (torch.randn(N, T, device=DEV) * 0.05).bfloat16()
+    b = torch.randn(N, device=DEV).bfloat16()
+    hi = x.bfloat16()
+    lo = (x - hi.float()).bfloat16()
+    a = torch.cat([hi, lo], dim=1).contiguous()
+    out = ops.gemm(a[:rows].contiguous(), w, b, out_f32=True, k_wrap=T)
+    ref = (x[:rows].double() @ w.double().T + b.double()).float()
+    torch.testing.assert_close(out, ref, rtol=RTOL, atol=ATOL)
+    if rows < 300:
+        full = ops.gemm(a, w, b, out_f32=True, k_wrap=T)
+        assert torch.equal(full[:rows], out)

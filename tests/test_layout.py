@@ -33,7 +33,7 @@ def test_header_symbols_are_exported_by_the_library():
     lib = L.load()  # builds with nvcc if the .so is missing; loading needs no GPU
     for sym in sorted(declared):
         assert hasattr(lib, sym), f"liborv_b200.so does not export {sym}"
-    assert lib.orvb_version() == 103
+    assert lib.orvb_version() == 104
     assert isinstance(lib.orvb_last_error(), bytes)
     # ... and nothing else: every orvb_* symbol the library exports is declared in the header
     import subprocess
