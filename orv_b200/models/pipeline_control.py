@@ -368,12 +368,18 @@ class CogVideoXImageToVideoPipelineTraj:
             # work of a few ms per step; it is issued AFTER the step's forward has been enqueued, so it overlaps the
             # GPU, and reaches the device through a double-buffered pinned staging area.
             draws = self.scheduler.noise_draws(len(ts_list))
-            nk = ("noise", tuple(latents.shape), latents.dtype)
+            # Ring of NS staging slots: the host may run up to 2 * NS iterations ahead of the GPU, so a descheduled host
+            # thread (the draws are tens of ms of CPU work per iteration on the large configs) cannot stall the device
+            # until the whole ring has drained.  (The occasional slow config-5 clip — one in four is 3 - 15 % longer — is
+            # NOT this: it happens with 2 and with 8 slots and with a second of host slack, i.e. on the device side,
+            # under the power cap; profiles/r02_notes.md, section 13.)
+            NS = max(2, int(os.environ.get("ORVB_NOISE_SLOTS", "8")))
+            nk = ("noise", tuple(latents.shape), latents.dtype, NS)
             if nk not in self._staging:
-                self._staging[nk] = ([torch.empty(latents.shape, dtype=latents.dtype, device=device) for _ in range(2)],
-                                     [torch.empty(latents.shape, dtype=latents.dtype).pin_memory() for _ in range(2)],
-                                     [torch.cuda.Event(), torch.cuda.Event()],
-                                     [torch.cuda.Event(), torch.cuda.Event()], torch.cuda.Stream(device=device))
+                self._staging[nk] = ([torch.empty(latents.shape, dtype=latents.dtype, device=device) for _ in range(NS)],
+                                     [torch.empty(latents.shape, dtype=latents.dtype).pin_memory() for _ in range(NS)],
+                                     [torch.cuda.Event() for _ in range(NS)],
+                                     [torch.cuda.Event() for _ in range(NS)], torch.cuda.Stream(device=device))
             noise_dev, noise_pin, noise_evt, used_evt, copy_stream = self._staging[nk]
             for ev in used_evt:  # "the sampler step that last read this slot has run": trivially true at the start
                 ev.record()
@@ -446,7 +452,7 @@ class CogVideoXImageToVideoPipelineTraj:
                         (1 - math.cos(math.pi * ((num_inference_steps - t) / num_inference_steps) ** 5.0)) / 2)
                 if fused:
                     if is_dpm:
-                        slot = i & 1
+                        slot = i % len(noise_dev)
                         if _is_cpu_gen(generator):
                             for _ in range(draws[i]):
                                 nz = randn_tensor(latents.shape, generator, "cpu", latents.dtype)
