@@ -123,6 +123,10 @@ int orvb_gemm_bf16(const orvb_gemm_args* args, void* stream);
  * < 0 = CTA-pair kernel (tcgen05 cta_group::2), 256 x (-value) tiles, the width that fills the last wave of the
  * device's SM pairs best. */
 int orvb_gemm_tile_width(int32_t m, int32_t n, int32_t epilogue);
+/* CTA-pair kernel only: when cutting N into n / width full tiles plus ONE narrower tile per 256-row block balances the SM
+ * pairs better than any uniform width (QKV of a 2B block: 22 x 256 + 128 instead of 30 x 192), the width of that narrower
+ * tile; 0 = uniform tiles. */
+int orvb_gemm_tile_remainder(int32_t m, int32_t n, int32_t epilogue);
 /* Test hook: orvb_gemm_bf16 with a forced tile.  bn in {64, 128, 192, 256} = single-CTA kernel with that N tile; -bn
  * (a multiple of 16 in 32..256) = CTA-pair kernel.  Used by the bit-identity test of the two kernels and by the tile
  * sweeps under tools/. */

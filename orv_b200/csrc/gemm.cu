@@ -244,7 +244,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   const uint32_t rank = cluster_ctarank();
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;  // num_m_tiles counts 256-row pairs here
+  const int num_tiles = p.tile_end;  // virtual tile indices (g2_tile); num_m_tiles counts 256-row pairs here
   const int num_k = (p.K + BK - 1) / BK;
   const int half_bn = bn >> 1;
 
@@ -286,10 +286,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     uint32_t phase = 0;
     const uint32_t stage_tx = 2u * static_cast<uint32_t>(G2_A_BYTES + half_bn * BK * 2);
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int m_blk = tile % p.num_m_tiles;
-      const int n_blk = tile / p.num_m_tiles;
-      const int a_row = m_blk * 256 + static_cast<int>(rank) * BM;
-      const int b_row = n_blk * bn + static_cast<int>(rank) * half_bn;
+      const G2Tile tl = g2_tile(p, tile, bn, num_clusters);
+      if (tl.w == 0) continue;
+      const int a_row = tl.m_blk * 256 + static_cast<int>(rank) * BM;
+      // (a narrower tile still loads boxes of bn / 2 rows of W: the MMA reads the first w / 2 of them in each CTA)
+      const int b_row = tl.n0 + static_cast<int>(rank) * (tl.w >> 1);
       for (int kb = 0; kb < num_k; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * stage_bytes;
@@ -311,12 +312,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     G2_STAMP(4);  // last stage requested
   } else if (warp == 1 && rank == 0) {
     // ================================ MMA issuer (leader CTA) ================================
-    const uint32_t idesc = umma_idesc_bf16(256, bn, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const G2Tile tl = g2_tile(p, tile, bn, num_clusters);
+      if (tl.w == 0) continue;
+      const uint32_t idesc = umma_idesc_bf16(256, tl.w, 0, 0);
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * G2_ACC_COLS);
@@ -377,8 +380,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       uint32_t rphase = 0;       // bit i: parity of my_rbar[i]
       bool stores_out = false;   // this warp has TMA stores whose source reads may still be in flight
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m_blk = tile % p.num_m_tiles;
-        const int n_blk = tile / p.num_m_tiles;
+        const G2Tile tl = g2_tile(p, tile, bn, num_clusters);  // (always full-width tiles on this path: host)
+        if (tl.w == 0) continue;
+        const int m_blk = tl.m_blk;
+        const int tile_n0 = tl.n0;
         const int row0 = m_blk * 256 + static_cast<int>(rank) * BM + ew * 32;
         const int row = row0 + lane;
         const bool rows_ok = row0 < p.M;  // warp-uniform
@@ -406,7 +411,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
 #pragma unroll 1
           for (int i = 0; i < 2; ++i) {
             const int u = unit_par + 2 * i;
-            const int n0 = n_blk * bn + u * 64;
+            const int n0 = tile_n0 + u * 64;
             if (u >= U || n0 >= p.N) break;  // warp-uniform
             const bool is_tail = tail != 0 && u == U - 1;
             uint8_t* buf = out_stage + (ew * U + u) * 4096;
@@ -442,7 +447,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
           for (int i = 0; i < 2; ++i) {
             const int u = unit_par + 2 * i;
             const int c = u * 64;
-            const int n0 = n_blk * bn + c;
+            const int n0 = tile_n0 + c;
             if (u >= U || n0 >= p.N) break;  // warp-uniform
             const bool is_tail = tail != 0 && u == U - 1;
             uint8_t* buf = out_stage + (ew * U + u) * 4096;
@@ -531,8 +536,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       }
     } else
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int m_blk = tile % p.num_m_tiles;
-      const int n_blk = tile / p.num_m_tiles;
+      const G2Tile tl = g2_tile(p, tile, bn, num_clusters);
+      if (tl.w == 0) continue;
+      const int m_blk = tl.m_blk;
+      const int tw = tl.w;  // this tile's width
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       if (warp == 4) {
@@ -543,18 +550,18 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       const int row = row0 + lane;
       const uint32_t taddr = tmem_base + static_cast<uint32_t>(acc * G2_ACC_COLS) + (static_cast<uint32_t>(ew * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < bn; c += 64) {
-        const int n0 = n_blk * bn + c;
+      for (int c = 0; c < tw; c += 64) {
+        const int n0 = tl.n0 + c;
         if (n0 >= p.N || row0 >= p.M) break;  // warp-uniform
         if (EW == 8 && ((c >> 6) & 1) != unit_par) continue;
         uint32_t r0[32], r1[32];
         tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c), r0);
-        tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c + 32), r1);  // may run past bn: still inside the buffer
+        tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(c + 32), r1);  // may run past the tile: still inside the buffer
         tmem_ld_wait();
         // Units that lie completely inside this tile go through shared memory + TMA (columns past N and rows past M are
         // clipped by the tensor map); the narrower last unit of a tile whose width is not a multiple of 64 must not
         // touch its neighbour's columns and is stored directly.
-        const bool staged = p.tma_store && (bn - c >= 64);
+        const bool staged = p.tma_store && (tw - c >= 64);
         uint8_t* sbuf = my_stage + (stores % NBUF) * (32 * 128);
         if (staged && stores >= NBUF) {
           if (lane == 0) bulk_wait_group_read<NBUF - 1>();  // the store that last used this buffer has read it
@@ -567,7 +574,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
             v[j] = __uint_as_float(r0[j]);
             v[32 + j] = __uint_as_float(r1[j]);
           }
-          int ncols = bn - c;
+          int ncols = tw - c;
           if (ncols > 64) ncols = 64;
           if (p.N - n0 < ncols) ncols = p.N - n0;
           epilogue_unit<EPI>(p, v, row, n0, ncols, staged ? sbuf + lane * 128 : nullptr, lane & 7);
@@ -646,9 +653,9 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
     ORVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_MAX));
     attr_set = true;
   }
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int tiles = p.rem_width > 0 ? p.num_m_tiles * (p.n_full + 1) : p.num_m_tiles * p.num_n_tiles;
   const int clusters = sm_count() / 2;
-  const int grid = 2 * (tiles < clusters ? tiles : clusters);
+  const int grid = 2 * (tiles < clusters ? tiles : clusters);  // (a mixed tile list has at least `clusters` full tiles)
   const int smem = g2_smem_bytes(p, bn);
   ORVB_REQUIRE(smem <= G2_SMEM_MAX, ORVB_EINVAL, "gemm: shared-memory plan of %d bytes does not fit", smem);
   ORVB_CHECK_CUDA(launch_kernel(kern, dim3(grid), dim3(g2_threads(EPI)), smem, stream, true, ta, tb, to, tt, p, bn));
@@ -680,6 +687,11 @@ static int launch_gemm_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb
   return ORVB_EINVAL;
 }
 
+// ORVB_GEMM_MIXED_TILES=0: uniform tile widths only (A/B of the full + remainder tile list).
+static bool mixed_tiles_enabled() {
+  const char* e = getenv("ORVB_GEMM_MIXED_TILES");
+  return !(e != nullptr && e[0] == '0');
+}
 static bool fast_resid_enabled() {
   const char* e = getenv("ORVB_GEMM_FAST_RESID");  // read per call: the tests switch it inside one process
   return !(e != nullptr && e[0] == '0');
@@ -714,12 +726,18 @@ int gemm_pick_bn(int m, int n) {
 // (G2_WAVE_FIXED + bn) column units (operand streaming of the fixed 256 rows of A + per-tile pipeline turnaround);
 // widths are multiples of 16 (64 when the epilogue normalises whole 64-wide heads).
 constexpr int G2_WAVE_FIXED = 96;
-int gemm_pick_bn_pair(int m, int n, int epi) {
+// `rem_out` (may be NULL = uniform tiles only): width of the ONE narrower tile per 256-row block when cutting N into
+// n / bn full tiles plus a remainder beats every uniform width (GemmDev::rem_width); 0 = uniform.  `fast_ok`: the GEMM is
+// eligible for the prefetching gated-residual epilogue, which needs a tile of at most three 64-column units: a width
+// <= 192 within 3 % of the best modelled cost is preferred (the model does not see the epilogue).
+int gemm_pick_bn_pair2(int m, int n, int epi, bool fast_ok, int* rem_out) {
   const int clusters = sm_count() / 2;
   const int mt = (m + 255) / 256;
   const int step = (epi == ORVB_EPI_QKV) ? 64 : 16;
-  int best_bn = 256;
+  int best_bn = 256, best_rem = 0;
   double best = 1e30;
+  int fast_bn = 0;
+  double fast_cost = 1e30;
   for (int bn = 256; bn >= 64; bn -= step) {
     const int nt = (n + bn - 1) / bn;
     const long tiles = static_cast<long>(mt) * nt;
@@ -728,10 +746,36 @@ int gemm_pick_bn_pair(int m, int n, int epi) {
     if (cost < best - 1e-9) {
       best = cost;
       best_bn = bn;
+      best_rem = 0;
+    }
+    if (fast_ok && bn <= 192 && cost < fast_cost - 1e-9) {
+      fast_cost = cost;
+      fast_bn = bn;
+    }
+    const int q = n / bn, r = n % bn;
+    if (rem_out != nullptr && !fast_ok && r >= 32 && r % step == 0 && static_cast<long>(mt) * q >= clusters) {
+      const long full = static_cast<long>(mt) * q;
+      const long base = full / clusters, extra = full % clusters;
+      const long n_light = clusters - extra;
+      const long per_light = (mt + n_light - 1) / n_light;
+      const double heavy = extra > 0 ? static_cast<double>(base + 1) * (G2_WAVE_FIXED + bn) : 0.0;
+      const double light = static_cast<double>(base) * (G2_WAVE_FIXED + bn) + static_cast<double>(per_light) * (G2_WAVE_FIXED + r);
+      const double c2 = heavy > light ? heavy : light;
+      if (c2 < best - 1e-9) {
+        best = c2;
+        best_bn = bn;
+        best_rem = r;
+      }
     }
   }
+  if (fast_ok && fast_bn > 0 && fast_cost <= 1.03 * best) {
+    best_bn = fast_bn;
+    best_rem = 0;
+  }
+  if (rem_out != nullptr) *rem_out = best_rem;
   return best_bn;
 }
+int gemm_pick_bn_pair(int m, int n, int epi) { return gemm_pick_bn_pair2(m, n, epi, false, nullptr); }
 
 // bn > 0: 1-CTA kernel with that N tile; bn < 0: CTA-pair kernel with N tile -bn.
 int gemm_launch_prepared(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tt,
@@ -770,9 +814,11 @@ int gemm_prepare(const orvb_gemm_args* a, int bn_override, CUtensorMap* ta, CUte
                  ORVB_ESHAPE, "orvb_gemm_bf16: gate pitch/offsets must be multiples of 4");
   }
   // More than one 128-row tile: CTA pairs (M = 256 MMAs); otherwise the 1-CTA kernel.
-  int bn;
+  int bn, rem = 0;
+  const bool fast_ok = a->epilogue == ORVB_EPI_GATE_RESID && a->resid != nullptr && a->resid == a->out && a->ldr == a->ldo &&
+                       a->resid_mod == 0 && a->src_rows == 0 && a->mv_tokens == 0 && !a->out_f32 && fast_resid_enabled();
   if (bn_override != 0) bn = bn_override;
-  else if (a->m > BM) bn = -gemm_pick_bn_pair(a->m, a->n, a->epilogue);
+  else if (a->m > BM) bn = -gemm_pick_bn_pair2(a->m, a->n, a->epilogue, fast_ok, mixed_tiles_enabled() ? &rem : nullptr);
   else bn = gemm_pick_bn(a->m, a->n);
   const bool pair = bn < 0;
   if (pair) {
@@ -803,8 +849,7 @@ int gemm_prepare(const orvb_gemm_args* a, int bn_override, CUtensorMap* ta, CUte
   // Gated residual written in place over its own residual (attn-out / FF2 of every block): the epilogue that prefetches
   // the residual tiles by TMA.  One staging tile per 64-column unit of the CTA's half tile -> needs the room a narrower
   // B stage leaves (tile widths up to 192).  ORVB_GEMM_FAST_RESID=0 keeps the generic epilogue (A/B, bit-identical).
-  if (pair && tma_store && a->epilogue == ORVB_EPI_GATE_RESID && a->resid == a->out && a->ldr == a->ldo &&
-      a->resid_mod == 0 && fast_resid_enabled()) {
+  if (pair && tma_store && fast_ok) {
     const int w = -bn, units = (w + 63) / 64, tail = w % 64;
     GemmDev f = d;
     f.stage_bytes = G2_A_BYTES + (((w / 2) * BK * 2 + 1023) & ~1023);
@@ -839,6 +884,19 @@ int gemm_prepare(const orvb_gemm_args* a, int bn_override, CUtensorMap* ta, CUte
   d.rope_cos = a->rope_cos; d.rope_sin = a->rope_sin;
   d.num_m_tiles = pair ? (a->m + 2 * BM - 1) / (2 * BM) : (a->m + BM - 1) / BM;
   d.num_n_tiles = pair ? (a->n - bn - 1) / (-bn) : (a->n + bn - 1) / bn;
+  d.tile_end = d.num_m_tiles * d.num_n_tiles;
+  d.n_full = 0;
+  d.rem_width = 0;
+  if (pair && rem > 0 && !d.fast_resid) {
+    // n / bn full tiles + one narrower tile per 256-row block, the narrow ones placed on the clusters with one full tile
+    // less (g2_tile): virtual indices [0, full) then rows of `clusters` slots of which the first n_light hold a tile
+    const int clusters = sm_count() / 2;
+    const int full = d.num_m_tiles * (a->n / -bn);
+    const int n_light = clusters - full % clusters;
+    d.n_full = a->n / -bn;
+    d.rem_width = rem;
+    d.tile_end = full + ((d.num_m_tiles + n_light - 1) / n_light) * clusters;
+  }
   *p = d;
   *bn_out = bn;
   return ORVB_OK;
@@ -897,5 +955,16 @@ extern "C" int orvb_gemm_set_debug(void* dev_buf) {
 extern "C" int orvb_gemm_tile_width(int32_t m, int32_t n, int32_t epilogue) {
   using namespace orvb;
   if (m <= 0 || n <= 0) return 0;
-  return m > BM ? -gemm_pick_bn_pair(m, n, epilogue) : gemm_pick_bn(m, n);
+  int rem = 0;
+  return m > BM ? -gemm_pick_bn_pair2(m, n, epilogue, false, mixed_tiles_enabled() ? &rem : nullptr) : gemm_pick_bn(m, n);
+}
+
+// Width of the one narrower tile per 256-row block when orvb_gemm_bf16 cuts N into n / width full tiles plus a remainder
+// (0 = uniform tiles; always 0 for the single-CTA kernel).
+extern "C" int orvb_gemm_tile_remainder(int32_t m, int32_t n, int32_t epilogue) {
+  using namespace orvb;
+  if (m <= BM || n <= 0 || !mixed_tiles_enabled()) return 0;
+  int rem = 0;
+  (void)gemm_pick_bn_pair2(m, n, epilogue, false, &rem);
+  return rem;
 }

@@ -31,7 +31,36 @@ struct GemmDev {
   int out_stage_bytes;  // output staging area behind the stages
   int fast_resid;       // gated-residual epilogue with the residual tile prefetched by TMA (see gemm2_bf16_kernel)
   int k_wrap;           // > 0: W has k_wrap columns, walked cyclically along K (orvb_gemm_args.k_wrap)
+  // CTA-pair kernel tile list: `tile_end` virtual tile indices, cluster c takes c, c + C, ...  With rem_width == 0 every
+  // tile is `bn` wide (the last one of a row may hang over N).  With rem_width > 0 the N range is cut into n_full tiles
+  // of bn columns plus ONE narrower tile of rem_width columns per 256-row block; the narrow tiles are numbered so that
+  // they fall on the clusters that got one full tile less (g2_tile): QKV of config 2 (N = 5760) runs 4 x 256 columns per
+  // cluster instead of 6 x 192.
+  int tile_end, n_full, rem_width;
 };
+
+struct G2Tile {
+  int m_blk, n0, w;  // 256-row block, first column, width; w == 0: this virtual index holds no tile
+};
+__device__ __forceinline__ G2Tile g2_tile(const GemmDev& p, int v, int bn, int num_clusters) {
+  G2Tile t;
+  const int mt = p.num_m_tiles;
+  const int full = (p.rem_width > 0) ? mt * p.n_full : p.tile_end;
+  if (v < full) {
+    t.m_blk = v % mt;
+    t.n0 = (v / mt) * bn;
+    t.w = bn;
+    return t;
+  }
+  const int wv = v - full;
+  const int row = wv / num_clusters, col = wv - row * num_clusters;
+  const int n_light = num_clusters - full % num_clusters;  // clusters with one full tile less (all of them if it divides)
+  const int k = row * n_light + col;
+  t.m_blk = k;
+  t.n0 = p.n_full * bn;
+  t.w = (col < n_light && k < mt) ? p.rem_width : 0;
+  return t;
+}
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 bytes = one swizzle span

@@ -236,7 +236,10 @@ def test_gemm_tile_choice_for_the_config2_block():
     from orv_b200 import _lib as L
     lib = L.load()
     S, D, FF = 3226, 1920, 7680
-    assert lib.orvb_gemm_tile_width(S, 3 * D, L.EPI_QKV) == -192
+    # QKV: 22 tiles of 256 columns + one of 128 per 256-row block = at most 4 x 256 columns per SM pair (6 x 192 uniform)
+    assert lib.orvb_gemm_tile_width(S, 3 * D, L.EPI_QKV) == -256
+    assert lib.orvb_gemm_tile_remainder(S, 3 * D, L.EPI_QKV) == 128
+    assert lib.orvb_gemm_tile_remainder(S, FF, L.EPI_GELU) == 0
     assert lib.orvb_gemm_tile_width(S, D, L.EPI_GATE_RESID) == -176
     assert lib.orvb_gemm_tile_width(S, FF, L.EPI_GELU) == -240
     for n in (64, 128, 1920, 3072, 5760, 9216, 12288):
