@@ -730,7 +730,7 @@ constexpr int G2_WAVE_FIXED = 96;
 // n / bn full tiles plus a remainder beats every uniform width (GemmDev::rem_width); 0 = uniform.  `fast_ok`: the GEMM is
 // eligible for the prefetching gated-residual epilogue, which needs a tile of at most three 64-column units: a width
 // <= 192 within 3 % of the best modelled cost is preferred (the model does not see the epilogue).
-int gemm_pick_bn_pair2(int m, int n, int epi, bool fast_ok, int* rem_out) {
+int gemm_pick_bn_pair2(int m, int n, int k, int epi, bool fast_ok, int* rem_out) {
   const int clusters = sm_count() / 2;
   const int mt = (m + 255) / 256;
   const int step = (epi == ORVB_EPI_QKV) ? 64 : 16;
@@ -768,14 +768,24 @@ int gemm_pick_bn_pair2(int m, int n, int epi, bool fast_ok, int* rem_out) {
       }
     }
   }
-  if (fast_ok && fast_bn > 0 && fast_cost <= 1.03 * best) {
+  // How much modelled mainloop cost the prefetching epilogue is worth: with a short K the generic epilogue of a 4-unit
+  // tile is as long as the tile's mainloop (config 4's attn-out, K = 3072: 72.8 us at 240 columns, 66.0 us at 192 with the
+  // prefetching epilogue, profiles/r02zz_cfg4_pref*.json); with K = 4 D it hides behind the mainloop and the wider tile
+  // wins (FF2: 226.7 vs 228.1 us).  ORVB_GEMM_FAST_PREF overrides both.
+  static const double pref_env = [] {
+    const char* e = getenv("ORVB_GEMM_FAST_PREF");
+    const double v = e != nullptr ? atof(e) : 0.0;
+    return v >= 1.0 ? v : 0.0;
+  }();
+  const double fast_pref = pref_env > 0.0 ? pref_env : (k <= 4096 ? 1.20 : 1.03);
+  if (fast_ok && fast_bn > 0 && fast_cost <= fast_pref * best) {
     best_bn = fast_bn;
     best_rem = 0;
   }
   if (rem_out != nullptr) *rem_out = best_rem;
   return best_bn;
 }
-int gemm_pick_bn_pair(int m, int n, int epi) { return gemm_pick_bn_pair2(m, n, epi, false, nullptr); }
+int gemm_pick_bn_pair(int m, int n, int epi) { return gemm_pick_bn_pair2(m, n, 1 << 30, epi, false, nullptr); }
 
 // bn > 0: 1-CTA kernel with that N tile; bn < 0: CTA-pair kernel with N tile -bn.
 int gemm_launch_prepared(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tt,
@@ -818,7 +828,7 @@ int gemm_prepare(const orvb_gemm_args* a, int bn_override, CUtensorMap* ta, CUte
   const bool fast_ok = a->epilogue == ORVB_EPI_GATE_RESID && a->resid != nullptr && a->resid == a->out && a->ldr == a->ldo &&
                        a->resid_mod == 0 && a->src_rows == 0 && a->mv_tokens == 0 && !a->out_f32 && fast_resid_enabled();
   if (bn_override != 0) bn = bn_override;
-  else if (a->m > BM) bn = -gemm_pick_bn_pair2(a->m, a->n, a->epilogue, fast_ok, mixed_tiles_enabled() ? &rem : nullptr);
+  else if (a->m > BM) bn = -gemm_pick_bn_pair2(a->m, a->n, a->k, a->epilogue, fast_ok, mixed_tiles_enabled() ? &rem : nullptr);
   else bn = gemm_pick_bn(a->m, a->n);
   const bool pair = bn < 0;
   if (pair) {
@@ -956,7 +966,7 @@ extern "C" int orvb_gemm_tile_width(int32_t m, int32_t n, int32_t epilogue) {
   using namespace orvb;
   if (m <= 0 || n <= 0) return 0;
   int rem = 0;
-  return m > BM ? -gemm_pick_bn_pair2(m, n, epilogue, false, mixed_tiles_enabled() ? &rem : nullptr) : gemm_pick_bn(m, n);
+  return m > BM ? -gemm_pick_bn_pair2(m, n, 1 << 30, epilogue, false, mixed_tiles_enabled() ? &rem : nullptr) : gemm_pick_bn(m, n);
 }
 
 // Width of the one narrower tile per 256-row block when orvb_gemm_bf16 cuts N into n / width full tiles plus a remainder
@@ -965,6 +975,6 @@ extern "C" int orvb_gemm_tile_remainder(int32_t m, int32_t n, int32_t epilogue) 
   using namespace orvb;
   if (m <= BM || n <= 0 || !mixed_tiles_enabled()) return 0;
   int rem = 0;
-  (void)gemm_pick_bn_pair2(m, n, epilogue, false, &rem);
+  (void)gemm_pick_bn_pair2(m, n, 1 << 30, epilogue, false, &rem);
   return rem;
 }
