@@ -257,44 +257,60 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttDev p) {
       }
     }
     issue_qk(1, 0);
-    for (int j = 0; j < n_kv; ++j) {
+    auto issue_pv = [&](int t, int j) {
       const int st = j % A5_STAGES;
-      const uint32_t par = static_cast<uint32_t>(j & 1);
-      if (j + 1 < n_kv) {
-#pragma unroll 1
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(&s_free[t], par);
-          tc_fence_after();
-          A5_STAMP(16 + t, j, 0);
-          issue_qk(t, j + 1);
-          A5_STAMP(16 + t, j, 1);
-        }
-      }
-#pragma unroll 1
-      for (int t = 0; t < 2; ++t) {
-        mbar_wait(&p_full[t], par);
+      mbar_wait(&p_full[t], static_cast<uint32_t>(j & 1));
+      tc_fence_after();
+      A5_STAMP(16 + t, j, 2);
+      if (t == 0) {  // tile 0 is the first user of V_j (tile 1's PV of the same step is issued one iteration later)
+        mbar_wait(&v_full[st], static_cast<uint32_t>((j / A5_STAGES) & 1));
         tc_fence_after();
-        A5_STAMP(16 + t, j, 2);
-        if (t == 0) {
-          mbar_wait(&v_full[st], static_cast<uint32_t>((j / A5_STAGES) & 1));
-          tc_fence_after();
-        }
-        const uint64_t v_desc = umma_desc_sw128(smem_u32(smem + A5_OFF_V + st * A5_TILE));
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < A5_BK / 16; ++k) {
-            // A: 16 keys = 8 TMEM columns of bf16 pairs.  B: keys k*16 .. +16 = 16 rows of 128 bytes.
-            umma_f16_ts(tmem_base + A5_COL_O + static_cast<uint32_t>(t * 64),
-                        tmem_base + A5_COL_P + static_cast<uint32_t>(t * 64 + k * 8),
-                        v_desc + static_cast<uint64_t>((k * 16 * 128) >> 4), idesc_pv, static_cast<uint32_t>((j | k) != 0));
-          }
-          tc_commit(&o_full[t]);
-          if (t == 1) tc_commit(&v_empty[st]);
-        }
-        __syncwarp();
-        A5_STAMP(16 + t, j, 3);
       }
+      const uint64_t v_desc = umma_desc_sw128(smem_u32(smem + A5_OFF_V + st * A5_TILE));
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < A5_BK / 16; ++k) {
+          // A: 16 keys = 8 TMEM columns of bf16 pairs.  B: keys k*16 .. +16 = 16 rows of 128 bytes.
+          umma_f16_ts(tmem_base + A5_COL_O + static_cast<uint32_t>(t * 64),
+                      tmem_base + A5_COL_P + static_cast<uint32_t>(t * 64 + k * 8),
+                      v_desc + static_cast<uint64_t>((k * 16 * 128) >> 4), idesc_pv, static_cast<uint32_t>((j | k) != 0));
+        }
+        tc_commit(&o_full[t]);
+        if (t == 1) tc_commit(&v_empty[st]);
+      }
+      __syncwarp();
+      A5_STAMP(16 + t, j, 3);
+    };
+    auto issue_next_qk = [&](int t, int j) {  // QK^T of step j + 1 as soon as the tile has copied S_j out of TMEM
+      if (j + 1 >= n_kv) return;
+      mbar_wait(&s_free[t], static_cast<uint32_t>(j & 1));
+      tc_fence_after();
+      A5_STAMP(16 + t, j, 0);
+      issue_qk(t, j + 1);
+      A5_STAMP(16 + t, j, 1);
+    };
+    // The single issuing thread works through its waits IN PROGRAM ORDER, so the order has to be the order in which the
+    // events arrive.  Query tile 1 runs about half a key step behind tile 0 (the stagger), which makes that order
+    //   S_0(j) copied -> P_1(j-1) written -> S_1(j) copied -> P_0(j) written.
+    // The natural program order (both QK^T of the next step, then both PV of this one) kept QK_0(j+1) waiting behind
+    // PV_1(j-1), i.e. behind tile 1's exponentials: tile 0 found its next S 250 clk late and tile 1 100 clk late in every
+    // key step (profiles/r02o_attn5_timeline.log, column "s_full wait").
+    for (int j = 0; j < n_kv; ++j) {
+#ifdef ORVB_ATT_NATURAL_ORDER
+      issue_next_qk(0, j);
+      issue_next_qk(1, j);
+      issue_pv(0, j);
+      issue_pv(1, j);
+#else
+      issue_next_qk(0, j);
+      if (j > 0) issue_pv(1, j - 1);
+      issue_next_qk(1, j);
+      issue_pv(0, j);
+#endif
     }
+#ifndef ORVB_ATT_NATURAL_ORDER
+    issue_pv(1, n_kv - 1);
+#endif
   } else {
     // ======================================= softmax (one thread per query row) ==================
     const int t = warp >> 2;

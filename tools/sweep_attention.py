@@ -36,6 +36,7 @@ if len(sys.argv) > 1:
 for kind, stagger, emu in settings:
     env = dict(os.environ)
     if kind == "v5":
-        env.update(ORVB_LIB_PATH="orv_b200/liborv_b200_exp.so", ORVB_ATT_STAGGER=str(stagger), ORVB_ATT_EMU=str(emu))
+        env.update(ORVB_LIB_PATH=os.environ.get("ORVB_SWEEP_LIB", "orv_b200/liborv_b200_exp.so"), ORVB_ATT_STAGGER=str(stagger),
+                   ORVB_ATT_EMU=str(emu))
     r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True, timeout=300)
     print(f"{kind} stagger={stagger} emu={emu}/8: {r.stdout.strip() or r.stderr.strip()[-300:]}", flush=True)
