@@ -289,14 +289,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttDev p) {
       issue_qk(t, j + 1);
       A5_STAMP(16 + t, j, 1);
     };
-    // The single issuing thread works through its waits IN PROGRAM ORDER, so the order has to be the order in which the
-    // events arrive.  Query tile 1 runs about half a key step behind tile 0 (the stagger), which makes that order
-    //   S_0(j) copied -> P_1(j-1) written -> S_1(j) copied -> P_0(j) written.
-    // The natural program order (both QK^T of the next step, then both PV of this one) kept QK_0(j+1) waiting behind
-    // PV_1(j-1), i.e. behind tile 1's exponentials: tile 0 found its next S 250 clk late and tile 1 100 clk late in every
-    // key step (profiles/r02o_attn5_timeline.log, column "s_full wait").
+    // The single issuing thread works through its waits IN PROGRAM ORDER.  Query tile 1 runs about half a key step behind
+    // tile 0 (the stagger), so the events arrive as S_0(j) copied -> P_1(j-1) written -> S_1(j) copied -> P_0(j) written,
+    // and the natural program order below (both QK^T of the next step, then both PV of this one) keeps QK_0(j+1) waiting
+    // behind PV_1(j-1): a softmax warp finds its next S 100 - 260 clk late in every key step
+    // (profiles/r02o_attn5_timeline.log, column "s_full wait").  Issuing in arrival order (-DORVB_ATT_EVENT_ORDER) removes
+    // that wait and is 1.2 % faster in isolation (121.0 -> 119.6 us) but 0.4 % SLOWER inside the power-capped step, twice
+    // in an alternating A/B on one box (attention 145.2 -> 146.6 us, clip 596.2 -> 598.9 ms, profiles/r03c_*): the
+    // natural order stays.
     for (int j = 0; j < n_kv; ++j) {
-#ifdef ORVB_ATT_NATURAL_ORDER
+#ifndef ORVB_ATT_EVENT_ORDER
       issue_next_qk(0, j);
       issue_next_qk(1, j);
       issue_pv(0, j);
@@ -308,7 +310,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttDev p) {
       issue_pv(0, j);
 #endif
     }
-#ifndef ORVB_ATT_NATURAL_ORDER
+#ifdef ORVB_ATT_EVENT_ORDER
     issue_pv(1, n_kv - 1);
 #endif
   } else {
