@@ -127,6 +127,12 @@ int orvb_gemm_tile_width(int32_t m, int32_t n, int32_t epilogue);
  * pairs better than any uniform width (QKV of a 2B block: 22 x 256 + 128 instead of 30 x 192), the width of that narrower
  * tile; 0 = uniform tiles. */
 int orvb_gemm_tile_remainder(int32_t m, int32_t n, int32_t epilogue);
+/* The tile list orvb_gemm_bf16 runs for an [m, n] x k problem on the CTA-pair kernel, in the order the SM pairs walk it
+ * (host arithmetic only): up to `capacity` records {sm_pair, first_row, first_column, width} of 4 x int32.  Returns the
+ * number of tiles (0: single-CTA kernel) or a negative error code.  in_place_resid: a GATE_RESID call written over its own
+ * residual.  Used by the host-side coverage test of the mixed tile list. */
+int orvb_gemm_tile_list(int32_t m, int32_t n, int32_t k, int32_t epilogue, int32_t in_place_resid, int32_t* out,
+                        int32_t capacity);
 /* Test hook: orvb_gemm_bf16 with a forced tile.  bn in {64, 128, 192, 256} = single-CTA kernel with that N tile; -bn
  * (a multiple of 16 in 32..256) = CTA-pair kernel.  Used by the bit-identity test of the two kernels and by the tile
  * sweeps under tools/. */

@@ -184,7 +184,7 @@ class SpatialNormArgs(C.Structure):
 
 EXPORTED_SYMBOLS = [
     "orvb_version", "orvb_last_error", "orvb_check_device",
-    "orvb_gemm_bf16", "orvb_gemm_bf16_bn", "orvb_gemm_tile_width", "orvb_gemm_tile_remainder", "orvb_attention_bf16", "orvb_attention", "orvb_attention_set_rescale_threshold",
+    "orvb_gemm_bf16", "orvb_gemm_bf16_bn", "orvb_gemm_tile_width", "orvb_gemm_tile_remainder", "orvb_gemm_tile_list", "orvb_attention_bf16", "orvb_attention", "orvb_attention_set_rescale_threshold",
     "orvb_attention_set_debug", "orvb_ln_modulate", "orvb_skinny_linear",
     "orvb_patchify", "orvb_unpatchify",
     "orvb_model_create", "orvb_model_destroy", "orvb_model_bind_weights", "orvb_workspace_bytes",
@@ -219,6 +219,9 @@ def load() -> C.CDLL:
     if hasattr(lib, "orvb_gemm_tile_width"):
         lib.orvb_gemm_tile_width.argtypes = [c_int, c_int, c_int]
         lib.orvb_gemm_tile_width.restype = c_int
+    if hasattr(lib, "orvb_gemm_tile_list"):
+        lib.orvb_gemm_tile_list.argtypes = [c_int, c_int, c_int, c_int, c_int, c_void_p, c_int]
+        lib.orvb_gemm_tile_list.restype = c_int
     if hasattr(lib, "orvb_gemm_tile_remainder"):
         lib.orvb_gemm_tile_remainder.argtypes = [c_int, c_int, c_int]
         lib.orvb_gemm_tile_remainder.restype = c_int

@@ -836,26 +836,29 @@ int gemm_prepare(const orvb_gemm_args* a, int bn_override, CUtensorMap* ta, CUte
     ORVB_REQUIRE(w >= 32 && w <= 256 && w % 16 == 0, ORVB_EINVAL, "gemm: pair tile width %d must be a multiple of 16 in [32, 256]", w);
     ORVB_REQUIRE(a->epilogue != ORVB_EPI_QKV || w % 64 == 0, ORVB_EINVAL, "gemm: the QKV epilogue needs a tile width that is a multiple of 64 (got %d)", w);
   }
-  int rc = make_tmap_2d_bf16(ta, a->a, a->m, a->k, a->lda, BM, BK);
+  const bool maps = ta != nullptr;  // planning only (orvb_gemm_tile_list, no driver needed) when the maps are not asked for
+  int rc = maps ? make_tmap_2d_bf16(ta, a->a, a->m, a->k, a->lda, BM, BK) : ORVB_OK;
   if (rc != ORVB_OK) return rc;
   ORVB_REQUIRE(a->k_wrap == 0 || (a->k_wrap > 0 && a->k_wrap % BK == 0 && a->k % a->k_wrap == 0), ORVB_ESHAPE,
                "orvb_gemm_bf16: k_wrap %d must be a multiple of %d dividing k = %d", a->k_wrap, BK, a->k);
-  rc = make_tmap_2d_bf16(tb, a->w, a->n, a->k_wrap > 0 ? a->k_wrap : a->k, a->ldw, pair ? (-bn) / 2 : bn, BK);
+  if (maps) rc = make_tmap_2d_bf16(tb, a->w, a->n, a->k_wrap > 0 ? a->k_wrap : a->k, a->ldw, pair ? (-bn) / 2 : bn, BK);
   if (rc != ORVB_OK) return rc;
   // Output through TMA (pair kernel, rows written in place): [32 rows x 64 cols] boxes of the [M, N] output
   const bool tma_store = pair && a->src_rows == 0 && a->mv_tokens == 0 && !a->out_f32;
-  if (tma_store) {
-    rc = make_tmap_2d_bf16(to, a->out, a->m, a->n, a->ldo, 32, 64);
-    if (rc != ORVB_OK) return rc;
-  } else {
-    *to = *ta;  // unused placeholder
+  if (maps) {
+    if (tma_store) {
+      rc = make_tmap_2d_bf16(to, a->out, a->m, a->n, a->ldo, 32, 64);
+      if (rc != ORVB_OK) return rc;
+    } else {
+      *to = *ta;  // unused placeholder
+    }
   }
   GemmDev d;
   d.k_wrap = a->k_wrap;
   d.stage_bytes = G2_STAGE_BYTES;
   d.out_stage_bytes = G2_OUT_STAGE_BYTES;
   d.fast_resid = 0;
-  *tt = *to;  // (placeholder unless the fast epilogue needs a tail map)
+  if (maps) *tt = *to;  // (placeholder unless the fast epilogue needs a tail map)
   // Gated residual written in place over its own residual (attn-out / FF2 of every block): the epilogue that prefetches
   // the residual tiles by TMA.  One staging tile per 64-column unit of the CTA's half tile -> needs the room a narrower
   // B stage leaves (tile widths up to 192).  ORVB_GEMM_FAST_RESID=0 keeps the generic epilogue (A/B, bit-identical).
@@ -869,7 +872,7 @@ int gemm_prepare(const orvb_gemm_args* a, int bn_override, CUtensorMap* ta, CUte
       d.stage_bytes = f.stage_bytes;
       d.out_stage_bytes = f.out_stage_bytes;
       d.fast_resid = 1;
-      if (tail != 0) {
+      if (tail != 0 && maps) {
         rc = make_tmap_2d_bf16_plain(tt, a->out, a->m, a->n, a->ldo, 32, tail);
         if (rc != ORVB_OK) return rc;
       }
@@ -910,6 +913,11 @@ int gemm_prepare(const orvb_gemm_args* a, int bn_override, CUtensorMap* ta, CUte
   *p = d;
   *bn_out = bn;
   return ORVB_OK;
+}
+
+// The planning half of gemm_prepare alone: kernel / tile choice and the tile list, no tensor maps (no driver call).
+int gemm_plan(const orvb_gemm_args* a, int bn_override, GemmDev* p, int* bn_out) {
+  return gemm_prepare(a, bn_override, nullptr, nullptr, nullptr, nullptr, p, bn_out);
 }
 
 int gemm_run(const orvb_gemm_args* a, cudaStream_t stream) {
@@ -967,6 +975,50 @@ extern "C" int orvb_gemm_tile_width(int32_t m, int32_t n, int32_t epilogue) {
   if (m <= 0 || n <= 0) return 0;
   int rem = 0;
   return m > BM ? -gemm_pick_bn_pair2(m, n, 1 << 30, epilogue, false, mixed_tiles_enabled() ? &rem : nullptr) : gemm_pick_bn(m, n);
+}
+
+// The tile list orvb_gemm_bf16 would run for this problem on the CTA-pair kernel, in the order the clusters walk it
+// (host arithmetic only; the same g2_tile() the kernel decodes its virtual tile indices with): up to `capacity` records
+// of {cluster, first row, first column, width}.  Returns the number of tiles (0 for the single-CTA kernel), or a negative
+// error code.  `in_place_resid` = the GATE_RESID call writes over its own residual (eligible for the prefetching epilogue).
+extern "C" int orvb_gemm_tile_list(int32_t m, int32_t n, int32_t k, int32_t epilogue, int32_t in_place_resid, int32_t* out,
+                                   int32_t capacity) {
+  using namespace orvb;
+  if (m <= BM || n <= 0) return 0;
+  orvb_gemm_args a;
+  memset(&a, 0, sizeof(a));
+  // pointers are only compared / checked for alignment, never dereferenced, by the planning part of gemm_prepare
+  static uint8_t dummy[64] __attribute__((aligned(64)));
+  a.a = dummy; a.w = dummy; a.out = dummy;
+  a.m = m; a.n = n; a.k = k; a.lda = k; a.ldw = k; a.ldo = n; a.epilogue = epilogue;
+  if (epilogue == ORVB_EPI_QKV) {
+    a.qk_dim = n / 3;
+    a.q_norm_w = a.q_norm_b = a.k_norm_w = a.k_norm_b = dummy;
+  }
+  if (in_place_resid) { a.resid = dummy; a.ldr = n; }
+  GemmDev p;
+  int bn = 0;
+  const int rc = gemm_plan(&a, 0, &p, &bn);
+  if (rc != ORVB_OK) return rc;
+  if (bn >= 0) return 0;
+  const int clusters_all = sm_count() / 2;
+  const int real_tiles = p.rem_width > 0 ? p.num_m_tiles * (p.n_full + 1) : p.num_m_tiles * p.num_n_tiles;
+  const int clusters = real_tiles < clusters_all ? real_tiles : clusters_all;
+  int count = 0;
+  for (int c = 0; c < clusters; ++c) {
+    for (int v = c; v < p.tile_end; v += clusters) {
+      const G2Tile t = g2_tile(p, v, -bn, clusters);
+      if (t.w == 0) continue;
+      if (out != nullptr && count < capacity) {
+        out[4 * count + 0] = c;
+        out[4 * count + 1] = t.m_blk * 256;
+        out[4 * count + 2] = t.n0;
+        out[4 * count + 3] = t.w;
+      }
+      ++count;
+    }
+  }
+  return count;
 }
 
 // Width of the one narrower tile per 256-row block when orvb_gemm_bf16 cuts N into n / width full tiles plus a remainder

@@ -42,7 +42,7 @@ struct GemmDev {
 struct G2Tile {
   int m_blk, n0, w;  // 256-row block, first column, width; w == 0: this virtual index holds no tile
 };
-__device__ __forceinline__ G2Tile g2_tile(const GemmDev& p, int v, int bn, int num_clusters) {
+__host__ __device__ __forceinline__ G2Tile g2_tile(const GemmDev& p, int v, int bn, int num_clusters) {
   G2Tile t;
   const int mt = p.num_m_tiles;
   const int full = (p.rem_width > 0) ? mt * p.n_full : p.tile_end;

@@ -250,3 +250,59 @@ def test_gemm_tile_choice_for_the_config2_block():
     assert lib.orvb_gemm_tile_width(128, 512, L.EPI_BIAS) > 0
     assert lib.orvb_gemm_tile_width(6, 512, L.EPI_BIAS) in (64, 128, 192, 256)
     assert lib.orvb_gemm_tile_width(0, 512, L.EPI_BIAS) == 0
+
+
+def _tile_list(lib, m, n, k, epi, in_place=0):
+    import ctypes as C
+    cap = 8192
+    buf = (C.c_int32 * (4 * cap))()
+    cnt = lib.orvb_gemm_tile_list(m, n, k, epi, in_place, buf, cap)
+    assert 0 <= cnt <= cap, cnt
+    return [tuple(buf[4 * i: 4 * i + 4]) for i in range(cnt)]
+
+
+def test_gemm_tile_lists_cover_the_output_exactly_once():
+    """Host-side check of the CTA-pair kernel's tile list (the same g2_tile() the kernel decodes its virtual tile indices
+    with, orv_b200/csrc/gemm_common.cuh): for uniform AND mixed lists (n / width full tiles + one narrower tile per 256-row
+    block, placed on the SM pairs with one full tile less) every output element belongs to exactly one tile, widths respect
+    the epilogue's granularity, and the busiest SM pair of a mixed list has no more columns than with uniform tiles."""
+    import numpy as np
+    from orv_b200 import _lib as L
+    lib = L.load()
+    shapes = [(3226, 5760, 1920, L.EPI_QKV, 0), (3226, 5760, 128, L.EPI_BIAS, 0), (6452, 5760, 1920, L.EPI_QKV, 0),
+              (4052, 3200, 192, L.EPI_BIAS, 0), (3226, 1920, 1920, L.EPI_GATE_RESID, 1), (3226, 1920, 7680, L.EPI_GATE_RESID, 1),
+              (3226, 7680, 1920, L.EPI_GELU, 0), (12876, 1920, 1920, L.EPI_GATE_RESID, 1), (4052, 3072, 3072, L.EPI_GATE_RESID, 1),
+              (4052, 9216, 3072, L.EPI_QKV, 0), (300, 11520, 1024, L.EPI_BIAS, 0), (129, 40, 8, L.EPI_BIAS, 0),
+              (18944, 1344, 64, L.EPI_BIAS, 0), (19000, 2112, 64, L.EPI_QKV, 0), (2000, 200, 64, L.EPI_GATE_RESID, 1)]
+    mixed_seen = 0
+    for (m, n, k, epi, inplace) in shapes:
+        tiles = _tile_list(lib, m, n, k, epi, inplace)
+        assert tiles, (m, n)
+        cover = np.zeros(((m + 255) // 256, n), dtype=np.int32)
+        load = {}
+        widths = set()
+        for (c, r0, n0, w) in tiles:
+            assert r0 % 256 == 0 and 0 <= r0 < m and n0 < n and 16 <= w <= 256 and w % 16 == 0, (m, n, c, r0, n0, w)
+            if epi == L.EPI_QKV:
+                assert w % 64 == 0 and n0 % 64 == 0
+            cover[r0 // 256, n0:min(n0 + w, n)] += 1
+            load[c] = load.get(c, 0) + w
+            widths.add(w)
+        assert (cover == 1).all(), f"{(m, n)}: {(cover != 1).sum()} output columns not covered exactly once"
+        assert len(load) <= 74 and len(widths) <= 2
+        rem = lib.orvb_gemm_tile_remainder(m, n, epi) if not inplace else 0
+        if len(widths) == 2:
+            mixed_seen += 1
+            bn = max(widths)
+            uniform_rounds = -(-(((m + 255) // 256) * (-(-n // bn))) // 74)
+            assert max(load.values()) <= uniform_rounds * bn
+            assert rem == min(widths)
+        if inplace and n % 64 == 0 and k <= 4096:
+            assert max(widths) <= 192  # room for the prefetching gated-residual epilogue
+    assert mixed_seen >= 3
+    # the headline case: QKV of a 2B block, at most 4 x 256 columns per SM pair (6 x 192 with uniform tiles)
+    tiles = _tile_list(lib, 3226, 5760, 1920, L.EPI_QKV)
+    load = {}
+    for (c, _, _, w) in tiles:
+        load[c] = load.get(c, 0) + w
+    assert len(tiles) == 13 * 23 and max(load.values()) == 1024
